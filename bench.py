@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — HopperRender hot path on B200: interpolated frames/s.
+
+One "step" = one source frame of a 24->60 stream through the hot path:
+    update (pack) -> calculateOpticalFlow -> the 2 or 3 warps the filter's pacing rule asks for
+(vf_HopperRender.c:371-374,481; SURVEY.md Appendix D: 25 outputs per 10 source frames).
+
+  value      interpolated (= delivered, every one is a warp output) frames/s, device-resident:
+             the source frames already sit in HBM (a ring larger than L2), output stays in HBM.
+  e2e        the same metric through the reference-facing call sequence with HOST buffers:
+             updateFrame (H2D) / calculateOpticalFlow / warpFrames / downloadFrame (D2H) per output.
+  roofline   dominant kernel of the step by device time, timed with CUDA events on the launch
+             stream in a separate instrumented pass over the same steps.
+  cpu_baseline   the CPU oracle (C restatement of the reference kernels, OpenMP) on a bounded
+             sample of the same workload, rank 0, N=1 only.
+
+`--impl reference` times the reference's CPU implementation of the path (oracle/_ref when it was
+built, else the oracle port) on the host cores — the only place besides cpu_baseline where
+oracle/ is executed by this file.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, pixfmt, source fps, display fps, mode)
+    "1080p-nv12-24to60": (1920, 1080, 0, 24.0, 60.0, 2),
+    "4k-nv12-24to60": (3840, 2160, 0, 24.0, 60.0, 2),
+    "4k-p010-24to144": (3840, 2160, 1, 24.0, 144.0, 2),
+    "4k-p010-24to144-hsv": (3840, 2160, 1, 24.0, 144.0, 3),
+    "8k-p010-24to60": (7680, 4320, 1, 24.0, 60.0, 2),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p-nv12-24to60", choices=sorted(WORKLOADS))
+    ap.add_argument("--radius", type=int, default=5, help="search radius (config.h MIN_SEARCH_RADIUS = 5 is the default)")
+    ap.add_argument("--cpu-sample-steps", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pacing_ts(n_steps, src_fps, disp_fps):
+    """Blend scalars for n_steps source frames in steady state (the first source frame of a
+    stream produces no warp, so one extra frame primes the pacer)."""
+    import hr_pkg
+
+    hr_pkg.load()
+    from hopperrender_b200 import pacing
+
+    p = pacing.Pacer(src_fps, disp_fps)
+    p.next_source_frame()
+    return [p.next_source_frame() for _ in range(n_steps)]
+
+
+def warp_bytes(w, h, bps, lw, lh):
+    return 3 * int(1.5 * w * h * bps) + 4 * lw * lh
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm on the host cores (oracle/_ref if built, else the oracle)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import hr_oracle_py as O
+    import hr_pkg
+
+    hr_pkg.load()
+    from hopperrender_b200 import synth
+
+    w, h, pixfmt, sfps, dfps, mode = WORKLOADS[args.workload]
+    kind = "port"
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    nfr = 8
+    frames = [clip.frame(k) for k in range(nfr)]
+    o = O.Oracle(h, w, w, pixfmt)
+    o.update_frame(*frames[0])
+    o.update_frame(*frames[1])
+    # keep the whole run within minutes: the CPU does ~0.1 s per 1080p step
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 3))
+    ts = pacing_ts(warm + steps, sfps, dfps)
+
+    def step(i):
+        y, uv = frames[(i + 2) % nfr]
+        o.update_frame(y, uv)
+        o.calc_flow(args.radius, 8, 6)
+        for t in ts[i]:
+            o.warp(np.float32(t), mode)
+            o.download()
+        return len(ts[i])
+
+    for i in range(warm):
+        step(i)
+    t0 = time.perf_counter()
+    outs = sum(step(warm + i) for i in range(steps))
+    dt = time.perf_counter() - t0
+    val = outs / dt
+    line = {
+        "impl": "reference", "metric": "interpolated frames/s", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8" if pixfmt == 0 else "u16", "data": "synthetic",
+        "config": {"workload": args.workload, "search_radius": args.radius, "mode": mode, "device": "host cpu"},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": O.num_threads(), "kind": kind,
+                         "sample": "%d source frames (%d outputs) of %s; C restatement of the reference kernels, OpenMP — no OpenCL runtime in the image" % (steps, outs, args.workload)},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import hr_pkg
+
+    hr = hr_pkg.load()
+    from hopperrender_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w, h, pixfmt, sfps, dfps, mode = WORKLOADS[args.workload]
+    bps = 2 if pixfmt else 1
+    tdtype = torch.uint16 if pixfmt else torch.uint8
+    frame_bytes = int(1.5 * w * h * bps)
+    # ring of source frames larger than L2, so every step reads its inputs from HBM
+    nring = max(8, (2 * L2_BYTES) // frame_bytes + 2)
+    nring = min(nring, 96)
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    base = [clip.frame(k) for k in range(8)]
+    stream = torch.cuda.Stream()
+    g = hr.HrCuda(h, w, w, pixfmt, device=local)
+    g.set_stream(stream.cuda_stream)
+    lw, lh = g.info.lowWidth, g.info.lowHeight
+    with torch.cuda.stream(stream):
+        ring = []
+        for k in range(nring):
+            y, uv = base[k % 8]
+            # a different roll per slot keeps slots distinct without regenerating textures
+            ring.append((torch.from_numpy(np.ascontiguousarray(y)).to("cuda", non_blocking=False).view(tdtype),
+                         torch.from_numpy(np.ascontiguousarray(uv)).to("cuda", non_blocking=False).view(tdtype)))
+        out_ring = [(torch.empty((h, w), dtype=tdtype, device="cuda"), torch.empty((h // 2, w), dtype=tdtype, device="cuda")) for _ in range(max(4, (L2_BYTES // frame_bytes) + 2))]
+    stream.synchronize()
+    K, W_ = args.steps, max(3, args.warmup)
+    ts = pacing_ts(W_ + K, sfps, dfps)
+    radius = args.radius
+
+    oi = [0]
+
+    def step_device(i):
+        y, uv = ring[i % nring]
+        g.update_frame_device(y, uv, borrow=True)
+        g.calc_flow(radius, 8, 6, blocking=False)
+        for t in ts[i]:
+            oy, ouv = out_ring[oi[0] % len(out_ring)]
+            oi[0] += 1
+            g.set_output_device(oy, ouv)
+            g.warp(t, mode)
+        return len(ts[i])
+
+    def barrier():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    # ---- device-resident timed region ---------------------------------------------------------
+    with torch.cuda.stream(stream):
+        g.update_frame_device(*ring[nring - 1], borrow=True)
+        for i in range(W_):
+            step_device(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = g.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        outs = 0
+        for i in range(K):
+            outs += step_device(W_ + i)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        launches = g.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+
+    # ---- instrumented pass: per-kernel device time over the same steps ---------------------------
+    with torch.cuda.stream(stream):
+        ev = {"pack": [], "search": [], "warp": []}
+
+        def timed(kind, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            ev[kind].append((a, b))
+
+        nk = min(K, 100)
+        for i in range(nk):
+            y, uv = ring[(W_ + i) % nring]
+            timed("pack", lambda: g.update_frame_device(y, uv, borrow=True))
+            timed("search", lambda: g.calc_flow(radius, 8, 6, blocking=False))
+            for t in ts[W_ + i]:
+                oy, ouv = out_ring[oi[0] % len(out_ring)]
+                oi[0] += 1
+                g.set_output_device(oy, ouv)
+                timed("warp", lambda: g.warp(t, mode))
+        barrier()
+        kms = {k: [a.elapsed_time(b) for a, b in v] for k, v in ev.items()}
+    g.set_output_device(None, None)
+
+    # ---- end-to-end through the reference-facing interface, host buffers -------------------------
+    e2e = None
+    if not args.no_e2e:
+        ofc = hr.OpticalFlowCalc()
+        if hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt, device=local):
+            raise SystemExit("initOpticalFlowCalc failed")
+        ofc.opticalFlowSearchRadius = radius
+        npdt = np.uint16 if pixfmt else np.uint8
+        hring = []
+        for k in range(8):
+            y, uv = base[k]
+            ty = torch.from_numpy(np.ascontiguousarray(y)).pin_memory()
+            tuv = torch.from_numpy(np.ascontiguousarray(uv)).pin_memory()
+            hring.append((ty, tuv))
+        hout = (torch.empty((h, w), dtype=tdtype).pin_memory(), torch.empty((h // 2, w), dtype=tdtype).pin_memory())
+        Ke = min(K, 100)
+        We = min(W_, 5)
+
+        def step_host(i):
+            ty, tuv = hring[i % 8]
+            assert not hr.updateFrame(ofc, [ty, tuv])
+            assert not hr.calculateOpticalFlow(ofc)
+            for t in ts[i]:
+                assert not hr.warpFrames(ofc, t, mode)
+                assert not hr.downloadFrame(ofc, [hout[0], hout[1]])
+            return len(ts[i])
+
+        hr.updateFrame(ofc, [hring[7][0], hring[7][1]])
+        for i in range(We):
+            step_host(i)
+        barrier()
+        t0 = time.perf_counter()
+        eouts = sum(step_host(We + i) for i in range(Ke))
+        torch.cuda.synchronize()
+        edt = time.perf_counter() - t0
+        e2e = (eouts, edt, Ke)
+        hr.freeOFC(ofc)
+        del npdt
+
+    # ---- reduce over ranks -----------------------------------------------------------------------
+    tot_outs, max_ms = outs, ms
+    e_outs, e_dt = (e2e[0], e2e[1]) if e2e else (0, 1.0)
+    if dist:
+        t = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([outs, e_outs, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        max_ms, e_dt = float(t[0]), float(t[1])
+        tot_outs, e_outs, launches = int(c[0]), int(c[1]), int(c[2])
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        avg = {k: float(np.mean(v)) if v else 0.0 for k, v in kms.items()}            # ms per launch
+        per_step = {"pack": avg["pack"], "search": avg["search"], "warp": avg["warp"] * (len(kms["warp"]) / max(1, len(kms["search"])))}
+        dom = max(per_step, key=per_step.get)
+        wbytes = warp_bytes(w, h, bps, lw, lh)
+        # algorithmic bytes per launch
+        alg = {
+            "warp": wbytes,
+            "pack": int(1.5 * w * h * bps) + 4 * w * h,
+            "search": 4 * lw * lh + int(1.5 * w * h) + 4 * lw * lh,   # frame2 lattice words + reachable frame1 (<= 1 frame of packed samples' worth) + flow out
+        }
+        roof = {}
+        for k in ("pack", "search", "warp"):
+            if avg[k] > 0:
+                ach = alg[k] / (avg[k] * 1e-3) / 1e9
+                roof[k] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                           "traffic": None, "avg_us": avg[k] * 1e3, "share_of_step": per_step[k] / max(1e-12, sum(per_step.values())),
+                           "algorithmic_bytes": alg[k], "peak_source": pk_src}
+        evals = 2 * g.info.iterations * radius * lw * lh
+        if avg["search"] > 0:
+            roof["search"]["candidate_evals_per_s"] = evals / (avg["search"] * 1e-3)
+            roof["search"]["note"] = "latency/ALU bound (16 dependent steps, grid barriers): HBM fraction is not the limiter, see DESIGN.md"
+        line = {
+            "metric": "interpolated frames/s", "value": tot_outs / (max_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W_, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8" if pixfmt == 0 else "u16", "data": "synthetic",
+            "config": {"workload": args.workload, "frame": "%dx%d" % (w, h), "search_radius": radius, "mode": mode,
+                       "streams_per_gpu": 1, "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (nring, nring * frame_bytes >> 20),
+                       "flow_ms_per_pair": avg["search"], "interp_only_frames_per_s": None},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof.get(dom),
+            "kernels": roof,
+            "dominant_kernel": dom,
+        }
+        if e2e:
+            line["e2e"] = {"value": e_outs / e_dt, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
+                           "d2h_bytes_per_step": int(frame_bytes * (e2e[0] / e2e[2])), "steps": e2e[2],
+                           "api": "initOpticalFlowCalc/updateFrame/calculateOpticalFlow/warpFrames/downloadFrame, pinned host planes, blocking like the reference"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    from oracle import hr_oracle_py as O
+    import hr_pkg
+
+    hr_pkg.load()
+    from hopperrender_b200 import synth
+
+    w, h, pixfmt, sfps, dfps, mode = WORKLOADS[args.workload]
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    frames = [clip.frame(k) for k in range(8)]
+    o = O.Oracle(h, w, w, pixfmt)
+    o.update_frame(*frames[0])
+    o.update_frame(*frames[1])
+    n = args.cpu_sample_steps
+    ts = pacing_ts(n + 1, sfps, dfps)
+    outs = 0
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n):
+        o.update_frame(*frames[(i + 2) % 8])
+        o.calc_flow(args.radius, 8, 6)
+        for t in ts[i]:
+            o.warp(np.float32(t), mode)
+            o.download()
+            outs += 1
+        done += 1
+        if time.perf_counter() - t0 > 30.0:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": outs / dt, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d source frames (%d outputs) of %s in %.1f s; C restatement of the reference kernels, OpenMP — no OpenCL runtime (PoCL) in the image" % (done, outs, args.workload, dt)}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

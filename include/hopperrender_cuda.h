@@ -1,0 +1,142 @@
+/*
+ * hopperrender_cuda.h — C ABI of libhopperrender_cuda.so, the B200 (sm_100a) replacement
+ * for the OpenCL layer under HopperRender's optical-flow-calc interface.
+ *
+ * Plain C, plain pointers and sizes. No OpenCL, no torch, no C++ types. Every function
+ * returns 0 on success and non-zero on failure (the reference's convention:
+ * video/filter/HopperRender/opticalFlowCalc.c:11-15 `CHECK_ERROR` -> return 1);
+ * hr_last_error() gives the text that the reference would have printed to stderr.
+ *
+ * Each entry point names the reference interface it replaces. "HR/" abbreviates
+ * /root/reference/video/filter/HopperRender/.
+ *
+ * Threading: like the reference (one in-order queue, HR/opticalFlowCalc.c:389-390, all
+ * calls from the thread that runs the filter graph, filters/filter_internal.h:123-124)
+ * a context is driven from one thread at a time.
+ */
+#ifndef HOPPERRENDER_CUDA_H
+#define HOPPERRENDER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HR_ABI_VERSION 1
+
+/* Pixel formats. NV12 is what the reference negotiates (HR/vf_HopperRender.c:668).
+ * P010 (16-bit little-endian, 10 significant bits MSB-aligned, video/img_format.h:237)
+ * has no reference implementation; its semantics are defined in DESIGN.md §P010. */
+#define HR_PIXFMT_NV12 0
+#define HR_PIXFMT_P010 1
+
+/* Frame output modes = enum FrameOutput, HR/vf_HopperRender.c:21 */
+#define HR_MODE_WARPED_12 0
+#define HR_MODE_WARPED_21 1
+#define HR_MODE_BLENDED 2
+#define HR_MODE_HSV_FLOW 3
+#define HR_MODE_GREY_FLOW 4
+#define HR_MODE_SIDE_BY_SIDE_1 5
+#define HR_MODE_SIDE_BY_SIDE_2 6
+
+/* Limits of this implementation (the reference build uses 5..16, HR/config.h:6-7). */
+#define HR_MIN_SEARCH_RADIUS 2
+#define HR_MAX_SEARCH_RADIUS 32
+
+typedef struct HrContext HrContext; /* opaque; replaces the cl_* members of struct OpticalFlowCalc, HR/opticalFlowCalc.h:30-64 */
+
+typedef struct HrInfo {
+    int abiVersion;
+    int device;            /* CUDA device ordinal                                   */
+    int frameHeight;       /* HR/opticalFlowCalc.h:14                                */
+    int frameWidth;        /* stride in samples, HR/opticalFlowCalc.h:13             */
+    int actualWidth;       /* HR/opticalFlowCalc.h:15                                */
+    int pixfmt;
+    int resScalar;         /* opticalFlowResScalar, HR/opticalFlowCalc.c:331-334     */
+    int lowWidth;          /* opticalFlowFrameWidth, HR/opticalFlowCalc.c:335        */
+    int lowHeight;         /* opticalFlowFrameHeight, HR/opticalFlowCalc.c:336       */
+    int firstWindow;       /* HR/opticalFlowCalc.c:133-143                           */
+    int iterations;        /* HR/opticalFlowCalc.c:146-149                           */
+    int searchCtas;        /* CTAs of the persistent search kernel                   */
+    int smCount;
+    size_t frameBytes;     /* 1.5 * H * stride * bytesPerSample                      */
+    size_t deviceBytes;    /* total HBM held by the context                          */
+} HrInfo;
+
+/* ---- lifetime: replaces initOpticalFlowCalc / freeOFC, HR/opticalFlowCalc.c:323-442, :236-253.
+ * device < 0 selects the current CUDA device. No JIT: kernels are embedded for sm_100a. */
+int hr_create(HrContext **out, int frameHeight, int frameWidth /*stride, samples*/, int actualWidth, int pixfmt, int device);
+int hr_destroy(HrContext *ctx);
+int hr_get_info(const HrContext *ctx, HrInfo *info);
+const char *hr_last_error(const HrContext *ctx); /* ctx may be NULL: error of the last failed hr_create */
+
+/* All work of a context is enqueued on one stream (the reference's single in-order queue).
+ * Pass a cudaStream_t to share the caller's stream (NULL restores the context's own). */
+int hr_set_stream(HrContext *ctx, void *cudaStream);
+int hr_synchronize(HrContext *ctx);
+
+/* ---- updateFrame, HR/opticalFlowCalc.c:96-107: blocking upload of the Y plane
+ * (frameHeight*stride samples) and the interleaved UV plane (frameHeight/2*stride samples) from
+ * HOST memory into the older frame slot, then swap, so that slot 1 is the newest frame. Also
+ * builds the search's phase-planar packed copy of the frame. */
+int hr_update_frame(HrContext *ctx, const void *yPlane, const void *uvPlane);
+
+/* Same, for a frame already in device memory (NVDEC / IMGFMT_CUDA input).
+ * borrow = 0: the planes are copied device-to-device into the context's slot.
+ * borrow = 1: no copy; the caller keeps both planes valid and unchanged until two further
+ *             hr_update_frame* calls have been made. Enqueue-only (does not block). */
+int hr_update_frame_device(HrContext *ctx, const void *dYPlane, const void *dUvPlane, int borrow);
+
+/* ---- calculateOpticalFlow, HR/opticalFlowCalc.c:126-203 (K1-K4: delta-sum search over
+ * `searchRadius` candidate layers, lowest-layer selection, offset update, 8x8 flow blur).
+ * searchRadius / deltaScalar / neighborBiasScalar are the struct fields the reference re-binds
+ * on every call (HR/opticalFlowCalc.c:130,166-170). If `seconds` is non-NULL the call blocks
+ * and stores the device time from the last hr_update_frame* to the end of the blur
+ * (= ofcCalcTime, HR/opticalFlowCalc.c:196-201); if NULL it only enqueues. */
+int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, double *seconds);
+
+/* ---- warpFrames, HR/opticalFlowCalc.c:205-234 (K5: flip lookup + bidirectional warp + blend +
+ * output levels + output modes, luma and chroma in one launch). Fails for t > 1 (:209-212).
+ * black/white are outputBlackLevel/outputWhiteLevel (HR/opticalFlowCalc.c:225-226). Enqueue-only. */
+int hr_warp(HrContext *ctx, float blendingScalar, int frameOutputMode, float blackLevel, float whiteLevel);
+
+/* ---- downloadFrame, HR/opticalFlowCalc.c:109-124: blocking copy of the output frame to HOST
+ * planes; `seconds` (may be NULL) receives warp-start -> download-end (= warpCalcTime). */
+int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds);
+
+/* Device-side view of the output frame (zero-copy hand-off to a CUDA VO; N2). Valid until the
+ * next hr_warp on this context; ordered on the context's stream. */
+int hr_get_output_device(HrContext *ctx, void **dYPlane, void **dUvPlane);
+/* Redirect the output of subsequent hr_warp calls into caller-owned device planes
+ * (NULL, NULL restores the internal buffer). */
+int hr_set_output_device(HrContext *ctx, void *dYPlane, void *dUvPlane);
+
+/* ---- parity taps (tests only; nothing on the playback path calls them). Blocking.
+ * raw / blurred: int16 [2][lowHeight][lowWidth], X plane then Y plane = offsetArray /
+ * blurredOffsetArray (HR/opticalFlowCalc.c:397-398). Either pointer may be NULL. */
+int hr_get_offsets(HrContext *ctx, int16_t *raw, int16_t *blurred);
+int hr_set_blurred_offsets(HrContext *ctx, const int16_t *blurred);
+/* Optional blur-only entry: north-star's "blur flow" step on caller data (K4 alone). */
+int hr_blur_flow(HrContext *ctx, const int16_t *rawHost, int16_t *blurredHost);
+/* Winning layer of every lattice point's window after search step `step` (0 .. 2*iterations-1):
+ * uint8 [lowHeight][lowWidth] (= lowestLayerArray at the window representatives,
+ * HR/Kernels/determineLowestLayerKernel.cl:10-20). Needs hr_set_trace(ctx, 1) before the flow. */
+int hr_set_trace(HrContext *ctx, int enable);
+int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers);
+
+/* Record CUDA events around every kernel launch (off by default; adds two event records per launch). */
+int hr_set_profiling(HrContext *ctx, int enable);
+/* Device time of the most recent search-kernel / warp-kernel / pack-kernel launch, seconds,
+ * measured with CUDA events on the context's stream. Blocking. Any pointer may be NULL. */
+int hr_get_kernel_times(HrContext *ctx, double *searchSeconds, double *warpSeconds, double *packSeconds);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+uint64_t hr_get_launch_count(const HrContext *ctx);
+
+int hr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPPERRENDER_CUDA_H */

@@ -1,0 +1,305 @@
+"""hopperrender_b200 — B200-native HopperRender hot path (package dir `mpv-frame-interpolator_b200/`).
+
+Python here is plumbing only: ctypes bindings of the C ABI (`include/hopperrender_cuda.h`)
+and a mirror of the reference's optical-flow-calc interface
+(`video/filter/HopperRender/opticalFlowCalc.h:77-124`) with the same names, argument meaning
+and inverted-bool error convention, so tests read like calls from `vf_HopperRender.c`.
+
+There is NO CPU fallback: if the CUDA library is missing or no GPU is present every compute
+entry point raises / reports failure.
+"""
+import ctypes as C
+import os
+import pathlib
+
+import numpy as np
+
+from . import build as _build
+
+PKG = pathlib.Path(__file__).resolve().parent
+ROOT = PKG.parent
+
+PIXFMT_NV12 = 0
+PIXFMT_P010 = 1
+
+# enum FrameOutput, video/filter/HopperRender/vf_HopperRender.c:21
+WarpedFrame12, WarpedFrame21, BlendedFrame, HSVFlow, GreyFlow, SideBySide1, SideBySide2 = range(7)
+
+# video/filter/HopperRender/config.h
+MAX_CALC_RES = 270
+MIN_SEARCH_RADIUS = 5
+MAX_SEARCH_RADIUS = 16
+
+
+class HrInfo(C.Structure):
+    _fields_ = [
+        ("abiVersion", C.c_int), ("device", C.c_int), ("frameHeight", C.c_int), ("frameWidth", C.c_int),
+        ("actualWidth", C.c_int), ("pixfmt", C.c_int), ("resScalar", C.c_int), ("lowWidth", C.c_int),
+        ("lowHeight", C.c_int), ("firstWindow", C.c_int), ("iterations", C.c_int), ("searchCtas", C.c_int),
+        ("smCount", C.c_int), ("frameBytes", C.c_size_t), ("deviceBytes", C.c_size_t),
+    ]
+
+
+# name -> (restype, argtypes); also the list tests check against include/hopperrender_cuda.h
+ABI = {
+    "hr_abi_version": (C.c_int, []),
+    "hr_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hr_destroy": (C.c_int, [C.c_void_p]),
+    "hr_get_info": (C.c_int, [C.c_void_p, C.POINTER(HrInfo)]),
+    "hr_last_error": (C.c_char_p, [C.c_void_p]),
+    "hr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hr_synchronize": (C.c_int, [C.c_void_p]),
+    "hr_update_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_update_frame_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hr_calc_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "hr_warp": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]),
+    "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_get_offsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_set_blurred_offsets": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hr_blur_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hr_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hr_get_launch_count": (C.c_uint64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def cuda_library_path() -> pathlib.Path:
+    return _build.CUDA_LIB
+
+
+def load_library(build_if_missing=True):
+    """dlopen libhopperrender_cuda.so (in-tree). Raises if it cannot be built/loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = cuda_library_path()
+    if not path.exists():
+        if not build_if_missing:
+            raise RuntimeError("libhopperrender_cuda.so is not built (run __graft_entry__.build())")
+        _build.build_cuda()
+    lib = C.CDLL(str(path))
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError here = ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class HrError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    """Host pointer of a numpy array / int address / torch tensor (data_ptr)."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("plane must be C-contiguous")
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+class HrCuda:
+    """Thin object wrapper over the C ABI (one HrContext)."""
+
+    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=PIXFMT_NV12, device=-1):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        aw = frameWidth if actualWidth is None else actualWidth
+        if self.lib.hr_create(C.byref(self.h), frameHeight, frameWidth, aw, pixfmt, device):
+            raise HrError(self.lib.hr_last_error(None).decode())
+        self.info = HrInfo()
+        self.lib.hr_get_info(self.h, C.byref(self.info))
+        self.pixfmt = pixfmt
+        self.dtype = np.uint16 if pixfmt == PIXFMT_P010 else np.uint8
+
+    def close(self):
+        if self.h:
+            self.lib.hr_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise HrError(self.lib.hr_last_error(self.h).decode())
+
+    def last_error(self):
+        return self.lib.hr_last_error(self.h).decode()
+
+    def set_stream(self, stream_handle):
+        self._chk(self.lib.hr_set_stream(self.h, C.c_void_p(stream_handle) if stream_handle else None))
+
+    def synchronize(self):
+        self._chk(self.lib.hr_synchronize(self.h))
+
+    def update_frame(self, y, uv):
+        self._chk(self.lib.hr_update_frame(self.h, _ptr(y), _ptr(uv)))
+
+    def update_frame_device(self, dy, duv, borrow=False):
+        self._chk(self.lib.hr_update_frame_device(self.h, _ptr(dy), _ptr(duv), 1 if borrow else 0))
+
+    def calc_flow(self, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6, blocking=True):
+        sec = C.c_double(0.0)
+        self._chk(self.lib.hr_calc_flow(self.h, radius, deltaScalar, neighborBiasScalar, C.byref(sec) if blocking else None))
+        return sec.value
+
+    def warp(self, t, mode=BlendedFrame, black=0.0, white=255.0):
+        self._chk(self.lib.hr_warp(self.h, float(t), int(mode), float(black), float(white)))
+
+    def download(self, y=None, uv=None):
+        H, W = self.info.frameHeight, self.info.frameWidth
+        if y is None:
+            y = np.empty((H, W), self.dtype)
+        if uv is None:
+            uv = np.empty((H // 2, W), self.dtype)
+        sec = C.c_double(0.0)
+        self._chk(self.lib.hr_download(self.h, _ptr(y), _ptr(uv), C.byref(sec)))
+        return y, uv, sec.value
+
+    def output_device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._chk(self.lib.hr_get_output_device(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_output_device(self, dy, duv):
+        self._chk(self.lib.hr_set_output_device(self.h, _ptr(dy), _ptr(duv)))
+
+    def get_offsets(self):
+        n = (2, self.info.lowHeight, self.info.lowWidth)
+        raw, blurred = np.empty(n, np.int16), np.empty(n, np.int16)
+        self._chk(self.lib.hr_get_offsets(self.h, _ptr(raw), _ptr(blurred)))
+        return raw, blurred
+
+    def set_blurred_offsets(self, blurred):
+        b = np.ascontiguousarray(blurred, np.int16)
+        assert b.shape == (2, self.info.lowHeight, self.info.lowWidth)
+        self._chk(self.lib.hr_set_blurred_offsets(self.h, _ptr(b)))
+
+    def blur_flow(self, raw):
+        r = np.ascontiguousarray(raw, np.int16)
+        assert r.shape == (2, self.info.lowHeight, self.info.lowWidth)
+        out = np.empty_like(r)
+        self._chk(self.lib.hr_blur_flow(self.h, _ptr(r), _ptr(out)))
+        return out
+
+    def set_trace(self, on=True):
+        self._chk(self.lib.hr_set_trace(self.h, 1 if on else 0))
+
+    def get_step_layers(self, step):
+        out = np.empty((self.info.lowHeight, self.info.lowWidth), np.uint8)
+        self._chk(self.lib.hr_get_step_layers(self.h, step, _ptr(out)))
+        return out
+
+    def set_profiling(self, on=True):
+        self._chk(self.lib.hr_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self.lib.hr_get_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"search": a.value, "warp": b.value, "pack": c.value}
+
+    def launch_count(self):
+        return int(self.lib.hr_get_launch_count(self.h))
+
+
+class OpticalFlowCalc:
+    """Mirror of `struct OpticalFlowCalc` (video/filter/HopperRender/opticalFlowCalc.h:10-65):
+    the fields the filter reads and writes keep their names; the cl_* members are replaced by
+    one opaque handle."""
+
+    def __init__(self):
+        self.isInitialized = False
+        self.frameWidth = 0
+        self.frameHeight = 0
+        self.actualWidth = 0
+        self.outputBlackLevel = 0.0
+        self.outputWhiteLevel = 255.0
+        self.opticalFlowResScalar = 0
+        self.opticalFlowFrameWidth = 0
+        self.opticalFlowFrameHeight = 0
+        self.opticalFlowSearchRadius = MIN_SEARCH_RADIUS
+        self.ofcCalcTime = 0.0
+        self.warpCalcTime = 0.0
+        self.deltaScalar = 8
+        self.neighborBiasScalar = 6
+        self.pixfmt = PIXFMT_NV12
+        self.impl = None
+
+
+# The six functions of opticalFlowCalc.h:77-124. Return value: False (0) = success,
+# True (1) = failure — the reference's inverted bool (opticalFlowCalc.c:11-15).
+
+def initOpticalFlowCalc(ofc: OpticalFlowCalc, frameHeight: int, frameWidth: int, actualWidth: int, pixfmt: int = PIXFMT_NV12, device: int = -1) -> bool:
+    try:
+        impl = HrCuda(frameHeight, frameWidth, actualWidth, pixfmt, device)
+    except (HrError, OSError, RuntimeError) as e:
+        print("[HopperRender] init failed: %s" % e)
+        return True
+    ofc.impl = impl
+    ofc.frameWidth, ofc.frameHeight, ofc.actualWidth = frameWidth, frameHeight, actualWidth
+    ofc.outputBlackLevel, ofc.outputWhiteLevel = 0.0, 255.0      # opticalFlowCalc.c:328-329
+    ofc.opticalFlowSearchRadius = MIN_SEARCH_RADIUS              # :330
+    ofc.opticalFlowResScalar = impl.info.resScalar
+    ofc.opticalFlowFrameWidth = impl.info.lowWidth
+    ofc.opticalFlowFrameHeight = impl.info.lowHeight
+    ofc.ofcCalcTime = ofc.warpCalcTime = 0.0
+    ofc.deltaScalar, ofc.neighborBiasScalar = 8, 6               # :339-340
+    ofc.pixfmt = pixfmt
+    ofc.isInitialized = True
+    return False
+
+
+def freeOFC(ofc: OpticalFlowCalc) -> None:
+    if ofc.impl is not None:
+        ofc.impl.close()
+        ofc.impl = None
+    ofc.isInitialized = False
+
+
+def updateFrame(ofc: OpticalFlowCalc, inputPlanes) -> bool:
+    if not ofc.isInitialized:
+        return True
+    return bool(ofc.impl.lib.hr_update_frame(ofc.impl.h, _ptr(inputPlanes[0]), _ptr(inputPlanes[1])))
+
+
+def downloadFrame(ofc: OpticalFlowCalc, outputPlanes) -> bool:
+    if not ofc.isInitialized:
+        return True
+    sec = C.c_double(0.0)
+    rc = ofc.impl.lib.hr_download(ofc.impl.h, _ptr(outputPlanes[0]), _ptr(outputPlanes[1]), C.byref(sec))
+    if not rc:
+        ofc.warpCalcTime = sec.value
+    return bool(rc)
+
+
+def calculateOpticalFlow(ofc: OpticalFlowCalc) -> bool:
+    if not ofc.isInitialized:
+        return True
+    sec = C.c_double(0.0)
+    rc = ofc.impl.lib.hr_calc_flow(ofc.impl.h, ofc.opticalFlowSearchRadius, ofc.deltaScalar, ofc.neighborBiasScalar, C.byref(sec))
+    if not rc:
+        ofc.ofcCalcTime = sec.value
+    return bool(rc)
+
+
+def warpFrames(ofc: OpticalFlowCalc, blendingScalar: float, frameOutputMode: int) -> bool:
+    if not ofc.isInitialized:
+        return True
+    return bool(ofc.impl.lib.hr_warp(ofc.impl.h, float(blendingScalar), int(frameOutputMode), float(ofc.outputBlackLevel), float(ofc.outputWhiteLevel)))

@@ -1,0 +1,626 @@
+/*
+ * hr_cuda.cu — C-ABI host layer of libhopperrender_cuda.so (include/hopperrender_cuda.h).
+ *
+ * Replaces the OpenCL host of the reference (video/filter/HopperRender/opticalFlowCalc.c):
+ * context/buffers (:323-442), upload + swap (:96-107), the 66-command flow loop (:126-203,
+ * here: one cooperative launch), the warp launches (:205-234, here: one launch for luma and
+ * chroma), the download (:109-124). There is no CPU fallback: every entry point fails when CUDA
+ * fails.
+ */
+#include "../../include/hopperrender_cuda.h"
+#include "hr_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAX_CALC_RES 270 /* video/filter/HopperRender/config.h:2 */
+
+struct HrContext {
+    int H, W, aW, pixfmt, bps;
+    int s, lw, lh, first, iters;
+    int device, smCount;
+    int tilesX, tilesY, numTiles, grid;
+    int planePitch, planeSize;
+    size_t frameSamples, frameBytes, packedBytes, deviceBytes;
+
+    cudaStream_t stream, ownStream;
+    uint8_t *frameBuf[2];          /* owned frame slots                                        */
+    const void *fy[2], *fuv[2];    /* [0] previous (frame1 / sourceFrame12), [1] newest         */
+    int fslot[2];                  /* which owned slot each of them uses (-1: borrowed)         */
+    uint32_t *packed[2];           /* packed copies, same order                                 */
+    uint8_t *outBuf;
+    void *outY, *outUV;            /* current output planes (internal or caller's)              */
+    int16_t *off, *blur;
+    uint32_t *T;
+    int tOff[HR_MAX_LEVELS];
+    int tWords;
+    uint32_t *bigSums;
+    int bigOff[2 * HR_MAX_LEVELS];
+    int bigWords;
+    unsigned long long *bar;
+    unsigned long long barBase;
+    int barriersPerLaunch;
+    uint8_t *trace;
+    int traceOn;
+    uint8_t *lut;
+    int *lutIdentityDev;
+    int lutIdentity, lutValid;
+    float lutBlack, lutWhite;
+    int useFastWarp;
+
+    cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
+    cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
+    int profiling;
+    int haveSearchT, haveWarpT, havePackT;
+    int framesSeen;
+    uint64_t launches;
+    char err[256];
+};
+
+static char g_createErr[256];
+
+static int fail(HrContext *ctx, const char *fmt, ...) {
+    char *dst = ctx ? ctx->err : g_createErr;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[HopperRender/CUDA] %s\n", dst);
+    return 1;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, "CUDA error in %s: %s (%s)", __func__, cudaGetErrorString(e_), #call); \
+    } while (0)
+
+static int bind_device(HrContext *ctx) {
+    CU(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
+
+extern "C" const char *hr_last_error(const HrContext *ctx) { return ctx ? ctx->err : g_createErr; }
+
+extern "C" uint64_t hr_get_launch_count(const HrContext *ctx) { return ctx ? ctx->launches : 0; }
+
+static void window_schedule(int lw, int lh, int *first, int *iters) {
+    /* opticalFlowCalc.c:133-149 */
+    int windowSize = 1;
+    int maxDim = lw > lh ? lw : lh;
+    if (maxDim && !(maxDim & (maxDim - 1))) {
+        windowSize = maxDim;
+    } else {
+        while (maxDim & (maxDim - 1)) maxDim &= (maxDim - 1);
+        windowSize = maxDim << 1;
+    }
+    windowSize /= 2;
+    int n = 0;
+    for (int w = windowSize; w > 1; w >>= 1) n++;
+    *first = windowSize;
+    *iters = n;
+}
+
+extern "C" int hr_destroy(HrContext *ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->frameBuf[0]);
+    cudaFree(ctx->frameBuf[1]);
+    cudaFree(ctx->packed[0]);
+    cudaFree(ctx->packed[1]);
+    cudaFree(ctx->outBuf);
+    cudaFree(ctx->off);
+    cudaFree(ctx->blur);
+    cudaFree(ctx->T);
+    cudaFree(ctx->bigSums);
+    cudaFree(ctx->bar);
+    cudaFree(ctx->trace);
+    cudaFree(ctx->lut);
+    cudaFree(ctx->lutIdentityDev);
+    if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
+    if (ctx->evFlowEnd) cudaEventDestroy(ctx->evFlowEnd);
+    if (ctx->evWarpStart) cudaEventDestroy(ctx->evWarpStart);
+    if (ctx->evDlEnd) cudaEventDestroy(ctx->evDlEnd);
+    for (int i = 0; i < 6; ++i)
+        if (ctx->evK[i]) cudaEventDestroy(ctx->evK[i]);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    free(ctx);
+    return 0;
+}
+
+static int create_impl(HrContext *ctx) {
+    if (bind_device(ctx)) return 1;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->smCount = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) return fail(ctx, "device %d does not support cooperative launch", ctx->device);
+
+    /* opticalFlowCalc.c:331-336 */
+    ctx->s = 0;
+    while ((ctx->H >> ctx->s) > MAX_CALC_RES) ctx->s++;
+    ctx->lw = (int)ceil(ctx->W / pow(2, ctx->s));
+    ctx->lh = (int)ceil(ctx->H / pow(2, ctx->s));
+    window_schedule(ctx->lw, ctx->lh, &ctx->first, &ctx->iters);
+    if (ctx->iters < 1 || ctx->iters > HR_MAX_LEVELS) return fail(ctx, "unsupported lattice %dx%d", ctx->lw, ctx->lh);
+
+    ctx->tilesX = (ctx->lw + HR_TILE - 1) / HR_TILE;
+    ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
+    ctx->numTiles = ctx->tilesX * ctx->tilesY;
+    int perSm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel, HR_TILE * HR_TILE, 0));
+    if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
+    const int maxResident = perSm * ctx->smCount;
+    ctx->grid = ctx->numTiles < maxResident ? ctx->numTiles : maxResident;
+    if ((ctx->numTiles + ctx->grid - 1) / ctx->grid > HR_MAX_TILES_PER_CTA)
+        return fail(ctx, "lattice %dx%d needs more than %d tiles per CTA", ctx->lw, ctx->lh, HR_MAX_TILES_PER_CTA);
+
+    ctx->planePitch = (ctx->lw + 31) & ~31;
+    ctx->planeSize = ctx->planePitch * ctx->lh;
+    const size_t planes = (size_t)1 << (2 * ctx->s);
+    ctx->packedBytes = planes * (size_t)ctx->planeSize * sizeof(uint32_t);
+    if (planes * (size_t)ctx->planeSize > 0x7fffffffULL) return fail(ctx, "frame too large for the packed layout");
+    ctx->frameSamples = (size_t)ctx->H * ctx->W + (size_t)(ctx->H / 2) * ctx->W;
+    ctx->frameBytes = ctx->frameSamples * ctx->bps;
+
+    /* level tables; 32-word aligned so that levels never share a 128-byte line */
+    int words = 0;
+    for (int it = 0; it < ctx->iters; ++it) {
+        const int ws = ctx->first >> it;
+        const int nwx = (ctx->lw + ws - 1) / ws, nwy = (ctx->lh + ws - 1) / ws;
+        ctx->tOff[it] = words;
+        words += (nwx * nwy + 31) & ~31;
+    }
+    ctx->tWords = words;
+    int bwords = 0, barriers = 0;
+    for (int k = 0; k < 2 * HR_MAX_LEVELS; ++k) ctx->bigOff[k] = -1;
+    for (int it = 0; it < ctx->iters; ++it) {
+        const int ws = ctx->first >> it;
+        if (ws > HR_TILE) {
+            const int nwx = (ctx->lw + ws - 1) / ws, nwy = (ctx->lh + ws - 1) / ws;
+            for (int axis = 0; axis < 2; ++axis) {
+                ctx->bigOff[it * 2 + axis] = bwords;
+                bwords += nwx * nwy * HR_RMAX;
+                barriers++;
+            }
+        }
+        const int nws = ws >> 1;
+        if (it + 1 < ctx->iters && (it + 1) >= HR_FIRST_NEIGHBOR_ITERATION && nws <= HR_TILE) barriers++;
+    }
+    barriers++; /* before the blur */
+    ctx->bigWords = bwords;
+    ctx->barriersPerLaunch = barriers;
+
+    const size_t ln = (size_t)ctx->lw * ctx->lh;
+    CU(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+    ctx->stream = ctx->ownStream;
+    CU(cudaMalloc(&ctx->frameBuf[0], ctx->frameBytes));
+    CU(cudaMalloc(&ctx->frameBuf[1], ctx->frameBytes));
+    CU(cudaMalloc(&ctx->outBuf, ctx->frameBytes));
+    CU(cudaMalloc(&ctx->packed[0], ctx->packedBytes));
+    CU(cudaMalloc(&ctx->packed[1], ctx->packedBytes));
+    CU(cudaMalloc(&ctx->off, 2 * ln * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->T, (size_t)(words ? words : 32) * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->bigSums, (size_t)(bwords ? bwords : 32) * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->bar, 128));
+    CU(cudaMalloc(&ctx->lut, 512));
+    CU(cudaMalloc(&ctx->lutIdentityDev, sizeof(int)));
+    CU(cudaMemset(ctx->frameBuf[0], 0, ctx->frameBytes));
+    CU(cudaMemset(ctx->frameBuf[1], 0, ctx->frameBytes));
+    CU(cudaMemset(ctx->outBuf, 0, ctx->frameBytes));
+    CU(cudaMemset(ctx->packed[0], 0, ctx->packedBytes));
+    CU(cudaMemset(ctx->packed[1], 0, ctx->packedBytes));
+    CU(cudaMemset(ctx->off, 0, 2 * ln * sizeof(int16_t)));
+    CU(cudaMemset(ctx->blur, 0, 2 * ln * sizeof(int16_t)));
+    CU(cudaMemset(ctx->T, 0, (size_t)(words ? words : 32) * sizeof(uint32_t)));
+    CU(cudaMemset(ctx->bigSums, 0, (size_t)(bwords ? bwords : 32) * sizeof(uint32_t)));
+    CU(cudaMemset(ctx->bar, 0, 128));
+    ctx->barBase = 0;
+    ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 4 + 128 + 516;
+    for (int i = 0; i < 2; ++i) {
+        ctx->fy[i] = ctx->frameBuf[i];
+        ctx->fuv[i] = ctx->frameBuf[i] + (size_t)ctx->H * ctx->W * ctx->bps;
+        ctx->fslot[i] = i;
+    }
+    ctx->outY = ctx->outBuf;
+    ctx->outUV = ctx->outBuf + (size_t)ctx->H * ctx->W * ctx->bps;
+    CU(cudaEventCreate(&ctx->evUpdate));
+    CU(cudaEventCreate(&ctx->evFlowEnd));
+    CU(cudaEventCreate(&ctx->evWarpStart));
+    CU(cudaEventCreate(&ctx->evDlEnd));
+    for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ctx->evK[i]));
+    const char *g = getenv("HR_WARP_GENERIC");
+    ctx->useFastWarp = !(g && g[0] == '1');
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int hr_create(HrContext **out, int frameHeight, int frameWidth, int actualWidth, int pixfmt, int device) {
+    if (!out) return fail(NULL, "hr_create: out is NULL");
+    *out = NULL;
+    if (pixfmt != HR_PIXFMT_NV12 && pixfmt != HR_PIXFMT_P010) return fail(NULL, "hr_create: unknown pixel format %d", pixfmt);
+    if (frameHeight < 8 || frameWidth < 8 || actualWidth < 8 || actualWidth > frameWidth || (frameHeight & 1) || (frameWidth & 1))
+        return fail(NULL, "hr_create: unsupported geometry h=%d stride=%d w=%d (need even h/stride >= 8, w <= stride)", frameHeight, frameWidth, actualWidth);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(NULL, "hr_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(NULL, "hr_create: cudaGetDevice failed");
+    if (device >= ndev) return fail(NULL, "hr_create: device %d out of range (%d devices)", device, ndev);
+    HrContext *ctx = (HrContext *)calloc(1, sizeof(HrContext));
+    if (!ctx) return fail(NULL, "hr_create: out of host memory");
+    ctx->H = frameHeight;
+    ctx->W = frameWidth;
+    ctx->aW = actualWidth;
+    ctx->pixfmt = pixfmt;
+    ctx->bps = pixfmt == HR_PIXFMT_P010 ? 2 : 1;
+    ctx->device = device;
+    if (create_impl(ctx)) {
+        snprintf(g_createErr, sizeof(g_createErr), "%s", ctx->err);
+        hr_destroy(ctx);
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int hr_get_info(const HrContext *ctx, HrInfo *info) {
+    if (!ctx || !info) return 1;
+    memset(info, 0, sizeof(*info));
+    info->abiVersion = HR_ABI_VERSION;
+    info->device = ctx->device;
+    info->frameHeight = ctx->H;
+    info->frameWidth = ctx->W;
+    info->actualWidth = ctx->aW;
+    info->pixfmt = ctx->pixfmt;
+    info->resScalar = ctx->s;
+    info->lowWidth = ctx->lw;
+    info->lowHeight = ctx->lh;
+    info->firstWindow = ctx->first;
+    info->iterations = ctx->iters;
+    info->searchCtas = ctx->grid;
+    info->smCount = ctx->smCount;
+    info->frameBytes = ctx->frameBytes;
+    info->deviceBytes = ctx->deviceBytes;
+    return 0;
+}
+
+extern "C" int hr_set_stream(HrContext *ctx, void *cudaStream) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cudaStream ? (cudaStream_t)cudaStream : ctx->ownStream;
+    return 0;
+}
+
+extern "C" int hr_synchronize(HrContext *ctx) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hr_set_trace(HrContext *ctx, int enable) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    if (enable && !ctx->trace) {
+        const size_t n = (size_t)2 * ctx->iters * ctx->lw * ctx->lh;
+        CU(cudaMalloc(&ctx->trace, n));
+        CU(cudaMemset(ctx->trace, 0, n));
+    }
+    ctx->traceOn = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int hr_set_profiling(HrContext *ctx, int enable) {
+    if (!ctx) return 1;
+    ctx->profiling = enable ? 1 : 0;
+    return 0;
+}
+
+/* pack the newest frame (slot 1) into its phase-planar copy */
+static int launch_pack(HrContext *ctx) {
+    const int bx = ctx->s <= 3 ? 128 : 64;
+    dim3 block(bx, 1 << ctx->s);
+    dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[4], ctx->stream));
+    if (ctx->bps == 1)
+        pack_frame_kernel<uint8_t><<<grid, block, 0, ctx->stream>>>((const uint8_t *)ctx->fy[1], (const uint8_t *)ctx->fuv[1], ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+    else
+        pack_frame_kernel<uint16_t><<<grid, block, 0, ctx->stream>>>((const uint16_t *)ctx->fy[1], (const uint16_t *)ctx->fuv[1], ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+    CU(cudaGetLastError());
+    if (ctx->profiling) {
+        CU(cudaEventRecord(ctx->evK[5], ctx->stream));
+        ctx->havePackT = 1;
+    }
+    ctx->launches++;
+    return 0;
+}
+
+/* opticalFlowCalc.c:102-105: the slot that held the previous-previous frame receives the new one */
+static void rotate_slots(HrContext *ctx, int *freeSlot) {
+    /* the owned slot not used by the current newest frame */
+    int used = ctx->fslot[1];
+    *freeSlot = used == 0 ? 1 : 0;
+    ctx->fy[0] = ctx->fy[1];
+    ctx->fuv[0] = ctx->fuv[1];
+    ctx->fslot[0] = ctx->fslot[1];
+    uint32_t *t = ctx->packed[0];
+    ctx->packed[0] = ctx->packed[1];
+    ctx->packed[1] = t;
+}
+
+extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *uvPlane) {
+    if (!ctx) return 1;
+    if (!yPlane || !uvPlane) return fail(ctx, "hr_update_frame: NULL plane");
+    if (bind_device(ctx)) return 1;
+    CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
+    int slot;
+    rotate_slots(ctx, &slot);
+    uint8_t *dst = ctx->frameBuf[slot];
+    const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
+    CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->fy[1] = dst;
+    ctx->fuv[1] = dst + ylen;
+    ctx->fslot[1] = slot;
+    if (launch_pack(ctx)) return 1;
+    ctx->framesSeen++;
+    CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
+    return 0;
+}
+
+extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void *dUV, int borrow) {
+    if (!ctx) return 1;
+    if (!dY || !dUV) return fail(ctx, "hr_update_frame_device: NULL plane");
+    if (bind_device(ctx)) return 1;
+    CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
+    int slot;
+    rotate_slots(ctx, &slot);
+    const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
+    if (borrow) {
+        ctx->fy[1] = dY;
+        ctx->fuv[1] = dUV;
+        ctx->fslot[1] = -1;
+    } else {
+        uint8_t *dst = ctx->frameBuf[slot];
+        CU(cudaMemcpyAsync(dst, dY, ylen, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dst + ylen, dUV, uvlen, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->fy[1] = dst;
+        ctx->fuv[1] = dst + ylen;
+        ctx->fslot[1] = slot;
+    }
+    if (launch_pack(ctx)) return 1;
+    ctx->framesSeen++;
+    return 0;
+}
+
+extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, double *seconds) {
+    if (!ctx) return 1;
+    if (searchRadius < HR_MIN_SEARCH_RADIUS || searchRadius > HR_MAX_SEARCH_RADIUS)
+        return fail(ctx, "hr_calc_flow: search radius %d outside [%d, %d]", searchRadius, HR_MIN_SEARCH_RADIUS, HR_MAX_SEARCH_RADIUS);
+    if (deltaScalar < 0 || deltaScalar > 31 || neighborBiasScalar < 0 || neighborBiasScalar > 31)
+        return fail(ctx, "hr_calc_flow: scalar out of range");
+    if (bind_device(ctx)) return 1;
+    FlowParams P;
+    memset(&P, 0, sizeof(P));
+    P.p1 = ctx->packed[0];
+    P.p2 = ctx->packed[1];
+    P.planePitch = ctx->planePitch;
+    P.planeSize = ctx->planeSize;
+    P.W = ctx->W;
+    P.H = ctx->H;
+    P.s = ctx->s;
+    P.lw = ctx->lw;
+    P.lh = ctx->lh;
+    P.first = ctx->first;
+    P.iters = ctx->iters;
+    P.R = searchRadius;
+    P.dS = deltaScalar;
+    P.nS = neighborBiasScalar;
+    P.tilesX = ctx->tilesX;
+    P.numTiles = ctx->numTiles;
+    P.T = ctx->T;
+    memcpy(P.tOff, ctx->tOff, sizeof(P.tOff));
+    P.bigSums = ctx->bigSums;
+    memcpy(P.bigOff, ctx->bigOff, sizeof(P.bigOff));
+    P.bigWords = ctx->bigWords;
+    P.bar = ctx->bar;
+    P.barBase = ctx->barBase;
+    P.off = ctx->off;
+    P.blur = ctx->blur;
+    P.trace = ctx->traceOn ? ctx->trace : NULL;
+    void *args[] = {&P};
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
+    CU(cudaLaunchCooperativeKernel((const void *)flow_search_kernel, dim3(ctx->grid), dim3(HR_TILE, HR_TILE), args, 0, ctx->stream));
+    if (ctx->profiling) {
+        CU(cudaEventRecord(ctx->evK[1], ctx->stream));
+        ctx->haveSearchT = 1;
+    }
+    ctx->barBase += (unsigned long long)ctx->barriersPerLaunch * ctx->grid;
+    ctx->launches++;
+    CU(cudaEventRecord(ctx->evFlowEnd, ctx->stream));
+    if (seconds) {
+        CU(cudaEventSynchronize(ctx->evFlowEnd));
+        float ms = 0.f;
+        if (ctx->framesSeen > 0) CU(cudaEventElapsedTime(&ms, ctx->evUpdate, ctx->evFlowEnd));
+        *seconds = (double)ms * 1e-3;
+    }
+    return 0;
+}
+
+static int ensure_lut(HrContext *ctx, float black, float white) {
+    if (ctx->lutValid && ctx->lutBlack == black && ctx->lutWhite == white) return 0;
+    levels_lut_kernel<<<1, 256, 0, ctx->stream>>>(ctx->lut, ctx->lutIdentityDev, black, white);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    CU(cudaMemcpyAsync(&ctx->lutIdentity, ctx->lutIdentityDev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->lutBlack = black;
+    ctx->lutWhite = white;
+    ctx->lutValid = 1;
+    return 0;
+}
+
+template <typename T>
+static int launch_warp(HrContext *ctx, float t, int mode, float black, float white) {
+    WarpParams<T> P;
+    P.f1y = (const T *)ctx->fy[0];
+    P.f1uv = (const T *)ctx->fuv[0];
+    P.f2y = (const T *)ctx->fy[1];
+    P.f2uv = (const T *)ctx->fuv[1];
+    P.outY = (T *)ctx->outY;
+    P.outUV = (T *)ctx->outUV;
+    P.flow = ctx->blur;
+    P.lut = ctx->lut;
+    P.lw = ctx->lw;
+    P.lh = ctx->lh;
+    P.H = ctx->H;
+    P.W = ctx->W;
+    P.aW = ctx->aW;
+    P.s = ctx->s;
+    P.mode = mode;
+    P.lutIdentity = ctx->lutIdentity;
+    P.t12 = t;            /* opticalFlowCalc.c:215-216, float */
+    P.t21 = 1.0f - t;
+    P.black = black;
+    P.white = white;
+    const int rows = ctx->H + (ctx->H >> 1);
+    dim3 block(32, 8);
+    dim3 grid((ctx->aW + 127) / 128, (rows + 7) / 8);
+    /* 32-bit accesses of the fast path need 4-byte aligned rows */
+    int fast = ctx->useFastWarp && (ctx->W % 4 == 0) && (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 4 == 0);
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], ctx->stream));
+    warp_blend_kernel<T><<<grid, block, 0, ctx->stream>>>(P, fast);
+    CU(cudaGetLastError());
+    if (ctx->profiling) {
+        CU(cudaEventRecord(ctx->evK[3], ctx->stream));
+        ctx->haveWarpT = 1;
+    }
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float white) {
+    if (!ctx) return 1;
+    if (t > 1.0f) { /* opticalFlowCalc.c:209-212 */
+        printf("Error: Blending scalar is greater than 1.0\n");
+        return fail(ctx, "hr_warp: blending scalar %f is greater than 1.0", (double)t);
+    }
+    if (mode < 0 || mode > 6) return fail(ctx, "hr_warp: unknown output mode %d", mode);
+    if (bind_device(ctx)) return 1;
+    if (ensure_lut(ctx, black, white)) return 1;
+    CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
+    return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, t, mode, black, white) : launch_warp<uint16_t>(ctx, t, mode, black, white);
+}
+
+extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds) {
+    if (!ctx) return 1;
+    if (!yPlane || !uvPlane) return fail(ctx, "hr_download: NULL plane");
+    if (bind_device(ctx)) return 1;
+    const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
+    CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(uvPlane, ctx->outUV, uvlen, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evDlEnd));
+    if (seconds) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
+            cudaGetLastError(); /* no warp was recorded yet */
+            ms = 0.f;
+        }
+        *seconds = (double)ms * 1e-3;
+    }
+    return 0;
+}
+
+extern "C" int hr_get_output_device(HrContext *ctx, void **dY, void **dUV) {
+    if (!ctx) return 1;
+    if (dY) *dY = ctx->outY;
+    if (dUV) *dUV = ctx->outUV;
+    return 0;
+}
+
+extern "C" int hr_set_output_device(HrContext *ctx, void *dY, void *dUV) {
+    if (!ctx) return 1;
+    if ((dY == NULL) != (dUV == NULL)) return fail(ctx, "hr_set_output_device: give both planes or neither");
+    if (dY) {
+        ctx->outY = dY;
+        ctx->outUV = dUV;
+    } else {
+        ctx->outY = ctx->outBuf;
+        ctx->outUV = ctx->outBuf + (size_t)ctx->H * ctx->W * ctx->bps;
+    }
+    return 0;
+}
+
+extern "C" int hr_get_offsets(HrContext *ctx, int16_t *raw, int16_t *blurred) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (raw) CU(cudaMemcpy(raw, ctx->off, n, cudaMemcpyDeviceToHost));
+    if (blurred) CU(cudaMemcpy(blurred, ctx->blur, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int hr_set_blurred_offsets(HrContext *ctx, const int16_t *blurred) {
+    if (!ctx || !blurred) return 1;
+    if (bind_device(ctx)) return 1;
+    const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(ctx->blur, blurred, n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int hr_blur_flow(HrContext *ctx, const int16_t *rawHost, int16_t *blurredHost) {
+    if (!ctx || !rawHost || !blurredHost) return 1;
+    if (bind_device(ctx)) return 1;
+    const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
+    int16_t *dIn = NULL, *dOut = NULL;
+    CU(cudaMalloc(&dIn, n));
+    CU(cudaMalloc(&dOut, n));
+    CU(cudaMemcpyAsync(dIn, rawHost, n, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 block(32, 8), grid((ctx->lw + 31) / 32, (ctx->lh + 7) / 8, 2);
+    blur_flow_kernel<<<grid, block, 0, ctx->stream>>>(dIn, dOut, ctx->lh, ctx->lw);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(blurredHost, dOut, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dIn);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return fail(ctx, "CUDA error in hr_blur_flow: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers) {
+    if (!ctx || !layers) return 1;
+    if (!ctx->trace) return fail(ctx, "hr_get_step_layers: tracing was not enabled");
+    if (step < 0 || step >= 2 * ctx->iters) return fail(ctx, "hr_get_step_layers: step %d out of range", step);
+    if (bind_device(ctx)) return 1;
+    const size_t ln = (size_t)ctx->lw * ctx->lh;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(layers, ctx->trace + (size_t)step * ln, ln, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int hr_get_kernel_times(HrContext *ctx, double *searchSeconds, double *warpSeconds, double *packSeconds) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    double *outs[3] = {searchSeconds, warpSeconds, packSeconds};
+    const int have[3] = {ctx->haveSearchT, ctx->haveWarpT, ctx->havePackT};
+    for (int i = 0; i < 3; ++i) {
+        if (!outs[i]) continue;
+        *outs[i] = 0.0;
+        if (!have[i]) continue;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->evK[2 * i], ctx->evK[2 * i + 1]));
+        *outs[i] = (double)ms * 1e-3;
+    }
+    return 0;
+}

@@ -1,0 +1,49 @@
+/*
+ * opticalFlowCalc.h — drop-in replacement for the reference's
+ * video/filter/HopperRender/opticalFlowCalc.h:1-126.
+ *
+ * Same six functions, same argument meaning, same inverted-bool convention (0/false = success,
+ * 1/true = failure), same public struct fields by name. The OpenCL members (cl_device_id ...
+ * cl_kernel, reference :30-64) are replaced by one opaque handle to the CUDA C-ABI library
+ * (include/hopperrender_cuda.h); <CL/cl.h> is no longer needed.
+ */
+#ifndef OPTICALFLOWCALC_H
+#define OPTICALFLOWCALC_H
+
+#include <stdbool.h>
+
+#include "config.h"
+
+typedef struct OpticalFlowCalc {
+    /* Video properties (reference :12-17) */
+    bool isInitialized;
+    int frameWidth;          /* stride of the frame, in samples */
+    int frameHeight;
+    int actualWidth;         /* width as encoded */
+    float outputBlackLevel;
+    float outputWhiteLevel;
+
+    /* Optical flow calculation (reference :20-27) */
+    int opticalFlowResScalar;
+    int opticalFlowFrameWidth;
+    int opticalFlowFrameHeight;
+    int opticalFlowSearchRadius;
+    double ofcCalcTime;
+    double warpCalcTime;
+    int deltaScalar;
+    int neighborBiasScalar;
+
+    /* CUDA implementation (replaces reference :30-64) */
+    int pixelFormat;         /* 0 = NV12 (what the reference negotiates), 1 = P010; set before init */
+    int cudaDevice;          /* 0 = current device, n = device ordinal n-1; set before init */
+    void *impl;              /* HrContext* */
+} OpticalFlowCalc;
+
+bool initOpticalFlowCalc(struct OpticalFlowCalc *ofc, const int frameHeight, const int frameWidth, const int actualWidth);
+void freeOFC(struct OpticalFlowCalc *ofc);
+bool updateFrame(struct OpticalFlowCalc *ofc, unsigned char **inputPlanes);
+bool downloadFrame(struct OpticalFlowCalc *ofc, unsigned char **outputPlanes);
+bool calculateOpticalFlow(struct OpticalFlowCalc *ofc);
+bool warpFrames(struct OpticalFlowCalc *ofc, const float blendingScalar, const int frameOutputMode);
+
+#endif /* OPTICALFLOWCALC_H */
