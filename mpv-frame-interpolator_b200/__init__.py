@@ -79,6 +79,8 @@ def load_library(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = cuda_library_path()
+    if os.environ.get("HR_CUDA_LIB"):          # kernel-variant experiments (tools/); never a fallback
+        path = pathlib.Path(os.environ["HR_CUDA_LIB"])
     if not path.exists():
         if not build_if_missing:
             raise RuntimeError("libhopperrender_cuda.so is not built (run __graft_entry__.build())")

@@ -50,7 +50,7 @@ def nvcc_path():
 
 
 def build_cuda(force=False, verbose_ptxas=False):
-    srcs = [CSRC / "hr_cuda.cu", CSRC / "hr_kernels.cuh", ROOT / "include" / "hopperrender_cuda.h"]
+    srcs = [CSRC / "hr_cuda.cu", *sorted(CSRC.glob("*.cuh")), ROOT / "include" / "hopperrender_cuda.h"]
     if not force and _newer(CUDA_LIB, srcs):
         return CUDA_LIB
     flags = list(NVCC_FLAGS)

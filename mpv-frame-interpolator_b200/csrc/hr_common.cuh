@@ -1,0 +1,116 @@
+/*
+ * hr_common.cuh — shared declarations of the sm_100a device code of the HopperRender hot path
+ * (hr_pack.cuh, hr_search.cuh, hr_warp.cuh).
+ *
+ * Written from scratch for B200; it is not a translation of the reference's OpenCL kernels
+ * (video/filter/HopperRender/Kernels/*.cl) but computes the same results:
+ *
+ *   pack_frame_kernel      per source frame: NV12/P010 -> phase-planar packed (Y,U,V,0) words, so
+ *                          that every delta-sum evaluation is ONE coalesced 32-bit load and ONE
+ *                          VABSDIFF4.U8.ACC (replaces the three strided byte gathers of
+ *                          calcDeltaSumsKernel.cl:96-98).
+ *   flow_search_kernel     one persistent cooperative launch for all 2*iterations search steps
+ *                          (K1 calcDeltaSumsKernel.cl:34-189 + K2 determineLowestLayerKernel.cl:2-22
+ *                          + K3 adjustOffsetArrayKernel.cl:2-18) and the 8x8 flow blur
+ *                          (K4 blurFlowKernel.cl:15-89); offsets are kept at window granularity.
+ *   warp_blend_kernel      K5 warpFrameKernel.cl:114-182: flip lookup, bidirectional warp, blend,
+ *                          levels, output modes; luma and chroma in one launch, 32-bit stores.
+ *
+ * Compiled with -fmad=false: the warp's float arithmetic must round after every operation (the
+ * reference's expressions evaluated in IEEE single precision without contraction), which is
+ * what the parity tests check bit for bit.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HR_TILE 32                 /* lattice points per tile side (one CTA)                     */
+#define HR_MAX_TILES_PER_CTA 8
+#define HR_MAX_LEVELS 16
+#define HR_ZCHUNK 8                /* candidate layers in flight per thread                       */
+#define HR_RMAX 32                 /* HR_MAX_SEARCH_RADIUS                                       */
+#define HR_FIRST_NEIGHBOR_ITERATION 4 /* calcDeltaSumsKernel.cl:1 */
+
+struct FlowParams {
+    const uint32_t *p1;      /* packed previous frame (frame1): all phase planes                 */
+    const uint32_t *p2;      /* packed newest frame (frame2): only phase plane (0,0) is read      */
+    int planePitch;          /* words per packed plane row                                       */
+    int planeSize;           /* words per packed plane                                           */
+    int W, H, s, lw, lh;
+    int first, iters, R, dS, nS;
+    int cand[HR_RMAX];       /* signed-square layer shifts, calcDeltaSumsKernel.cl:68-72         */
+    int tilesX, numTiles;
+    uint32_t *T;             /* per-level window offset tables, int16x2 (x | y << 16)             */
+    int tOff[HR_MAX_LEVELS]; /* word offset of level `it` in T                                    */
+    uint32_t *bigSums;       /* cross-CTA window sums for windows > tile: [bigStep][win][HR_RMAX] */
+    int bigOff[2 * HR_MAX_LEVELS]; /* word offset of search step k in bigSums (-1: not a big step) */
+    int bigWords;
+    unsigned long long *bar; /* monotonic grid-barrier counter                                   */
+    unsigned long long barBase;
+    int16_t *off;            /* raw offsets  [2][lh][lw]  (offsetArray)                           */
+    int16_t *blur;           /* blurred      [2][lh][lw]  (blurredOffsetArray)                    */
+    uint8_t *trace;          /* optional [steps][lh][lw] winning layer per point, or NULL         */
+};
+
+template <typename T>
+struct WarpParams {
+    const T *f1y, *f1uv;     /* sourceFrame12 = previous frame                                    */
+    const T *f2y, *f2uv;     /* sourceFrame21 = newest frame                                      */
+    T *outY, *outUV;
+    const int16_t *flow;     /* blurred offsets [2][lh][lw]                                       */
+    const uint8_t *lut;      /* [2][256] 8-bit levels LUT (Y then UV)                             */
+    int lw, lh, H, W, aW, s, mode, lutIdentity;
+    float t12, t21, black, white;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* small helpers                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ int hr_min(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int hr_max(int a, int b) { return a > b ? a : b; }
+
+/* calcDeltaSumsKernel.cl:84-93 single reflection, then clamp (the reference leaves |offset| >= dim
+ * undefined; this implementation clamps). */
+__device__ __forceinline__ int search_mirror(int p, int D) {
+    if (p >= D) p = 2 * D - p - 1;
+    else if (p < 0) p = -p - 1;
+    return hr_min(hr_max(p, 0), D - 1);
+}
+/* calcDeltaSumsKernel.cl:68-72: signed square of the relative layer */
+__device__ __forceinline__ int candidate(int z, int R) {
+    const int rel = z - (R >> 1);
+    return rel * (rel < 0 ? -rel : rel);
+}
+__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+/* Grid-wide barrier of the persistent search kernel (all CTAs are co-resident: cooperative
+ * launch). The counter only grows; `target` is carried by every CTA. */
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &target, unsigned nCtas) {
+    __syncthreads();
+    target += nCtas;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        red_release_add_u64(bar, 1ULL);              /* release: orders this CTA's earlier writes (cumulative over bar.sync) */
+        while (ld_relaxed_u64(bar) < target) {
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+

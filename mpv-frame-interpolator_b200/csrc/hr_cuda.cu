@@ -8,7 +8,10 @@
  * fails.
  */
 #include "../../include/hopperrender_cuda.h"
-#include "hr_kernels.cuh"
+#include "hr_common.cuh"
+#include "hr_pack.cuh"
+#include "hr_search.cuh"
+#include "hr_warp.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -153,7 +156,8 @@ static int create_impl(HrContext *ctx) {
     ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
     ctx->numTiles = ctx->tilesX * ctx->tilesY;
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel, HR_TILE * HR_TILE, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel, HR_WARPS * 32, 0));
+    if (perSm > 1) perSm = 1; /* one tile per SM: the search is latency-bound, spread it out */
     if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
     const int maxResident = perSm * ctx->smCount;
     ctx->grid = ctx->numTiles < maxResident ? ctx->numTiles : maxResident;
@@ -422,6 +426,10 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     P.R = searchRadius;
     P.dS = deltaScalar;
     P.nS = neighborBiasScalar;
+    for (int z = 0; z < HR_RMAX; ++z) {
+        const int rel = z - searchRadius / 2;
+        P.cand[z] = z < searchRadius ? rel * abs(rel) : 0;
+    }
     P.tilesX = ctx->tilesX;
     P.numTiles = ctx->numTiles;
     P.T = ctx->T;
@@ -436,7 +444,7 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     P.trace = ctx->traceOn ? ctx->trace : NULL;
     void *args[] = {&P};
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
-    CU(cudaLaunchCooperativeKernel((const void *)flow_search_kernel, dim3(ctx->grid), dim3(HR_TILE, HR_TILE), args, 0, ctx->stream));
+    CU(cudaLaunchCooperativeKernel((const void *)flow_search_kernel, dim3(ctx->grid), dim3(HR_WARPS * 32), args, 0, ctx->stream));
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], ctx->stream));
         ctx->haveSearchT = 1;
