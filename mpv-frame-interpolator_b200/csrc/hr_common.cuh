@@ -25,7 +25,7 @@
 #include <stdint.h>
 
 #define HR_TILE 32                 /* lattice points per tile side (one CTA)                     */
-#define HR_MAX_TILES_PER_CTA 8
+#define HR_MAX_TILES_PER_CTA 4
 #define HR_MAX_LEVELS 16
 #define HR_ZCHUNK 8                /* candidate layers in flight per thread                       */
 #define HR_RMAX 32                 /* HR_MAX_SEARCH_RADIUS                                       */

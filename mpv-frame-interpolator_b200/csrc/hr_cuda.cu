@@ -25,7 +25,7 @@ struct HrContext {
     int H, W, aW, pixfmt, bps;
     int s, lw, lh, first, iters;
     int device, smCount;
-    int tilesX, tilesY, numTiles, grid;
+    int tilesX, tilesY, numTiles, grid, multiTile;
     int planePitch, planeSize;
     size_t frameSamples, frameBytes, packedBytes, deviceBytes;
 
@@ -156,11 +156,12 @@ static int create_impl(HrContext *ctx) {
     ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
     ctx->numTiles = ctx->tilesX * ctx->tilesY;
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel, HR_WARPS * 32, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<true>, HR_THREADS, 0));
     if (perSm > 1) perSm = 1; /* one tile per SM: the search is latency-bound, spread it out */
     if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
     const int maxResident = perSm * ctx->smCount;
     ctx->grid = ctx->numTiles < maxResident ? ctx->numTiles : maxResident;
+    ctx->multiTile = ctx->numTiles > ctx->grid;
     if ((ctx->numTiles + ctx->grid - 1) / ctx->grid > HR_MAX_TILES_PER_CTA)
         return fail(ctx, "lattice %dx%d needs more than %d tiles per CTA", ctx->lw, ctx->lh, HR_MAX_TILES_PER_CTA);
 
@@ -444,7 +445,8 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     P.trace = ctx->traceOn ? ctx->trace : NULL;
     void *args[] = {&P};
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
-    CU(cudaLaunchCooperativeKernel((const void *)flow_search_kernel, dim3(ctx->grid), dim3(HR_WARPS * 32), args, 0, ctx->stream));
+    const void *kfn = ctx->multiTile ? (const void *)flow_search_kernel<true> : (const void *)flow_search_kernel<false>;
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, ctx->stream));
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], ctx->stream));
         ctx->haveSearchT = 1;

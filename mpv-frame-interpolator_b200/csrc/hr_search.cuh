@@ -7,15 +7,18 @@
  * driver loop opticalFlowCalc.c:126-203 (66 queue commands -> 1 launch).
  *
  * Work decomposition (B200: 148 SMs x 4 sub-partitions):
- *   - CTA = 4 warps = one 32x32 tile of the lattice; every WARP owns a fixed 16x16 block, every
- *     thread a column of 8 points in it (lane&15 = column, lane>>4 = upper/lower 8 rows). The
- *     480x270 lattice of every 16:9 format gives 135 CTAs <= 148 SMs.
- *   - Windows <= 16 are warp-local: 8 register adds + <= 5 shuffles per layer, no shared memory,
- *     no block barrier. Offsets live in registers across iterations.
- *   - Window = 32: four warp totals meet in shared memory (one block barrier per step).
- *   - Windows >= 64: CTA totals meet in L2 (red.add) + one grid barrier per step.
+ *   - CTA = 16 warps = one 32x32 tile of the lattice (480x270 -> 135 CTAs <= 148 SMs, one per SM,
+ *     4 warps per sub-partition to hide the L2 latency of the sample loads).
+ *   - warp = one 8x8 block of the tile; thread = two vertically adjacent points of it
+ *     (lane&7 = column, lane>>3 = row pair). Both points always share a window (window >= 2), so a
+ *     thread carries ONE offset pair in registers through all 16 steps.
+ *   - Windows <= 8 are warp-local: xor-butterflies (window 8: one REDUX), every lane of a window
+ *     scores the layers itself. No shared memory, no block barrier.
+ *   - Windows 16 / 32: warp REDUX totals meet in shared memory; one warp per window scores the
+ *     layers (lane = layer). Two block barriers per step.
+ *   - Windows >= 64 span CTAs: tile totals meet in L2 (red.add) + one grid barrier per step.
  *   - Neighbour bias (iteration >= 4) reads the previous level's window table from L2; one grid
- *     barrier per iteration orders it. 11 grid barriers per flow at 480x270.
+ *     barrier per level orders it.
  *   - Every evaluation is one 32-bit load from the phase-planar packed frame (hr_pack.cuh) and one
  *     VABSDIFF4.U8.ACC; both biases are added once per window as count*bias (mod 2^32 — exact,
  *     because every point of a window shares offset and neighbours).
@@ -23,65 +26,19 @@
 #pragma once
 #include "hr_common.cuh"
 
-#define HR_WARPS 4          /* warps per CTA                                  */
-#define HR_BLK 16           /* lattice points per warp-block side             */
-#define HR_PPT 8            /* points per thread                              */
+#define HR_THREADS 512      /* threads per CTA                                 */
+#define HR_NWARPS 16        /* warps per CTA = 8x8 blocks per tile             */
 
 struct SearchShared {
-    uint32_t warpTot[HR_WARPS][HR_RMAX];          /* per-warp block totals, windows >= 32           */
-    int tileOffX[HR_MAX_TILES_PER_CTA], tileOffY[HR_MAX_TILES_PER_CTA];
-    int winner;
+    uint32_t warpTot[HR_NWARPS][HR_RMAX];        /* per-warp block totals, windows >= 16            */
+    int winner[4];                               /* winning layer of the tile's window(s)           */
     union {
-        struct {                                  /* blur phase                                     */
-            int16_t tX[40 * 40], tY[40 * 40];     /* tile + 4-point halo of the raw offsets          */
-            int hX[40 * 32], hY[40 * 32];         /* horizontal 8-tap sums                           */
+        int4 parked[HR_MAX_TILES_PER_CTA][HR_THREADS]; /* MULTI only: per-thread state of each owned tile */
+        struct {                                  /* blur phase                                      */
+            int16_t tX[40 * 40], tY[40 * 40];     /* tile + 4-point halo of the raw offsets           */
+            int hX[40 * 32], hY[40 * 32];         /* horizontal 8-tap sums                            */
         } blur;
     };
-};
-
-/* Window total for layer z (calcDeltaSumsKernel.cl:99-150 summed over the window, mod 2^32). */
-__device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int curAxis, uint32_t count, bool useNb, int nb0, int nb1,
-                                                 int nb2, int nb3, int dS, int nS) {
-    const int own = (int)(int16_t)(curAxis + c);
-    uint32_t bias = (uint32_t)(uint16_t)abs(own);
-    if (useNb) {
-        const uint32_t nb = (uint32_t)(uint16_t)abs(nb0 - own) + (uint32_t)(uint16_t)abs(nb1 - own) +
-                            (uint32_t)(uint16_t)abs(nb2 - own) + (uint32_t)(uint16_t)abs(nb3 - own);
-        bias += nb << nS;
-    }
-    return (sad << dS) + count * bias;
-}
-
-/* The four neighbour offsets of calcDeltaSumsKernel.cl:112-128 for the window whose lattice origin
- * is (x0,y0): positions +-2*ws clamped to the lattice, read from the previous level's table. All
- * points of a window resolve to the same four windows, so one lookup serves the whole window. */
-__device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int ws, int axis, int x0, int y0, int &nb0, int &nb1,
-                                                int &nb2, int &nb3) {
-    const int pws = ws << 1;
-    const int lgp = 31 - __clz(pws);
-    const int pnwx = (P.lw + pws - 1) >> lgp;
-    const uint32_t *Tp = P.T + P.tOff[it - 1];
-    const int yd = hr_min(y0 + pws, P.lh - 1) >> lgp, yu = hr_max(y0 - pws, 0) >> lgp;
-    const int xr = hr_min(x0 + pws, P.lw - 1) >> lgp, xl = hr_max(x0 - pws, 0) >> lgp;
-    const int xc = x0 >> lgp, yc = y0 >> lgp;
-    const uint32_t a = ldcg_u32(Tp + yd * pnwx + xc); /* down  */
-    const uint32_t b = ldcg_u32(Tp + yc * pnwx + xr); /* right */
-    const uint32_t c = ldcg_u32(Tp + yc * pnwx + xl); /* left  */
-    const uint32_t d = ldcg_u32(Tp + yu * pnwx + xc); /* up    */
-    const int sh = axis ? 16 : 0;
-    nb0 = (int)(int16_t)(a >> sh);
-    nb1 = (int)(int16_t)(b >> sh);
-    nb2 = (int)(int16_t)(c >> sh);
-    nb3 = (int)(int16_t)(d >> sh);
-}
-
-/* Per-thread view of its 8 lattice points for one search step. */
-struct PointSet {
-    int fixedIdx[HR_PPT]; /* word index contributed by the axis that does not move this step */
-    int moveBase[HR_PPT]; /* full-resolution coordinate on the searched axis before the layer shift */
-    int mulA, mulB;       /* word index of moving coordinate p = (p & m) * mulA + (p >> s) * mulB     */
-    int D;                /* frame extent along the searched axis                                    */
-    bool interior;        /* warp-uniform: no layer of any point of the warp leaves the frame          */
 };
 
 /* |a-b| over the four packed bytes, summed, plus c: one VABSDIFF4.U8.ACC */
@@ -91,211 +48,105 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
     return d;
 }
 
-/* Set up the PointSet for a step: the fixed axis is mirrored once, the moving axis keeps its base.
- * axis 0: layers move x; axis 1: layers move y. Rows of the thread: yTop .. yTop+7 (clamped). */
-template <bool UNIFORM>
-__device__ __forceinline__ void make_points(const FlowParams &P, int axis, int cx, int yTop, const int (&offX)[HR_PPT],
-                                            const int (&offY)[HR_PPT], int ox, int oy, PointSet &ps) {
-    const int s = P.s, m = (1 << s) - 1;
-    int lo = 0x7fffffff, hi = -0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < HR_PPT; ++k) {
-        const int cyk = hr_min(yTop + k, P.lh - 1);
-        const int oxk = UNIFORM ? ox : offX[k], oyk = UNIFORM ? oy : offY[k];
-        if (axis == 0) {
-            const int y = search_mirror((cyk << s) + oyk, P.H);
-            ps.fixedIdx[k] = ((y & m) << s) * P.planeSize + (y >> s) * P.planePitch;
-            ps.moveBase[k] = (cx << s) + oxk;
-        } else {
-            const int x = search_mirror((cx << s) + oxk, P.W);
-            ps.fixedIdx[k] = (x & m) * P.planeSize + (x >> s);
-            ps.moveBase[k] = (cyk << s) + oyk;
-        }
-        lo = hr_min(lo, ps.moveBase[k]);
-        hi = hr_max(hi, ps.moveBase[k]);
+/* Window total for layer shift c (calcDeltaSumsKernel.cl:99-150 summed over the window, mod 2^32):
+ * (SAD << deltaScalar) + count * (|own| + (sum of the four |neighbour - own|) << neighborBiasScalar),
+ * magnitudes as unsigned 16-bit. nbA / nbB hold two int16 neighbour offsets each. */
+__device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int cur, uint32_t count, bool useNb, uint32_t nbA, uint32_t nbB,
+                                                 int dS, int nS) {
+    const int own = (int)(int16_t)(cur + c);
+    uint32_t bias = (uint32_t)(uint16_t)abs(own);
+    if (useNb) {
+        const uint32_t nb = (uint32_t)(uint16_t)abs((int)(int16_t)nbA - own) + (uint32_t)(uint16_t)abs(((int)nbA >> 16) - own) +
+                            (uint32_t)(uint16_t)abs((int)(int16_t)nbB - own) + (uint32_t)(uint16_t)abs(((int)nbB >> 16) - own);
+        bias += nb << nS;
     }
-    ps.mulA = axis ? (P.planeSize << s) : P.planeSize;
-    ps.mulB = axis ? P.planePitch : 1;
-    ps.D = axis ? P.H : P.W;
-    ps.interior = __all_sync(0xffffffffu, lo + P.cand[0] >= 0 && hi + P.cand[P.R - 1] < ps.D);
+    return (sad << dS) + count * bias;
 }
 
-/* Issue the loads of up to HR_ZCHUNK layers x 8 points before anything consumes them: with one
- * warp per SM sub-partition the memory latency is hidden by instruction-level parallelism only. */
-__device__ __forceinline__ void load_chunk(const FlowParams &P, const PointSet &ps, int z0, int nz, uint32_t (&v1)[HR_ZCHUNK][HR_PPT]) {
+/* The four neighbour windows of calcDeltaSumsKernel.cl:112-128 for the window whose lattice origin
+ * is (x0,y0): positions +-2*ws clamped to the lattice, read from the previous level's table (words
+ * hold x | y << 16). All points of a window resolve to the same four windows, so one lookup serves
+ * the whole window and both axis steps of the level. */
+__device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int ws, int x0, int y0, uint32_t (&nw)[4]) {
+    const int pws = ws << 1;
+    const int lgp = 31 - __clz(pws);
+    const int pnwx = (P.lw + pws - 1) >> lgp;
+    const uint32_t *Tp = P.T + P.tOff[it - 1];
+    const int yd = hr_min(y0 + pws, P.lh - 1) >> lgp, yu = hr_max(y0 - pws, 0) >> lgp;
+    const int xr = hr_min(x0 + pws, P.lw - 1) >> lgp, xl = hr_max(x0 - pws, 0) >> lgp;
+    const int xc = x0 >> lgp, yc = y0 >> lgp;
+    nw[0] = ldcg_u32(Tp + yd * pnwx + xc); /* down  */
+    nw[1] = ldcg_u32(Tp + yc * pnwx + xr); /* right */
+    nw[2] = ldcg_u32(Tp + yc * pnwx + xl); /* left  */
+    nw[3] = ldcg_u32(Tp + yu * pnwx + xc); /* up    */
+}
+/* pick one axis out of the four neighbour words: two int16 per result word */
+__device__ __forceinline__ void neighbour_axis(const uint32_t (&nw)[4], int axis, uint32_t &nbA, uint32_t &nbB) {
+    const uint32_t sel = axis ? 0x7632u : 0x5410u;
+    nbA = __byte_perm(nw[0], nw[1], sel);
+    nbB = __byte_perm(nw[2], nw[3], sel);
+}
+
+/* Per-thread geometry inside a tile */
+struct TileGeom {
+    int tx0, ty0;         /* lattice origin of the tile                                    */
+    int px, py;           /* lattice position of the thread's upper point (clamped)         */
+    uint32_t m0, m1;      /* all-ones if the upper / lower point is inside the lattice      */
+};
+__device__ __forceinline__ TileGeom tile_geom(const FlowParams &P, int tile, int warp, int lane) {
+    TileGeom g;
+    g.tx0 = (tile % P.tilesX) * HR_TILE;
+    g.ty0 = (tile / P.tilesX) * HR_TILE;
+    const int x = g.tx0 + (warp & 3) * 8 + (lane & 7);
+    const int y = g.ty0 + (warp >> 2) * 8 + (lane >> 3) * 2;
+    g.m0 = (x < P.lw && y < P.lh) ? 0xffffffffu : 0u;
+    g.m1 = (x < P.lw && y + 1 < P.lh) ? 0xffffffffu : 0u;
+    g.px = x;
+    g.py = y;
+    return g;
+}
+
+/* SAD of the thread's two points for layers z0 .. z0+nz-1 of one search step.
+ * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s. */
+__device__ __forceinline__ void eval_chunk(const FlowParams &P, int axis, const TileGeom &g, int ox, int oy, uint32_t v2a, uint32_t v2b, int z0, int nz,
+                                           uint32_t (&acc)[HR_ZCHUNK]) {
     const int s = P.s, m = (1 << s) - 1;
-    if (ps.interior) {
+    const int cx = hr_min(g.px, P.lw - 1), cy0 = hr_min(g.py, P.lh - 1), cy1 = hr_min(g.py + 1, P.lh - 1);
+    uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
+    if (axis == 0) {
+        /* layers move x: the two rows are fixed, both points share the moving column */
+        const int ya = search_mirror((cy0 << s) + oy, P.H), yb = search_mirror((cy1 << s) + oy, P.H);
+        const uint32_t *ra = P.p1 + (((ya & m) << s) * P.planeSize + (ya >> s) * P.planePitch);
+        const uint32_t *rb = P.p1 + (((yb & m) << s) * P.planeSize + (yb >> s) * P.planePitch);
+        const int base = (cx << s) + ox;
 #pragma unroll
         for (int j = 0; j < HR_ZCHUNK; ++j) {
             if (j < nz) {
-                const int c = P.cand[z0 + j];
-#pragma unroll
-                for (int k = 0; k < HR_PPT; ++k) {
-                    const int p = ps.moveBase[k] + c;
-                    v1[j][k] = __ldg(P.p1 + (ps.fixedIdx[k] + (p & m) * ps.mulA + (p >> s) * ps.mulB));
-                }
+                const int x = search_mirror(base + P.cand[z0 + j], P.W);
+                const int xi = (x & m) * P.planeSize + (x >> s);
+                va[j] = __ldg(ra + xi);
+                vb[j] = __ldg(rb + xi);
             }
         }
     } else {
+        /* layers move y: the column is fixed */
+        const int x = search_mirror((cx << s) + ox, P.W);
+        const uint32_t *col = P.p1 + ((x & m) * P.planeSize + (x >> s));
+        const int ba = (cy0 << s) + oy, bb = (cy1 << s) + oy;
+        const int mulA = P.planeSize << s;
 #pragma unroll
         for (int j = 0; j < HR_ZCHUNK; ++j) {
             if (j < nz) {
                 const int c = P.cand[z0 + j];
-#pragma unroll
-                for (int k = 0; k < HR_PPT; ++k) {
-                    const int p = search_mirror(ps.moveBase[k] + c, ps.D);
-                    v1[j][k] = __ldg(P.p1 + (ps.fixedIdx[k] + (p & m) * ps.mulA + (p >> s) * ps.mulB));
-                }
+                const int ya = search_mirror(ba + c, P.H), yb = search_mirror(bb + c, P.H);
+                va[j] = __ldg(col + ((ya & m) * mulA + (ya >> s) * P.planePitch));
+                vb[j] = __ldg(col + ((yb & m) * mulA + (yb >> s) * P.planePitch));
             }
         }
     }
-}
-
-/* One search step for windows of WS <= 16 lattice points (warp-local).
- * offX/offY: per-point offsets in registers, updated in place. wz[g]: winning layer of the g-th
- * window stacked in the thread's column (for the trace tap). */
-template <int WS>
-__device__ __forceinline__ void step_small(const FlowParams &P, int it, int axis, int lane, int bx0, int by0, int cx, int yTop,
-                                           const uint32_t (&v2)[HR_PPT], unsigned vmask, int (&offX)[HR_PPT], int (&offY)[HR_PPT],
-                                           int (&wz)[HR_PPT / (WS < HR_PPT ? WS : HR_PPT)]) {
-    constexpr int VG = WS < HR_PPT ? WS : HR_PPT; /* rows of one window held by one thread              */
-    constexpr int NG = HR_PPT / VG;                /* windows stacked in the thread's column             */
-    constexpr int NF = NG > WS ? NG / WS : 1;      /* windows one lane finalises (2 for WS=2, else 1)    */
-    const int lx = lane & 15, half = lane >> 4;
-    const int R = P.R;
-    const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
-    const int sub = lx & (WS - 1);                 /* lane's column inside its window                    */
-
-    PointSet ps;
-    make_points<false>(P, axis, cx, yTop, offX, offY, 0, 0, ps);
-
-    /* the window(s) this lane finalises: slot i handles stacked window g = sub + i*WS (if < NG) */
-    int cur[NF], nbA[NF], nbB[NF];                 /* neighbours packed 2 x int16                        */
-    uint32_t cnt[NF], bestS[NF];
-    int bestZ[NF];
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
-        const int g = sub + i * WS;
-        const int x0 = bx0 + (lx & ~(WS - 1));
-        const int y0 = by0 + (WS == 16 ? 0 : half * 8 + g * VG);
-        cnt[i] = 0;
-        nbA[i] = nbB[i] = 0;
-        cur[i] = 0;
-        bestS[i] = 0xffffffffu;
-        bestZ[i] = 0;
-        if (g < NG && x0 < P.lw && y0 < P.lh) {
-            cnt[i] = (uint32_t)(hr_min(x0 + WS, P.lw) - x0) * (uint32_t)(hr_min(y0 + WS, P.lh) - y0);
-            if (useNb) {
-                int n0, n1, n2, n3;
-                load_neighbours(P, it, WS, axis, x0, y0, n0, n1, n2, n3);
-                nbA[i] = (n0 & 0xffff) | (n1 << 16);
-                nbB[i] = (n2 & 0xffff) | (n3 << 16);
-            }
-        }
-#pragma unroll
-        for (int gg = 0; gg < NG; ++gg)
-            if (gg == g) cur[i] = axis ? offY[gg * VG] : offX[gg * VG];
-    }
-
-    for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) {
-        const int nz = hr_min(HR_ZCHUNK, R - z0);
-        uint32_t v1[HR_ZCHUNK][HR_PPT];
-        load_chunk(P, ps, z0, nz, v1);
-        uint32_t sg[HR_ZCHUNK][NG];
-        /* thread-local column sums */
-#pragma unroll
-        for (int j = 0; j < HR_ZCHUNK; ++j) {
-            if (j < nz) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    uint32_t a = 0;
-#pragma unroll
-                    for (int r = 0; r < VG; ++r) {
-                        const int k = g * VG + r;
-                        a = sad4_acc(((vmask >> k) & 1u) ? v1[j][k] : v2[k], v2[k], a);
-                    }
-                    sg[j][g] = a;
-                }
-            }
-        }
-        /* butterflies across the window's columns (independent chains for every layer) */
-#pragma unroll
-        for (int o = 1; o < WS && o < 16; o <<= 1) {
-#pragma unroll
-            for (int j = 0; j < HR_ZCHUNK; ++j)
-                if (j < nz) {
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) sg[j][g] += __shfl_xor_sync(0xffffffffu, sg[j][g], o);
-                }
-        }
-        if (WS == 16) {
-#pragma unroll
-            for (int j = 0; j < HR_ZCHUNK; ++j)
-                if (j < nz) sg[j][0] += __shfl_xor_sync(0xffffffffu, sg[j][0], 16);
-        }
-        /* biases + first-minimum scan (determineLowestLayerKernel.cl:13-18) */
-#pragma unroll
-        for (int i = 0; i < NF; ++i) {
-            if (cnt[i]) {
-#pragma unroll
-                for (int j = 0; j < HR_ZCHUNK; ++j) {
-                    if (j < nz) {
-                        uint32_t sad = sg[j][(NG > 1) ? i * WS : 0];
-                        if (NG > 1) { /* window sub + i*WS: a register select, sub < WS <= 4 here */
-#pragma unroll
-                            for (int q = 1; q < WS && i * WS + q < NG; ++q)
-                                if (sub == q) sad = sg[j][i * WS + q];
-                        }
-                        const uint32_t S = window_total(sad, P.cand[z0 + j], cur[i], cnt[i], useNb, (int)(int16_t)nbA[i], nbA[i] >> 16,
-                                                        (int)(int16_t)nbB[i], nbB[i] >> 16, P.dS, P.nS);
-                        if (z0 + j == 0 || S < bestS[i]) {
-                            bestS[i] = S;
-                            bestZ[i] = z0 + j;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    /* winners back to every lane of the window, then the offset update (adjustOffsetArrayKernel.cl:11-17) */
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        const int src = (lane & ~(WS - 1) & (WS == 16 ? 0 : 31)) | (g & (WS - 1));
-        wz[g] = __shfl_sync(0xffffffffu, bestZ[g / WS < NF ? g / WS : 0], src);
-        const int upd = P.cand[wz[g]];
-#pragma unroll
-        for (int r = 0; r < VG; ++r) {
-            if (axis) offY[g * VG + r] += upd;
-            else offX[g * VG + r] += upd;
-        }
-    }
-}
-
-/* Per-warp block totals (windows >= 32): sum of the warp's 256 points for every layer, lane z
- * ends up holding layer z. Offsets are uniform over the tile. */
-__device__ __forceinline__ uint32_t block_totals(const FlowParams &P, int axis, int lane, int cx, int yTop, const uint32_t (&v2)[HR_PPT],
-                                                 unsigned vmask, int ox, int oy) {
-    const int dummy[HR_PPT] = {0, 0, 0, 0, 0, 0, 0, 0};
-    PointSet ps;
-    make_points<true>(P, axis, cx, yTop, dummy, dummy, ox, oy, ps);
-    const int R = P.R;
-    uint32_t mineTot = 0;
-    for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) {
-        const int nz = hr_min(HR_ZCHUNK, R - z0);
-        uint32_t v1[HR_ZCHUNK][HR_PPT];
-        load_chunk(P, ps, z0, nz, v1);
-#pragma unroll
-        for (int j = 0; j < HR_ZCHUNK; ++j) {
-            if (j < nz) {
-                uint32_t a = 0;
-#pragma unroll
-                for (int k = 0; k < HR_PPT; ++k) a = sad4_acc(((vmask >> k) & 1u) ? v1[j][k] : v2[k], v2[k], a);
-                a = __reduce_add_sync(0xffffffffu, a);
-                if (lane == z0 + j) mineTot = a;
-            }
-        }
-    }
-    return mineTot;
+    for (int j = 0; j < HR_ZCHUNK; ++j)
+        if (j < nz) acc[j] = sad4_acc(vb[j] & g.m1, v2b, sad4_acc(va[j] & g.m0, v2a, 0u));
 }
 
 /* Executed by one full warp: lane z holds the window's SAD for layer z; returns the winner. */
@@ -303,210 +154,208 @@ __device__ __forceinline__ int finalize_warp(const FlowParams &P, int it, int ws
     const int R = P.R;
     const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
     const uint32_t count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
-    int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
-    if (useNb) load_neighbours(P, it, ws, axis, x0, y0, nb0, nb1, nb2, nb3);
-    const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, nb0, nb1, nb2, nb3, P.dS, P.nS) : 0xffffffffu;
+    uint32_t nbA = 0, nbB = 0;
+    if (useNb) {
+        uint32_t nw[4];
+        load_neighbours(P, it, ws, x0, y0, nw);
+        neighbour_axis(nw, axis, nbA, nbB);
+    }
+    const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, nbA, nbB, P.dS, P.nS) : 0xffffffffu;
     const uint32_t mn = __reduce_min_sync(0xffffffffu, S);
     const unsigned ballot = __ballot_sync(0xffffffffu, S == mn && lane < R);
     return __ffs(ballot) - 1;
 }
 
-/* Per-tile thread geometry */
-struct TileGeom {
-    int tx0, ty0, bx0, by0, cx, yTop;
-    unsigned vmask;
-};
-__device__ __forceinline__ TileGeom tile_geom(const FlowParams &P, int tile, int warp, int lx, int half) {
-    TileGeom g;
-    g.tx0 = (tile % P.tilesX) * HR_TILE;
-    g.ty0 = (tile / P.tilesX) * HR_TILE;
-    g.bx0 = g.tx0 + (warp & 1) * HR_BLK;
-    g.by0 = g.ty0 + (warp >> 1) * HR_BLK;
-    g.cx = hr_min(g.bx0 + lx, P.lw - 1);
-    g.yTop = g.by0 + half * 8;
-    g.vmask = 0;
-#pragma unroll
-    for (int k = 0; k < HR_PPT; ++k)
-        if (g.bx0 + lx < P.lw && g.yTop + k < P.lh) g.vmask |= 1u << k;
-    return g;
-}
-__device__ __forceinline__ void load_frame2(const FlowParams &P, const TileGeom &g, uint32_t (&v2)[HR_PPT]) {
-#pragma unroll
-    for (int k = 0; k < HR_PPT; ++k) v2[k] = __ldg(P.p2 + hr_min(g.yTop + k, P.lh - 1) * P.planePitch + g.cx);
+__device__ __forceinline__ void trace_store(const FlowParams &P, const TileGeom &g, int step, int winner) {
+    if (P.trace) {
+        if (g.m0) P.trace[((size_t)step * P.lh + g.py) * P.lw + g.px] = (uint8_t)winner;
+        if (g.m1) P.trace[((size_t)step * P.lh + g.py + 1) * P.lw + g.px] = (uint8_t)winner;
+    }
 }
 
-__global__ void __launch_bounds__(HR_WARPS * 32, 1) flow_search_kernel(const FlowParams P) {
+template <bool MULTI>
+__global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowParams P) {
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lx = lane & 15, half = lane >> 4;
     const unsigned nCtas = gridDim.x;
     unsigned long long barTarget = P.barBase;
     const int R = P.R;
-    const bool multi = P.numTiles > (int)nCtas;
     const size_t ln = (size_t)P.lw * P.lh;
 
-    if (tid < HR_MAX_TILES_PER_CTA) {
-        sh.tileOffX[tid] = 0;
-        sh.tileOffY[tid] = 0;
-    }
-    __syncthreads();
+    /* per-thread state of the owned tile: offset pair and the two frame2 words */
+    int ox = 0, oy = 0;
+    uint32_t v2a = 0, v2b = 0;
+    TileGeom g = tile_geom(P, blockIdx.x, warp, lane);
 
-    /* register state of the tile this CTA owns (re-loaded per tile when a CTA owns several) */
-    int offX[HR_PPT], offY[HR_PPT];
-    uint32_t v2[HR_PPT];
-#pragma unroll
-    for (int k = 0; k < HR_PPT; ++k) offX[k] = offY[k] = 0;
-    TileGeom tg = tile_geom(P, blockIdx.x, warp, lx, half);
-    load_frame2(P, tg, v2);
-    bool smallStarted = false;
+    auto load_frame2 = [&](const TileGeom &gg) {
+        const int cx = hr_min(gg.px, P.lw - 1);
+        v2a = __ldg(P.p2 + hr_min(gg.py, P.lh - 1) * P.planePitch + cx) & gg.m0;
+        v2b = __ldg(P.p2 + hr_min(gg.py + 1, P.lh - 1) * P.planePitch + cx) & gg.m1;
+    };
+    if (!MULTI) {
+        load_frame2(g);
+    } else {
+        int slot = 0;
+        for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
+            g = tile_geom(P, tile, warp, lane);
+            load_frame2(g);
+            sh.parked[slot][tid] = make_int4(0, 0, (int)v2a, (int)v2b);
+        }
+    }
+#define HR_UNPARK(slot_, tile_)                                   \
+    if (MULTI) {                                                  \
+        g = tile_geom(P, tile_, warp, lane);                      \
+        const int4 st_ = sh.parked[slot_][tid];                   \
+        ox = st_.x; oy = st_.y; v2a = (uint32_t)st_.z; v2b = (uint32_t)st_.w; \
+    }
+#define HR_PARK(slot_) \
+    if (MULTI) sh.parked[slot_][tid] = make_int4(ox, oy, (int)v2a, (int)v2b);
 
     for (int it = 0; it < P.iters; ++it) {
         const int ws = P.first >> it;
         const int lgw = 31 - __clz(ws);
         const int nwx = (P.lw + ws - 1) >> lgw;
         uint32_t *Tcur = P.T + P.tOff[it];
+        const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
+        const bool small = ws <= 8;      /* warp-local windows                         */
+        const bool big = ws > HR_TILE;   /* windows spanning several tiles (CTAs)      */
+        uint32_t nw[4] = {0u, 0u, 0u, 0u};
 
-        if (ws >= HR_TILE) {
-            const bool big = ws > HR_TILE;
-            for (int axis = 0; axis < 2; ++axis) {
-                const int step = it * 2 + axis;
-                int slot = 0;
-                for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-                    if (multi) {
-                        tg = tile_geom(P, tile, warp, lx, half);
-                        load_frame2(P, tg, v2);
-                    }
-                    const int ox = sh.tileOffX[slot], oy = sh.tileOffY[slot];
-                    const uint32_t tot = block_totals(P, axis, lane, tg.cx, tg.yTop, v2, tg.vmask, ox, oy);
-                    sh.warpTot[warp][lane] = tot;
-                    __syncthreads();
-                    const int wx = tg.tx0 >> lgw, wy = tg.ty0 >> lgw;
-                    if (warp == 0) {
-                        const uint32_t t4 = sh.warpTot[0][lane] + sh.warpTot[1][lane] + sh.warpTot[2][lane] + sh.warpTot[3][lane];
-                        if (big) {
-                            if (lane < R) atomicAdd(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane, t4);
-                        } else {
-                            const int cur = axis ? oy : ox;
-                            const int winner = finalize_warp(P, it, ws, axis, lane, t4, wx << lgw, wy << lgw, cur);
-                            if (lane == 0) {
-                                if (axis) sh.tileOffY[slot] = cur + P.cand[winner];
-                                else sh.tileOffX[slot] = cur + P.cand[winner];
-                                sh.winner = winner;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    if (!big) {
-                        if (P.trace) {
-#pragma unroll
-                            for (int k = 0; k < HR_PPT; ++k)
-                                if ((tg.vmask >> k) & 1u) P.trace[((size_t)step * P.lh + tg.yTop + k) * P.lw + tg.cx] = (uint8_t)sh.winner;
-                        }
-                        if (axis == 1 && tid == 0) Tcur[wy * nwx + wx] = (uint32_t)(uint16_t)sh.tileOffX[slot] | ((uint32_t)(uint16_t)sh.tileOffY[slot] << 16);
-                        __syncthreads();
-                    }
-                }
-                if (big) {
-                    grid_barrier(P.bar, barTarget, nCtas);
-                    slot = 0;
-                    for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-                        if (multi) tg = tile_geom(P, tile, warp, lx, half);
-                        const int wx = tg.tx0 >> lgw, wy = tg.ty0 >> lgw;
-                        if (warp == 0) {
-                            const int cur = axis ? sh.tileOffY[slot] : sh.tileOffX[slot];
-                            const uint32_t sad = (lane < R) ? ldcg_u32(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane) : 0u;
-                            const int winner = finalize_warp(P, it, ws, axis, lane, sad, wx << lgw, wy << lgw, cur);
-                            if (lane == 0) {
-                                if (axis) sh.tileOffY[slot] = cur + P.cand[winner];
-                                else sh.tileOffX[slot] = cur + P.cand[winner];
-                                sh.winner = winner;
-                            }
-                        }
-                        __syncthreads();
-                        if (P.trace) {
-#pragma unroll
-                            for (int k = 0; k < HR_PPT; ++k)
-                                if ((tg.vmask >> k) & 1u) P.trace[((size_t)step * P.lh + tg.yTop + k) * P.lw + tg.cx] = (uint8_t)sh.winner;
-                        }
-                        if (axis == 1 && tid == 0) Tcur[wy * nwx + wx] = (uint32_t)(uint16_t)sh.tileOffX[slot] | ((uint32_t)(uint16_t)sh.tileOffY[slot] << 16);
-                        __syncthreads();
-                    }
-                }
-            }
-        } else {
-            /* ---------------- warp-local windows ------------------------------------------------- */
+        for (int axis = 0; axis < 2; ++axis) {
+            const int step = it * 2 + axis;
             int slot = 0;
             for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-                if (multi) {
-                    tg = tile_geom(P, tile, warp, lx, half);
-                    load_frame2(P, tg, v2);
-                }
-                if (!smallStarted) {
-                    /* first warp-local level: every point inherits the tile's offset */
-#pragma unroll
-                    for (int k = 0; k < HR_PPT; ++k) {
-                        offX[k] = sh.tileOffX[slot];
-                        offY[k] = sh.tileOffY[slot];
+                HR_UNPARK(slot, tile);
+                const int cur = axis ? oy : ox;
+                /* the thread's own window (warp-local levels only) */
+                const int x0 = g.px & ~(ws - 1), y0 = g.py & ~(ws - 1);
+                uint32_t count = 0, nbA = 0, nbB = 0;
+                if (small) {
+                    if (x0 < P.lw && y0 < P.lh) {
+                        count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
+                        if (useNb && (axis == 0 || MULTI)) load_neighbours(P, it, ws, x0, y0, nw);
                     }
-                } else if (multi) {
-#pragma unroll
-                    for (int k = 0; k < HR_PPT; ++k) {
-                        const size_t idx = (size_t)hr_min(tg.yTop + k, P.lh - 1) * P.lw + tg.cx;
-                        offX[k] = P.off[idx];
-                        offY[k] = P.off[ln + idx];
-                    }
+                    neighbour_axis(nw, axis, nbA, nbB);
                 }
-                for (int axis = 0; axis < 2; ++axis) {
-                    int wzk[HR_PPT]; /* winner per point, for the trace only */
-                    if (ws == 16) {
-                        int wz[1];
-                        step_small<16>(P, it, axis, lane, tg.bx0, tg.by0, tg.cx, tg.yTop, v2, tg.vmask, offX, offY, wz);
+                uint32_t bestS = 0xffffffffu, mine = 0u;
+                int winner = 0;
+                for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) {
+                    const int nz = hr_min(HR_ZCHUNK, R - z0);
+                    uint32_t acc[HR_ZCHUNK];
+                    eval_chunk(P, axis, g, ox, oy, v2a, v2b, z0, nz, acc);
 #pragma unroll
-                        for (int k = 0; k < HR_PPT; ++k) wzk[k] = wz[0];
-                    } else if (ws == 8) {
-                        int wz[1];
-                        step_small<8>(P, it, axis, lane, tg.bx0, tg.by0, tg.cx, tg.yTop, v2, tg.vmask, offX, offY, wz);
-#pragma unroll
-                        for (int k = 0; k < HR_PPT; ++k) wzk[k] = wz[0];
-                    } else if (ws == 4) {
-                        int wz[2];
-                        step_small<4>(P, it, axis, lane, tg.bx0, tg.by0, tg.cx, tg.yTop, v2, tg.vmask, offX, offY, wz);
-#pragma unroll
-                        for (int k = 0; k < HR_PPT; ++k) wzk[k] = wz[k >> 2];
-                    } else {
-                        int wz[4];
-                        step_small<2>(P, it, axis, lane, tg.bx0, tg.by0, tg.cx, tg.yTop, v2, tg.vmask, offX, offY, wz);
-#pragma unroll
-                        for (int k = 0; k < HR_PPT; ++k) wzk[k] = wz[k >> 1];
-                    }
-                    if (P.trace) {
-#pragma unroll
-                        for (int k = 0; k < HR_PPT; ++k)
-                            if ((tg.vmask >> k) & 1u) P.trace[((size_t)(it * 2 + axis) * P.lh + tg.yTop + k) * P.lw + tg.cx] = (uint8_t)wzk[k];
-                    }
-                }
-                /* publish this level's windows (neighbours / next level / blur) */
-#pragma unroll
-                for (int k = 0; k < HR_PPT; ++k) {
-                    const int y = tg.yTop + k;
-                    if (((tg.vmask >> k) & 1u) && ((tg.bx0 + lx) & (ws - 1)) == 0 && (y & (ws - 1)) == 0)
-                        Tcur[(y >> lgw) * nwx + ((tg.bx0 + lx) >> lgw)] = (uint32_t)(uint16_t)offX[k] | ((uint32_t)(uint16_t)offY[k] << 16);
-                }
-                if (multi || it == P.iters - 1) {
-#pragma unroll
-                    for (int k = 0; k < HR_PPT; ++k)
-                        if ((tg.vmask >> k) & 1u) {
-                            const size_t idx = (size_t)(tg.yTop + k) * P.lw + tg.cx;
-                            P.off[idx] = (int16_t)offX[k];
-                            P.off[ln + idx] = (int16_t)offY[k];
+                    for (int j = 0; j < HR_ZCHUNK; ++j) {
+                        if (j < nz) {
+                            uint32_t a = acc[j];
+                            if (ws >= 8) {
+                                a = __reduce_add_sync(0xffffffffu, a);
+                            } else {
+                                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                                if (ws == 4) {
+                                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                                }
+                            }
+                            if (small) {
+                                /* first-minimum scan, determineLowestLayerKernel.cl:13-18 */
+                                const uint32_t S = window_total(a, P.cand[z0 + j], cur, count, useNb, nbA, nbB, P.dS, P.nS);
+                                if (z0 + j == 0 || S < bestS) {
+                                    bestS = S;
+                                    winner = z0 + j;
+                                }
+                            } else if (lane == z0 + j) {
+                                mine = a;
+                            }
                         }
+                    }
+                }
+                if (!small) {
+                    sh.warpTot[warp][lane] = mine;
+                    __syncthreads();
+                    if (big) {
+                        if (warp == 0) {
+                            uint32_t t = 0;
+#pragma unroll
+                            for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
+                            const int wx = g.tx0 >> lgw, wy = g.ty0 >> lgw;
+                            if (lane < R) atomicAdd(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane, t);
+                        }
+                        __syncthreads();
+                        continue; /* scored after the grid barrier */
+                    }
+                    if (ws == HR_TILE) {
+                        if (warp == 0) {
+                            uint32_t t = 0;
+#pragma unroll
+                            for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
+                            const int wz = finalize_warp(P, it, ws, axis, lane, t, g.tx0, g.ty0, cur);
+                            if (lane == 0) sh.winner[0] = wz;
+                        }
+                    } else if (((warp & 1) | ((warp >> 2) & 1)) == 0) { /* window 16: leader warp of each 2x2 warp group */
+                        const uint32_t t = sh.warpTot[warp][lane] + sh.warpTot[warp + 1][lane] + sh.warpTot[warp + 4][lane] + sh.warpTot[warp + 5][lane];
+                        const int wx0 = g.tx0 + (warp & 2) * 8, wy0 = g.ty0 + (warp >> 3) * 16;
+                        int wz = 0;
+                        if (wx0 < P.lw && wy0 < P.lh) wz = finalize_warp(P, it, ws, axis, lane, t, wx0, wy0, cur);
+                        if (lane == 0) sh.winner[(warp >> 3) * 2 + ((warp >> 1) & 1)] = wz;
+                    }
+                    __syncthreads();
+                    winner = sh.winner[ws == HR_TILE ? 0 : (warp >> 3) * 2 + ((warp >> 1) & 1)];
+                }
+                if (axis) oy += P.cand[winner];
+                else ox += P.cand[winner];
+                trace_store(P, g, step, winner);
+                /* publish this level's windows (neighbours of the next level / blur) */
+                if (axis == 1 && g.m0 && g.px == (g.px & ~(ws - 1)) && g.py == (g.py & ~(ws - 1)))
+                    Tcur[(g.py >> lgw) * nwx + (g.px >> lgw)] = (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16);
+                HR_PARK(slot);
+            }
+            if (big) {
+                grid_barrier(P.bar, barTarget, nCtas);
+                slot = 0;
+                for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
+                    HR_UNPARK(slot, tile);
+                    const int wx = g.tx0 >> lgw, wy = g.ty0 >> lgw;
+                    if (warp == 0) {
+                        const int cur = axis ? oy : ox;
+                        const uint32_t sad = (lane < R) ? ldcg_u32(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane) : 0u;
+                        const int wz = finalize_warp(P, it, ws, axis, lane, sad, wx << lgw, wy << lgw, cur);
+                        if (lane == 0) sh.winner[0] = wz;
+                    }
+                    __syncthreads();
+                    const int winner = sh.winner[0];
+                    if (axis) oy += P.cand[winner];
+                    else ox += P.cand[winner];
+                    trace_store(P, g, step, winner);
+                    if (axis == 1 && tid == 0 && g.tx0 == (wx << lgw) && g.ty0 == (wy << lgw))
+                        Tcur[wy * nwx + wx] = (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16);
+                    HR_PARK(slot);
+                    if (MULTI) __syncthreads();
                 }
             }
-            smallStarted = true;
         }
         const int nws = ws >> 1;
         if (it + 1 < P.iters && (it + 1) >= HR_FIRST_NEIGHBOR_ITERATION && nws <= HR_TILE) grid_barrier(P.bar, barTarget, nCtas);
     }
+
+    /* raw offsets (offsetArray) */
+    {
+        int slot = 0;
+        for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
+            HR_UNPARK(slot, tile);
+            if (g.m0) {
+                const size_t idx = (size_t)g.py * P.lw + g.px;
+                P.off[idx] = (int16_t)ox;
+                P.off[ln + idx] = (int16_t)oy;
+            }
+            if (g.m1) {
+                const size_t idx = (size_t)(g.py + 1) * P.lw + g.px;
+                P.off[idx] = (int16_t)ox;
+                P.off[ln + idx] = (int16_t)oy;
+            }
+        }
+    }
+#undef HR_UNPARK
+#undef HR_PARK
 
     /* ------------- blur the raw offsets (K4), reading the last level's window table --------------- */
     grid_barrier(P.bar, barTarget, nCtas);
@@ -517,7 +366,7 @@ __global__ void __launch_bounds__(HR_WARPS * 32, 1) flow_search_kernel(const Flo
         const uint32_t *Tl = P.T + P.tOff[P.iters - 1];
         int16_t *tX = sh.blur.tX, *tY = sh.blur.tY;
         int *hX = sh.blur.hX, *hY = sh.blur.hY;
-        constexpr int NT = HR_WARPS * 32;
+        constexpr int NT = HR_THREADS;
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas) {
             const int tx0 = (tile % P.tilesX) * HR_TILE, ty0 = (tile / P.tilesX) * HR_TILE;
 #pragma unroll
