@@ -126,6 +126,13 @@ int hr_blur_flow(HrContext *ctx, const int16_t *rawHost, int16_t *blurredHost);
 int hr_set_trace(HrContext *ctx, int enable);
 int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers);
 
+/* Developer tap: SM-clock stamps taken by thread 0 of every search CTA at fixed points of the launch
+ * (step start, layers reduced, window published / complete, level done, search done, blur done).
+ * stamps: int64 [min(maxCtas, searchCtas)][HR_TIMELINE_SLOTS]; unused slots are 0. Blocking. */
+#define HR_TIMELINE_SLOTS 128
+int hr_set_timeline(HrContext *ctx, int enable);
+int hr_get_timeline(HrContext *ctx, long long *stamps, int maxCtas);
+
 /* Record CUDA events around every kernel launch (off by default; adds two event records per launch). */
 int hr_set_profiling(HrContext *ctx, int enable);
 /* Device time of the most recent search-kernel / warp-kernel / pack-kernel launch, seconds,

@@ -61,6 +61,8 @@ ABI = {
     "hr_blur_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hr_set_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hr_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hr_get_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -207,6 +209,14 @@ class HrCuda:
     def get_step_layers(self, step):
         out = np.empty((self.info.lowHeight, self.info.lowWidth), np.uint8)
         self._chk(self.lib.hr_get_step_layers(self.h, step, _ptr(out)))
+        return out
+
+    def set_timeline(self, on=True):
+        self._chk(self.lib.hr_set_timeline(self.h, 1 if on else 0))
+
+    def get_timeline(self):
+        out = np.zeros((self.info.searchCtas, 128), np.int64)
+        self._chk(self.lib.hr_get_timeline(self.h, _ptr(out), self.info.searchCtas))
         return out
 
     def set_profiling(self, on=True):

@@ -30,6 +30,7 @@
 #define HR_ZCHUNK 8                /* candidate layers in flight per thread                       */
 #define HR_RMAX 32                 /* HR_MAX_SEARCH_RADIUS                                       */
 #define HR_FIRST_NEIGHBOR_ITERATION 4 /* calcDeltaSumsKernel.cl:1 */
+#define HR_TIMELINE_SLOTS 128
 
 struct FlowParams {
     const uint32_t *p1;      /* packed previous frame (frame1): all phase planes                 */
@@ -39,17 +40,16 @@ struct FlowParams {
     int W, H, s, lw, lh;
     int first, iters, R, dS, nS;
     int cand[HR_RMAX];       /* signed-square layer shifts, calcDeltaSumsKernel.cl:68-72         */
-    int tilesX, numTiles;
-    uint32_t *T;             /* per-level window offset tables, int16x2 (x | y << 16)             */
+    int tilesX, tilesY, numTiles;
+    unsigned long long *T;   /* per-level window offset tables: epoch << 32 | (x | y << 16)       */
     int tOff[HR_MAX_LEVELS]; /* word offset of level `it` in T                                    */
-    uint32_t *bigSums;       /* cross-CTA window sums for windows > tile: [bigStep][win][HR_RMAX] */
-    int bigOff[2 * HR_MAX_LEVELS]; /* word offset of search step k in bigSums (-1: not a big step) */
-    int bigWords;
-    unsigned long long *bar; /* monotonic grid-barrier counter                                   */
-    unsigned long long barBase;
+    unsigned long long *partial; /* cross-tile window sums [bigStep][tile][HR_RMAX]: epoch << 32 | tile total */
+    int bigOff[2 * HR_MAX_LEVELS]; /* word offset of search step k in partial (-1: not a big step) */
+    uint32_t epoch;          /* tag of this launch (never 0, differs from the previous launch)     */
     int16_t *off;            /* raw offsets  [2][lh][lw]  (offsetArray)                           */
     int16_t *blur;           /* blurred      [2][lh][lw]  (blurredOffsetArray)                    */
     uint8_t *trace;          /* optional [steps][lh][lw] winning layer per point, or NULL         */
+    long long *timeline;     /* optional [ctas][HR_TIMELINE_SLOTS] clock64 stamps of thread 0, or NULL */
 };
 
 template <typename T>
@@ -100,17 +100,23 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsig
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-/* Grid-wide barrier of the persistent search kernel (all CTAs are co-resident: cooperative
- * launch). The counter only grows; `target` is carried by every CTA. */
-__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &target, unsigned nCtas) {
-    __syncthreads();
-    target += nCtas;
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        red_release_add_u64(bar, 1ULL);              /* release: orders this CTA's earlier writes (cumulative over bar.sync) */
-        while (ld_relaxed_u64(bar) < target) {
-        }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    }
-    __syncthreads();
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/* ---- tile-to-tile hand-off without barriers ------------------------------------------------------
+ * Every word that one CTA produces for another (window-table entries, per-tile window sums) is a
+ * 64-bit word written exactly once per launch: payload in the low half, the launch's epoch tag in the
+ * high half, stored with one 64-bit store. A consumer loads the word it needs and re-loads while the
+ * tag is stale: the payload and its "ready" flag arrive together, so no fence, no flag array, no
+ * atomics and no grid barrier are needed, and a CTA only ever waits for the words it actually reads.
+ * All CTAs are co-resident (cooperative launch) and producers never wait on consumers of the same
+ * level, so polling cannot deadlock. */
+__device__ __forceinline__ void put_tagged(unsigned long long *p, uint32_t epoch, uint32_t payload) {
+    st_relaxed_u64(p, ((unsigned long long)epoch << 32) | payload);
+}
+__device__ __forceinline__ uint32_t get_tagged(const unsigned long long *p, uint32_t epoch) {
+    unsigned long long v = ld_relaxed_u64(p);
+    while ((uint32_t)(v >> 32) != epoch) v = ld_relaxed_u64(p);
+    return (uint32_t)v;
+}

@@ -37,17 +37,17 @@ struct HrContext {
     uint8_t *outBuf;
     void *outY, *outUV;            /* current output planes (internal or caller's)              */
     int16_t *off, *blur;
-    uint32_t *T;
+    unsigned long long *T;
     int tOff[HR_MAX_LEVELS];
     int tWords;
-    uint32_t *bigSums;
+    unsigned long long *partial;   /* cross-tile window sums [bigStep][tile][HR_RMAX], epoch-tagged  */
     int bigOff[2 * HR_MAX_LEVELS];
     int bigWords;
-    unsigned long long *bar;
-    unsigned long long barBase;
-    int barriersPerLaunch;
+    uint32_t epoch;                /* tag of the last search launch                                */
     uint8_t *trace;
     int traceOn;
+    long long *timeline;
+    int timelineOn;
     uint8_t *lut;
     int *lutIdentityDev;
     int lutIdentity, lutValid;
@@ -121,9 +121,9 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->off);
     cudaFree(ctx->blur);
     cudaFree(ctx->T);
-    cudaFree(ctx->bigSums);
-    cudaFree(ctx->bar);
+    cudaFree(ctx->partial);
     cudaFree(ctx->trace);
+    cudaFree(ctx->timeline);
     cudaFree(ctx->lut);
     cudaFree(ctx->lutIdentityDev);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
@@ -156,7 +156,7 @@ static int create_impl(HrContext *ctx) {
     ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
     ctx->numTiles = ctx->tilesX * ctx->tilesY;
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<true>, HR_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<0, true>, HR_THREADS, 0));
     if (perSm > 1) perSm = 1; /* one tile per SM: the search is latency-bound, spread it out */
     if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
     const int maxResident = perSm * ctx->smCount;
@@ -182,24 +182,18 @@ static int create_impl(HrContext *ctx) {
         words += (nwx * nwy + 31) & ~31;
     }
     ctx->tWords = words;
-    int bwords = 0, barriers = 0;
+    /* per-tile totals of the search steps whose windows span several tiles */
+    int bwords = 0;
     for (int k = 0; k < 2 * HR_MAX_LEVELS; ++k) ctx->bigOff[k] = -1;
     for (int it = 0; it < ctx->iters; ++it) {
-        const int ws = ctx->first >> it;
-        if (ws > HR_TILE) {
-            const int nwx = (ctx->lw + ws - 1) / ws, nwy = (ctx->lh + ws - 1) / ws;
+        if ((ctx->first >> it) > HR_TILE) {
             for (int axis = 0; axis < 2; ++axis) {
                 ctx->bigOff[it * 2 + axis] = bwords;
-                bwords += nwx * nwy * HR_RMAX;
-                barriers++;
+                bwords += ctx->numTiles * HR_RMAX;
             }
         }
-        const int nws = ws >> 1;
-        if (it + 1 < ctx->iters && (it + 1) >= HR_FIRST_NEIGHBOR_ITERATION && nws <= HR_TILE) barriers++;
     }
-    barriers++; /* before the blur */
     ctx->bigWords = bwords;
-    ctx->barriersPerLaunch = barriers;
 
     const size_t ln = (size_t)ctx->lw * ctx->lh;
     CU(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
@@ -211,9 +205,8 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMalloc(&ctx->packed[1], ctx->packedBytes));
     CU(cudaMalloc(&ctx->off, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
-    CU(cudaMalloc(&ctx->T, (size_t)(words ? words : 32) * sizeof(uint32_t)));
-    CU(cudaMalloc(&ctx->bigSums, (size_t)(bwords ? bwords : 32) * sizeof(uint32_t)));
-    CU(cudaMalloc(&ctx->bar, 128));
+    CU(cudaMalloc(&ctx->T, (size_t)(words ? words : 32) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->partial, (size_t)(bwords ? bwords : 32) * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->lut, 512));
     CU(cudaMalloc(&ctx->lutIdentityDev, sizeof(int)));
     CU(cudaMemset(ctx->frameBuf[0], 0, ctx->frameBytes));
@@ -223,11 +216,10 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMemset(ctx->packed[1], 0, ctx->packedBytes));
     CU(cudaMemset(ctx->off, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blur, 0, 2 * ln * sizeof(int16_t)));
-    CU(cudaMemset(ctx->T, 0, (size_t)(words ? words : 32) * sizeof(uint32_t)));
-    CU(cudaMemset(ctx->bigSums, 0, (size_t)(bwords ? bwords : 32) * sizeof(uint32_t)));
-    CU(cudaMemset(ctx->bar, 0, 128));
-    ctx->barBase = 0;
-    ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 4 + 128 + 516;
+    CU(cudaMemset(ctx->T, 0, (size_t)(words ? words : 32) * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->partial, 0, (size_t)(bwords ? bwords : 32) * sizeof(unsigned long long)));
+    ctx->epoch = 0;
+    ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 8 + 516;
     for (int i = 0; i < 2; ++i) {
         ctx->fy[i] = ctx->frameBuf[i];
         ctx->fuv[i] = ctx->frameBuf[i] + (size_t)ctx->H * ctx->W * ctx->bps;
@@ -321,6 +313,28 @@ extern "C" int hr_set_trace(HrContext *ctx, int enable) {
     return 0;
 }
 
+extern "C" int hr_set_timeline(HrContext *ctx, int enable) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    if (enable && !ctx->timeline) {
+        const size_t n = (size_t)ctx->grid * HR_TIMELINE_SLOTS * sizeof(long long);
+        CU(cudaMalloc(&ctx->timeline, n));
+        CU(cudaMemset(ctx->timeline, 0, n));
+    }
+    ctx->timelineOn = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int hr_get_timeline(HrContext *ctx, long long *stamps, int maxCtas) {
+    if (!ctx || !stamps) return 1;
+    if (!ctx->timeline) return fail(ctx, "hr_get_timeline: the timeline was not enabled");
+    if (bind_device(ctx)) return 1;
+    const int n = maxCtas < ctx->grid ? maxCtas : ctx->grid;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(stamps, ctx->timeline, (size_t)n * HR_TIMELINE_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int hr_set_profiling(HrContext *ctx, int enable) {
     if (!ctx) return 1;
     ctx->profiling = enable ? 1 : 0;
@@ -404,6 +418,20 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
     return 0;
 }
 
+/* The search radius the filter uses drifts between MIN_SEARCH_RADIUS and MAX_SEARCH_RADIUS
+ * (config.h:6-7, vf_HopperRender.c:326-345): those radii get a kernel with the layer loop fully
+ * unrolled and the layer shifts as immediates; any other radius runs the generic kernel. */
+static const void *search_kernel_for(int R, int multi) {
+    if (multi) return (const void *)flow_search_kernel<0, true>;
+    switch (R) {
+#define HR_RCASE(r) case r: return (const void *)flow_search_kernel<r, false>;
+        HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
+        HR_RCASE(13) HR_RCASE(14) HR_RCASE(15) HR_RCASE(16)
+#undef HR_RCASE
+        default: return (const void *)flow_search_kernel<0, false>;
+    }
+}
+
 extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, double *seconds) {
     if (!ctx) return 1;
     if (searchRadius < HR_MIN_SEARCH_RADIUS || searchRadius > HR_MAX_SEARCH_RADIUS)
@@ -432,26 +460,26 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
         P.cand[z] = z < searchRadius ? rel * abs(rel) : 0;
     }
     P.tilesX = ctx->tilesX;
+    P.tilesY = ctx->tilesY;
     P.numTiles = ctx->numTiles;
     P.T = ctx->T;
     memcpy(P.tOff, ctx->tOff, sizeof(P.tOff));
-    P.bigSums = ctx->bigSums;
+    P.partial = ctx->partial;
     memcpy(P.bigOff, ctx->bigOff, sizeof(P.bigOff));
-    P.bigWords = ctx->bigWords;
-    P.bar = ctx->bar;
-    P.barBase = ctx->barBase;
+    if (++ctx->epoch == 0) ctx->epoch = 1; /* 0 is the tag of never-written words */
+    P.epoch = ctx->epoch;
     P.off = ctx->off;
     P.blur = ctx->blur;
     P.trace = ctx->traceOn ? ctx->trace : NULL;
+    P.timeline = ctx->timelineOn ? ctx->timeline : NULL;
     void *args[] = {&P};
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
-    const void *kfn = ctx->multiTile ? (const void *)flow_search_kernel<true> : (const void *)flow_search_kernel<false>;
+    const void *kfn = search_kernel_for(searchRadius, ctx->multiTile);
     CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, ctx->stream));
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], ctx->stream));
         ctx->haveSearchT = 1;
     }
-    ctx->barBase += (unsigned long long)ctx->barriersPerLaunch * ctx->grid;
     ctx->launches++;
     CU(cudaEventRecord(ctx->evFlowEnd, ctx->stream));
     if (seconds) {

@@ -49,17 +49,13 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 }
 
 /* Window total for layer shift c (calcDeltaSumsKernel.cl:99-150 summed over the window, mod 2^32):
- * (SAD << deltaScalar) + count * (|own| + (sum of the four |neighbour - own|) << neighborBiasScalar),
- * magnitudes as unsigned 16-bit. nbA / nbB hold two int16 neighbour offsets each. */
-__device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int cur, uint32_t count, bool useNb, uint32_t nbA, uint32_t nbB,
-                                                 int dS, int nS) {
-    const int own = (int)(int16_t)(cur + c);
-    uint32_t bias = (uint32_t)(uint16_t)abs(own);
-    if (useNb) {
-        const uint32_t nb = (uint32_t)(uint16_t)abs((int)(int16_t)nbA - own) + (uint32_t)(uint16_t)abs(((int)nbA >> 16) - own) +
-                            (uint32_t)(uint16_t)abs((int)(int16_t)nbB - own) + (uint32_t)(uint16_t)abs(((int)nbB >> 16) - own);
-        bias += nb << nS;
-    }
+ * (SAD << deltaScalar) + count * (|own| + (sum of the four |neighbour - own|) << neighborBiasScalar).
+ * The reference takes the magnitudes on 16-bit values; offsets never leave +-(16 levels x 16^2), so
+ * plain 32-bit |a-b| (one VABSDIFF each) is the same number. n[]: the four neighbour offsets. */
+__device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int cur, uint32_t count, bool useNb, const int (&n)[4], int dS, int nS) {
+    const int own = cur + c;
+    uint32_t bias = (uint32_t)abs(own);
+    if (useNb) bias += __sad(n[3], own, __sad(n[2], own, __sad(n[1], own, __sad(n[0], own, 0u)))) << nS;
     return (sad << dS) + count * bias;
 }
 
@@ -71,20 +67,25 @@ __device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int
     const int pws = ws << 1;
     const int lgp = 31 - __clz(pws);
     const int pnwx = (P.lw + pws - 1) >> lgp;
-    const uint32_t *Tp = P.T + P.tOff[it - 1];
+    const unsigned long long *Tp = P.T + P.tOff[it - 1];
     const int yd = hr_min(y0 + pws, P.lh - 1) >> lgp, yu = hr_max(y0 - pws, 0) >> lgp;
     const int xr = hr_min(x0 + pws, P.lw - 1) >> lgp, xl = hr_max(x0 - pws, 0) >> lgp;
     const int xc = x0 >> lgp, yc = y0 >> lgp;
-    nw[0] = ldcg_u32(Tp + yd * pnwx + xc); /* down  */
-    nw[1] = ldcg_u32(Tp + yc * pnwx + xr); /* right */
-    nw[2] = ldcg_u32(Tp + yc * pnwx + xl); /* left  */
-    nw[3] = ldcg_u32(Tp + yu * pnwx + xc); /* up    */
+    const unsigned long long *q[4] = {Tp + yd * pnwx + xc /* down */, Tp + yc * pnwx + xr /* right */, Tp + yc * pnwx + xl /* left */,
+                                      Tp + yu * pnwx + xc /* up */};
+    unsigned long long v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ld_relaxed_u64(q[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        while ((uint32_t)(v[i] >> 32) != P.epoch) v[i] = ld_relaxed_u64(q[i]); /* the producing tile has not got there yet */
+        nw[i] = (uint32_t)v[i];
+    }
 }
-/* pick one axis out of the four neighbour words: two int16 per result word */
-__device__ __forceinline__ void neighbour_axis(const uint32_t (&nw)[4], int axis, uint32_t &nbA, uint32_t &nbB) {
-    const uint32_t sel = axis ? 0x7632u : 0x5410u;
-    nbA = __byte_perm(nw[0], nw[1], sel);
-    nbB = __byte_perm(nw[2], nw[3], sel);
+/* pick one axis out of the four neighbour words */
+__device__ __forceinline__ void neighbour_axis(const uint32_t (&nw)[4], int axis, int (&n)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n[i] = axis ? ((int)nw[i] >> 16) : (int)(int16_t)nw[i];
 }
 
 /* Per-thread geometry inside a tile */
@@ -106,61 +107,56 @@ __device__ __forceinline__ TileGeom tile_geom(const FlowParams &P, int tile, int
     return g;
 }
 
-/* SAD of the thread's two points for layers z0 .. z0+nz-1 of one search step.
- * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s. */
-__device__ __forceinline__ void eval_chunk(const FlowParams &P, int axis, const TileGeom &g, int ox, int oy, uint32_t v2a, uint32_t v2b, int z0, int nz,
-                                           uint32_t (&acc)[HR_ZCHUNK]) {
+/* Layer shift of layer z: calcDeltaSumsKernel.cl:68-72. RT > 0: search radius known at compile time. */
+template <int RT>
+__device__ __forceinline__ int layer_shift(const FlowParams &P, int z) {
+    if (RT > 0) {
+        const int rel = z - RT / 2;
+        return rel * (rel < 0 ? -rel : rel);
+    }
+    return P.cand[z];
+}
+
+/* SAD of the thread's two points for layers z0 .. z0+HR_ZCHUNK-1 (those below R) of one search step.
+ * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
+ * INTERIOR (warp-uniform): no layer of any lane leaves the frame on the searched axis -> no mirror. */
+template <int RT, bool INTERIOR>
+__device__ __forceinline__ void eval_chunk(const FlowParams &P, int R, int axis, int fa, int fb, int ma, int mb, uint32_t m0, uint32_t m1, uint32_t v2a,
+                                           uint32_t v2b, int z0, uint32_t (&acc)[HR_ZCHUNK]) {
     const int s = P.s, m = (1 << s) - 1;
-    const int cx = hr_min(g.px, P.lw - 1), cy0 = hr_min(g.py, P.lh - 1), cy1 = hr_min(g.py + 1, P.lh - 1);
+    const int mulA = axis ? (P.planeSize << s) : P.planeSize;
+    const int mulB = axis ? P.planePitch : 1;
+    const int D = axis ? P.H : P.W;
     uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
-    if (axis == 0) {
-        /* layers move x: the two rows are fixed, both points share the moving column */
-        const int ya = search_mirror((cy0 << s) + oy, P.H), yb = search_mirror((cy1 << s) + oy, P.H);
-        const uint32_t *ra = P.p1 + (((ya & m) << s) * P.planeSize + (ya >> s) * P.planePitch);
-        const uint32_t *rb = P.p1 + (((yb & m) << s) * P.planeSize + (yb >> s) * P.planePitch);
-        const int base = (cx << s) + ox;
 #pragma unroll
-        for (int j = 0; j < HR_ZCHUNK; ++j) {
-            if (j < nz) {
-                const int x = search_mirror(base + P.cand[z0 + j], P.W);
-                const int xi = (x & m) * P.planeSize + (x >> s);
-                va[j] = __ldg(ra + xi);
-                vb[j] = __ldg(rb + xi);
+    for (int j = 0; j < HR_ZCHUNK; ++j) {
+        if (z0 + j < R) {
+            const int c = layer_shift<RT>(P, z0 + j);
+            int pa = ma + c, pb = mb + c;
+            if (!INTERIOR) {
+                pa = search_mirror(pa, D);
+                pb = search_mirror(pb, D);
             }
-        }
-    } else {
-        /* layers move y: the column is fixed */
-        const int x = search_mirror((cx << s) + ox, P.W);
-        const uint32_t *col = P.p1 + ((x & m) * P.planeSize + (x >> s));
-        const int ba = (cy0 << s) + oy, bb = (cy1 << s) + oy;
-        const int mulA = P.planeSize << s;
-#pragma unroll
-        for (int j = 0; j < HR_ZCHUNK; ++j) {
-            if (j < nz) {
-                const int c = P.cand[z0 + j];
-                const int ya = search_mirror(ba + c, P.H), yb = search_mirror(bb + c, P.H);
-                va[j] = __ldg(col + ((ya & m) * mulA + (ya >> s) * P.planePitch));
-                vb[j] = __ldg(col + ((yb & m) * mulA + (yb >> s) * P.planePitch));
-            }
+            va[j] = __ldg(P.p1 + (fa + (pa & m) * mulA + (pa >> s) * mulB));
+            vb[j] = __ldg(P.p1 + (fb + (pb & m) * mulA + (pb >> s) * mulB));
         }
     }
 #pragma unroll
     for (int j = 0; j < HR_ZCHUNK; ++j)
-        if (j < nz) acc[j] = sad4_acc(vb[j] & g.m1, v2b, sad4_acc(va[j] & g.m0, v2a, 0u));
+        if (z0 + j < R) acc[j] = sad4_acc(vb[j] & m1, v2b, sad4_acc(va[j] & m0, v2a, 0u));
 }
 
 /* Executed by one full warp: lane z holds the window's SAD for layer z; returns the winner. */
-__device__ __forceinline__ int finalize_warp(const FlowParams &P, int it, int ws, int axis, int lane, uint32_t sad, int x0, int y0, int cur) {
-    const int R = P.R;
+__device__ __forceinline__ int finalize_warp(const FlowParams &P, int R, int it, int ws, int axis, int lane, uint32_t sad, int x0, int y0, int cur) {
     const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
     const uint32_t count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
-    uint32_t nbA = 0, nbB = 0;
+    int n[4] = {0, 0, 0, 0};
     if (useNb) {
         uint32_t nw[4];
         load_neighbours(P, it, ws, x0, y0, nw);
-        neighbour_axis(nw, axis, nbA, nbB);
+        neighbour_axis(nw, axis, n);
     }
-    const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, nbA, nbB, P.dS, P.nS) : 0xffffffffu;
+    const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, n, P.dS, P.nS) : 0xffffffffu;
     const uint32_t mn = __reduce_min_sync(0xffffffffu, S);
     const unsigned ballot = __ballot_sync(0xffffffffu, S == mn && lane < R);
     return __ffs(ballot) - 1;
@@ -173,14 +169,18 @@ __device__ __forceinline__ void trace_store(const FlowParams &P, const TileGeom 
     }
 }
 
-template <bool MULTI>
+template <int RT, bool MULTI>
 __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowParams P) {
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nCtas = gridDim.x;
-    unsigned long long barTarget = P.barBase;
-    const int R = P.R;
+    const int R = RT > 0 ? RT : P.R;
+    const int s = P.s, m = (1 << s) - 1;
     const size_t ln = (size_t)P.lw * P.lh;
+    int stampIdx = 0;
+#define HR_STAMP()                                                                                         \
+    if (P.timeline && tid == 0 && stampIdx < HR_TIMELINE_SLOTS) P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + stampIdx++] = clock64();
+    HR_STAMP();
 
     /* per-thread state of the owned tile: offset pair and the two frame2 words */
     int ox = 0, oy = 0;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
         const int ws = P.first >> it;
         const int lgw = 31 - __clz(ws);
         const int nwx = (P.lw + ws - 1) >> lgw;
-        uint32_t *Tcur = P.T + P.tOff[it];
+        unsigned long long *Tcur = P.T + P.tOff[it];
         const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
         const bool small = ws <= 8;      /* warp-local windows                         */
         const bool big = ws > HR_TILE;   /* windows spanning several tiles (CTAs)      */
@@ -226,26 +226,46 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
             int slot = 0;
             for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
                 HR_UNPARK(slot, tile);
+                HR_STAMP(); /* step start (after the neighbour-table wait) */
                 const int cur = axis ? oy : ox;
                 /* the thread's own window (warp-local levels only) */
                 const int x0 = g.px & ~(ws - 1), y0 = g.py & ~(ws - 1);
-                uint32_t count = 0, nbA = 0, nbB = 0;
+                uint32_t count = 0;
+                int nb[4] = {0, 0, 0, 0};
                 if (small) {
                     if (x0 < P.lw && y0 < P.lh) {
                         count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
                         if (useNb && (axis == 0 || MULTI)) load_neighbours(P, it, ws, x0, y0, nw);
                     }
-                    neighbour_axis(nw, axis, nbA, nbB);
+                    neighbour_axis(nw, axis, nb);
                 }
+                /* sample addressing of this step: fixed part (the axis that does not move) and the moving
+                 * coordinate before the layer shift, for the upper (a) and lower (b) point */
+                const int cx = hr_min(g.px, P.lw - 1), cy0 = hr_min(g.py, P.lh - 1), cy1 = hr_min(g.py + 1, P.lh - 1);
+                int fa, fb, ma, mb;
+                if (axis == 0) {
+                    const int ya = search_mirror((cy0 << s) + oy, P.H), yb = search_mirror((cy1 << s) + oy, P.H);
+                    fa = ((ya & m) << s) * P.planeSize + (ya >> s) * P.planePitch;
+                    fb = ((yb & m) << s) * P.planeSize + (yb >> s) * P.planePitch;
+                    ma = mb = (cx << s) + ox;
+                } else {
+                    const int x = search_mirror((cx << s) + ox, P.W);
+                    fa = fb = (x & m) * P.planeSize + (x >> s);
+                    ma = (cy0 << s) + oy;
+                    mb = (cy1 << s) + oy;
+                }
+                const int cmin = layer_shift<RT>(P, 0), cmax = layer_shift<RT>(P, R - 1);
+                const bool interior = __all_sync(0xffffffffu, hr_min(ma, mb) + cmin >= 0 && hr_max(ma, mb) + cmax < (axis ? P.H : P.W));
+
                 uint32_t bestS = 0xffffffffu, mine = 0u;
                 int winner = 0;
-                for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) {
-                    const int nz = hr_min(HR_ZCHUNK, R - z0);
+                auto do_chunk = [&](int z0) {
                     uint32_t acc[HR_ZCHUNK];
-                    eval_chunk(P, axis, g, ox, oy, v2a, v2b, z0, nz, acc);
+                    if (interior) eval_chunk<RT, true>(P, R, axis, fa, fb, ma, mb, g.m0, g.m1, v2a, v2b, z0, acc);
+                    else eval_chunk<RT, false>(P, R, axis, fa, fb, ma, mb, g.m0, g.m1, v2a, v2b, z0, acc);
 #pragma unroll
                     for (int j = 0; j < HR_ZCHUNK; ++j) {
-                        if (j < nz) {
+                        if (z0 + j < R) {
                             uint32_t a = acc[j];
                             if (ws >= 8) {
                                 a = __reduce_add_sync(0xffffffffu, a);
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                             }
                             if (small) {
                                 /* first-minimum scan, determineLowestLayerKernel.cl:13-18 */
-                                const uint32_t S = window_total(a, P.cand[z0 + j], cur, count, useNb, nbA, nbB, P.dS, P.nS);
+                                const uint32_t S = window_total(a, layer_shift<RT>(P, z0 + j), cur, count, useNb, nb, P.dS, P.nS);
                                 if (z0 + j == 0 || S < bestS) {
                                     bestS = S;
                                     winner = z0 + j;
@@ -268,7 +288,15 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                             }
                         }
                     }
+                };
+                if constexpr (RT > 0) {
+#pragma unroll
+                    for (int z0 = 0; z0 < RT; z0 += HR_ZCHUNK) do_chunk(z0);
+                } else {
+#pragma unroll 1
+                    for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) do_chunk(z0);
                 }
+                HR_STAMP(); /* layers evaluated and reduced */
                 if (!small) {
                     sh.warpTot[warp][lane] = mine;
                     __syncthreads();
@@ -277,25 +305,24 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                             uint32_t t = 0;
 #pragma unroll
                             for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
-                            const int wx = g.tx0 >> lgw, wy = g.ty0 >> lgw;
-                            if (lane < R) atomicAdd(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane, t);
+                            put_tagged(P.partial + P.bigOff[step] + tile * HR_RMAX + lane, P.epoch, t);
                         }
-                        __syncthreads();
-                        continue; /* scored after the grid barrier */
+                        __syncthreads(); /* warpTot is reused below */
+                        continue; /* scored below, from the totals of all tiles of the window */
                     }
                     if (ws == HR_TILE) {
                         if (warp == 0) {
                             uint32_t t = 0;
 #pragma unroll
                             for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
-                            const int wz = finalize_warp(P, it, ws, axis, lane, t, g.tx0, g.ty0, cur);
+                            const int wz = finalize_warp(P, R, it, ws, axis, lane, t, g.tx0, g.ty0, cur);
                             if (lane == 0) sh.winner[0] = wz;
                         }
                     } else if (((warp & 1) | ((warp >> 2) & 1)) == 0) { /* window 16: leader warp of each 2x2 warp group */
                         const uint32_t t = sh.warpTot[warp][lane] + sh.warpTot[warp + 1][lane] + sh.warpTot[warp + 4][lane] + sh.warpTot[warp + 5][lane];
                         const int wx0 = g.tx0 + (warp & 2) * 8, wy0 = g.ty0 + (warp >> 3) * 16;
                         int wz = 0;
-                        if (wx0 < P.lw && wy0 < P.lh) wz = finalize_warp(P, it, ws, axis, lane, t, wx0, wy0, cur);
+                        if (wx0 < P.lw && wy0 < P.lh) wz = finalize_warp(P, R, it, ws, axis, lane, t, wx0, wy0, cur);
                         if (lane == 0) sh.winner[(warp >> 3) * 2 + ((warp >> 1) & 1)] = wz;
                     }
                     __syncthreads();
@@ -306,19 +333,36 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                 trace_store(P, g, step, winner);
                 /* publish this level's windows (neighbours of the next level / blur) */
                 if (axis == 1 && g.m0 && g.px == (g.px & ~(ws - 1)) && g.py == (g.py & ~(ws - 1)))
-                    Tcur[(g.py >> lgw) * nwx + (g.px >> lgw)] = (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16);
+                    put_tagged(Tcur + (g.py >> lgw) * nwx + (g.px >> lgw), P.epoch, (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16));
                 HR_PARK(slot);
             }
             if (big) {
-                grid_barrier(P.bar, barTarget, nCtas);
                 slot = 0;
                 for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
                     HR_UNPARK(slot, tile);
                     const int wx = g.tx0 >> lgw, wy = g.ty0 >> lgw;
+                    /* the tiles of this window */
+                    const int tpw = ws >> 5;
+                    const int ax0 = wx * tpw, ay0 = wy * tpw;
+                    const int ax1 = hr_min(ax0 + tpw, P.tilesX) - 1, ay1 = hr_min(ay0 + tpw, P.tilesY) - 1;
+                    HR_STAMP(); /* tile total published */
+                    {
+                        /* sum the window's tile totals in a fixed order: warp w takes tiles w, w+16, ... (independent
+                         * L2 loads), lane = layer; the 16 warp sums meet in shared memory */
+                        const int wT = ax1 - ax0 + 1, nT = wT * (ay1 - ay0 + 1);
+                        const unsigned long long *ps = P.partial + P.bigOff[step] + lane;
+                        uint32_t t = 0;
+#pragma unroll 4
+                        for (int i = warp; i < nT; i += HR_NWARPS) t += get_tagged(ps + ((ay0 + i / wT) * P.tilesX + ax0 + i % wT) * HR_RMAX, P.epoch);
+                        sh.warpTot[warp][lane] = t;
+                    }
+                    __syncthreads();
                     if (warp == 0) {
                         const int cur = axis ? oy : ox;
-                        const uint32_t sad = (lane < R) ? ldcg_u32(P.bigSums + P.bigOff[step] + (wy * nwx + wx) * HR_RMAX + lane) : 0u;
-                        const int wz = finalize_warp(P, it, ws, axis, lane, sad, wx << lgw, wy << lgw, cur);
+                        uint32_t sad = 0;
+#pragma unroll
+                        for (int w = 0; w < HR_NWARPS; ++w) sad += sh.warpTot[w][lane];
+                        const int wz = finalize_warp(P, R, it, ws, axis, lane, sad, wx << lgw, wy << lgw, cur);
                         if (lane == 0) sh.winner[0] = wz;
                     }
                     __syncthreads();
@@ -327,16 +371,16 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                     else ox += P.cand[winner];
                     trace_store(P, g, step, winner);
                     if (axis == 1 && tid == 0 && g.tx0 == (wx << lgw) && g.ty0 == (wy << lgw))
-                        Tcur[wy * nwx + wx] = (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16);
+                        put_tagged(Tcur + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16));
                     HR_PARK(slot);
                     if (MULTI) __syncthreads();
                 }
             }
         }
-        const int nws = ws >> 1;
-        if (it + 1 < P.iters && (it + 1) >= HR_FIRST_NEIGHBOR_ITERATION && nws <= HR_TILE) grid_barrier(P.bar, barTarget, nCtas);
+        HR_STAMP(); /* level done */
     }
 
+    HR_STAMP(); /* search done */
     /* raw offsets (offsetArray) */
     {
         int slot = 0;
@@ -358,17 +402,17 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
 #undef HR_PARK
 
     /* ------------- blur the raw offsets (K4), reading the last level's window table --------------- */
-    grid_barrier(P.bar, barTarget, nCtas);
     {
         const int lws = P.first >> (P.iters - 1); /* = 2 */
         const int lgl = 31 - __clz(lws);
         const int lnwx = (P.lw + lws - 1) >> lgl;
-        const uint32_t *Tl = P.T + P.tOff[P.iters - 1];
+        const unsigned long long *Tl = P.T + P.tOff[P.iters - 1];
         int16_t *tX = sh.blur.tX, *tY = sh.blur.tY;
         int *hX = sh.blur.hX, *hY = sh.blur.hY;
         constexpr int NT = HR_THREADS;
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas) {
-            const int tx0 = (tile % P.tilesX) * HR_TILE, ty0 = (tile / P.tilesX) * HR_TILE;
+            const int ttx = tile % P.tilesX, tty = tile / P.tilesX;
+            const int tx0 = ttx * HR_TILE, ty0 = tty * HR_TILE;
 #pragma unroll
             for (int u = 0; u < (40 * 40 + NT - 1) / NT; ++u) {
                 const int i = tid + u * NT;
@@ -380,7 +424,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                 if (gx >= P.lw) gx = 2 * P.lw - gx - 1; else if (gx < 0) gx = -gx - 1;
                 gy = hr_min(hr_max(gy, 0), P.lh - 1);
                 gx = hr_min(hr_max(gx, 0), P.lw - 1);
-                const uint32_t v = ldcg_u32(Tl + (gy >> lgl) * lnwx + (gx >> lgl));
+                const uint32_t v = get_tagged(Tl + (gy >> lgl) * lnwx + (gx >> lgl), P.epoch);
                 tX[i] = (int16_t)(v & 0xffffu);
                 tY[i] = (int16_t)(v >> 16);
             }
@@ -414,9 +458,9 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
             }
             __syncthreads();
         }
-        /* leave the cross-CTA sums zeroed for the next launch (all consumers passed the barrier) */
-        for (int i = blockIdx.x * NT + tid; i < P.bigWords; i += nCtas * NT) P.bigSums[i] = 0u;
     }
+    HR_STAMP(); /* blur done */
+#undef HR_STAMP
 }
 
 /* Stand-alone K4 (parity tap hr_blur_flow): direct 64-tap form of blurFlowKernel.cl:80-88. */
