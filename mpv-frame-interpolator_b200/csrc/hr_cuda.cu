@@ -156,7 +156,7 @@ static int create_impl(HrContext *ctx) {
     ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
     ctx->numTiles = ctx->tilesX * ctx->tilesY;
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<0, true>, HR_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<0, true, false>, HR_THREADS, 0));
     if (perSm > 1) perSm = 1; /* one tile per SM: the search is latency-bound, spread it out */
     if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
     const int maxResident = perSm * ctx->smCount;
@@ -421,14 +421,15 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
 /* The search radius the filter uses drifts between MIN_SEARCH_RADIUS and MAX_SEARCH_RADIUS
  * (config.h:6-7, vf_HopperRender.c:326-345): those radii get a kernel with the layer loop fully
  * unrolled and the layer shifts as immediates; any other radius runs the generic kernel. */
-static const void *search_kernel_for(int R, int multi) {
-    if (multi) return (const void *)flow_search_kernel<0, true>;
+static const void *search_kernel_for(int R, int multi, int timeline) {
+    if (multi) return (const void *)flow_search_kernel<0, true, false>;
+    if (timeline) return R == 5 ? (const void *)flow_search_kernel<5, false, true> : (const void *)flow_search_kernel<0, false, true>;
     switch (R) {
-#define HR_RCASE(r) case r: return (const void *)flow_search_kernel<r, false>;
+#define HR_RCASE(r) case r: return (const void *)flow_search_kernel<r, false, false>;
         HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
         HR_RCASE(13) HR_RCASE(14) HR_RCASE(15) HR_RCASE(16)
 #undef HR_RCASE
-        default: return (const void *)flow_search_kernel<0, false>;
+        default: return (const void *)flow_search_kernel<0, false, false>;
     }
 }
 
@@ -474,7 +475,7 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     P.timeline = ctx->timelineOn ? ctx->timeline : NULL;
     void *args[] = {&P};
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
-    const void *kfn = search_kernel_for(searchRadius, ctx->multiTile);
+    const void *kfn = search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn);
     CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, ctx->stream));
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], ctx->stream));

@@ -16,15 +16,19 @@
  *     scores the layers itself. No shared memory, no block barrier.
  *   - Windows 16 / 32: warp REDUX totals meet in shared memory; one warp per window scores the
  *     layers (lane = layer). Two block barriers per step.
- *   - Windows >= 64 span CTAs: tile totals meet in L2 (red.add) + one grid barrier per step.
- *   - Neighbour bias (iteration >= 4) reads the previous level's window table from L2; one grid
- *     barrier per level orders it.
+ *   - Windows >= 64 span CTAs: every tile publishes its totals, every tile of the window sums them in
+ *     a fixed order. Neighbour bias (iteration >= 4) and the blur halo read the previous level's
+ *     window table of the adjacent tiles. Both hand-offs go through epoch-tagged 64-bit words in L2
+ *     (hr_common.cuh): no grid barrier, no atomics, a CTA only waits for the words it reads.
+ *   - Every step is compiled for its window class and axis (templates), and for the search radii
+ *     the filter uses (5..16) with the layer loop unrolled and the layer shifts as immediates.
  *   - Every evaluation is one 32-bit load from the phase-planar packed frame (hr_pack.cuh) and one
  *     VABSDIFF4.U8.ACC; both biases are added once per window as count*bias (mod 2^32 — exact,
  *     because every point of a window shares offset and neighbours).
  */
 #pragma once
 #include "hr_common.cuh"
+#include <type_traits>
 
 #define HR_THREADS 512      /* threads per CTA                                 */
 #define HR_NWARPS 16        /* warps per CTA = 8x8 blocks per tile             */
@@ -88,25 +92,6 @@ __device__ __forceinline__ void neighbour_axis(const uint32_t (&nw)[4], int axis
     for (int i = 0; i < 4; ++i) n[i] = axis ? ((int)nw[i] >> 16) : (int)(int16_t)nw[i];
 }
 
-/* Per-thread geometry inside a tile */
-struct TileGeom {
-    int tx0, ty0;         /* lattice origin of the tile                                    */
-    int px, py;           /* lattice position of the thread's upper point (clamped)         */
-    uint32_t m0, m1;      /* all-ones if the upper / lower point is inside the lattice      */
-};
-__device__ __forceinline__ TileGeom tile_geom(const FlowParams &P, int tile, int warp, int lane) {
-    TileGeom g;
-    g.tx0 = (tile % P.tilesX) * HR_TILE;
-    g.ty0 = (tile / P.tilesX) * HR_TILE;
-    const int x = g.tx0 + (warp & 3) * 8 + (lane & 7);
-    const int y = g.ty0 + (warp >> 2) * 8 + (lane >> 3) * 2;
-    g.m0 = (x < P.lw && y < P.lh) ? 0xffffffffu : 0u;
-    g.m1 = (x < P.lw && y + 1 < P.lh) ? 0xffffffffu : 0u;
-    g.px = x;
-    g.py = y;
-    return g;
-}
-
 /* Layer shift of layer z: calcDeltaSumsKernel.cl:68-72. RT > 0: search radius known at compile time. */
 template <int RT>
 __device__ __forceinline__ int layer_shift(const FlowParams &P, int z) {
@@ -117,44 +102,17 @@ __device__ __forceinline__ int layer_shift(const FlowParams &P, int z) {
     return P.cand[z];
 }
 
-/* SAD of the thread's two points for layers z0 .. z0+HR_ZCHUNK-1 (those below R) of one search step.
- * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
- * INTERIOR (warp-uniform): no layer of any lane leaves the frame on the searched axis -> no mirror. */
-template <int RT, bool INTERIOR>
-__device__ __forceinline__ void eval_chunk(const FlowParams &P, int R, int axis, int fa, int fb, int ma, int mb, uint32_t m0, uint32_t m1, uint32_t v2a,
-                                           uint32_t v2b, int z0, uint32_t (&acc)[HR_ZCHUNK]) {
-    const int s = P.s, m = (1 << s) - 1;
-    const int mulA = axis ? (P.planeSize << s) : P.planeSize;
-    const int mulB = axis ? P.planePitch : 1;
-    const int D = axis ? P.H : P.W;
-    uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
-#pragma unroll
-    for (int j = 0; j < HR_ZCHUNK; ++j) {
-        if (z0 + j < R) {
-            const int c = layer_shift<RT>(P, z0 + j);
-            int pa = ma + c, pb = mb + c;
-            if (!INTERIOR) {
-                pa = search_mirror(pa, D);
-                pb = search_mirror(pb, D);
-            }
-            va[j] = __ldg(P.p1 + (fa + (pa & m) * mulA + (pa >> s) * mulB));
-            vb[j] = __ldg(P.p1 + (fb + (pb & m) * mulA + (pb >> s) * mulB));
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < HR_ZCHUNK; ++j)
-        if (z0 + j < R) acc[j] = sad4_acc(vb[j] & m1, v2b, sad4_acc(va[j] & m0, v2a, 0u));
-}
-
-/* Executed by one full warp: lane z holds the window's SAD for layer z; returns the winner. */
-__device__ __forceinline__ int finalize_warp(const FlowParams &P, int R, int it, int ws, int axis, int lane, uint32_t sad, int x0, int y0, int cur) {
+/* Executed by one full warp: lane z holds the window's SAD for layer z; returns the winner.
+ * nw: the window's four neighbour words (loaded on the first axis step of a level, reused on the second). */
+template <int AXIS>
+__device__ __forceinline__ int finalize_warp(const FlowParams &P, int R, int it, int ws, int lane, uint32_t sad, int x0, int y0, int cur, bool loadNb,
+                                             uint32_t (&nw)[4]) {
     const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
     const uint32_t count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
     int n[4] = {0, 0, 0, 0};
     if (useNb) {
-        uint32_t nw[4];
-        load_neighbours(P, it, ws, x0, y0, nw);
-        neighbour_axis(nw, axis, n);
+        if (loadNb) load_neighbours(P, it, ws, x0, y0, nw);
+        neighbour_axis(nw, AXIS, n);
     }
     const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, n, P.dS, P.nS) : 0xffffffffu;
     const uint32_t mn = __reduce_min_sync(0xffffffffu, S);
@@ -162,244 +120,360 @@ __device__ __forceinline__ int finalize_warp(const FlowParams &P, int R, int it,
     return __ffs(ballot) - 1;
 }
 
-__device__ __forceinline__ void trace_store(const FlowParams &P, const TileGeom &g, int step, int winner) {
+/* Everything a thread carries: its place in the tile and the search state of its two points. */
+struct Thr {
+    int tile, tx0, ty0;   /* owned tile and its lattice origin                                        */
+    int px, py;           /* lattice position of the upper point; the lower one is (px, py+1)           */
+    uint32_t m0, m1;      /* all-ones if the upper / lower point is inside the lattice                  */
+    int cxs, cy0s, cy1s;  /* full-resolution coordinates of the (clamped) points: lattice << s          */
+    int ox, oy;           /* the offset pair both points share                                         */
+    uint32_t v2a, v2b;    /* frame2 words of the two points (0 when outside)                            */
+    uint32_t nw[4];       /* neighbour words of the current level                                      */
+};
+__device__ __forceinline__ void thr_place(const FlowParams &P, Thr &t, int tile, int warp, int lane) {
+    t.tile = tile;
+    t.tx0 = (tile % P.tilesX) * HR_TILE;
+    t.ty0 = (tile / P.tilesX) * HR_TILE;
+    t.px = t.tx0 + (warp & 3) * 8 + (lane & 7);
+    t.py = t.ty0 + (warp >> 2) * 8 + (lane >> 3) * 2;
+    t.m0 = (t.px < P.lw && t.py < P.lh) ? 0xffffffffu : 0u;
+    t.m1 = (t.px < P.lw && t.py + 1 < P.lh) ? 0xffffffffu : 0u;
+    t.cxs = hr_min(t.px, P.lw - 1) << P.s;
+    t.cy0s = hr_min(t.py, P.lh - 1) << P.s;
+    t.cy1s = hr_min(t.py + 1, P.lh - 1) << P.s;
+}
+
+__device__ __forceinline__ void trace_store(const FlowParams &P, const Thr &t, int step, int winner) {
     if (P.trace) {
-        if (g.m0) P.trace[((size_t)step * P.lh + g.py) * P.lw + g.px] = (uint8_t)winner;
-        if (g.m1) P.trace[((size_t)step * P.lh + g.py + 1) * P.lw + g.px] = (uint8_t)winner;
+        if (t.m0) P.trace[((size_t)step * P.lh + t.py) * P.lw + t.px] = (uint8_t)winner;
+        if (t.m1) P.trace[((size_t)step * P.lh + t.py + 1) * P.lw + t.px] = (uint8_t)winner;
     }
 }
 
-template <int RT, bool MULTI>
+/* One search step of one tile. WS: 2, 4, 8 (warp-local windows), 16, 32 (tile-local) or 64 (= any
+ * window larger than a tile; the real size is `ws`). AXIS 0: the layers move x, 1: y.
+ * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
+ * For WS = 64 the step only publishes the tile's totals; big_finish() scores them. */
+template <int RT, int WS, int AXIS>
+__device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp) {
+    constexpr bool small = WS <= 8;
+    const int R = RT > 0 ? RT : P.R;
+    const int s = P.s, m = (1 << s) - 1;
+    const int step = it * 2 + AXIS;
+    const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
+    const int cur = AXIS ? t.oy : t.ox;
+
+    /* the thread's own window (warp-local levels): population; its neighbours are fetched further down,
+     * after the sample loads have been issued */
+    uint32_t count = 0;
+    int nb[4] = {0, 0, 0, 0};
+    const int x0 = t.px & ~(WS - 1), y0 = t.py & ~(WS - 1);
+    const bool ownWindow = small && x0 < P.lw && y0 < P.lh;
+    if (ownWindow) count = (uint32_t)(hr_min(x0 + WS, P.lw) - x0) * (uint32_t)(hr_min(y0 + WS, P.lh) - y0);
+
+    /* sample addressing: the fixed part (the axis that does not move) and the moving coordinate before
+     * the layer shift, for the upper (a) and lower (b) point */
+    int fa, fb, ma, mb;
+    if (AXIS == 0) {
+        const int ya = search_mirror(t.cy0s + t.oy, P.H), yb = search_mirror(t.cy1s + t.oy, P.H);
+        fa = ((ya & m) << s) * P.planeSize + (ya >> s) * P.planePitch;
+        fb = ((yb & m) << s) * P.planeSize + (yb >> s) * P.planePitch;
+        ma = mb = t.cxs + t.ox;
+    } else {
+        const int x = search_mirror(t.cxs + t.ox, P.W);
+        fa = fb = (x & m) * P.planeSize + (x >> s);
+        ma = t.cy0s + t.oy;
+        mb = t.cy1s + t.oy;
+    }
+    const int D = AXIS ? P.H : P.W;
+    const int mulA = AXIS ? (P.planeSize << s) : P.planeSize;
+    /* warp-uniform: no layer of any lane leaves the frame on the searched axis -> no mirror */
+    const bool interior = __all_sync(0xffffffffu, ma + layer_shift<RT>(P, 0) >= 0 && mb + layer_shift<RT>(P, R - 1) < D);
+
+    uint32_t bestS = 0xffffffffu, mine = 0u;
+    int winner = 0;
+    auto issue = [&](int z0, uint32_t (&va)[HR_ZCHUNK], uint32_t (&vb)[HR_ZCHUNK]) {
+#pragma unroll
+        for (int j = 0; j < HR_ZCHUNK; ++j) {
+            if (z0 + j < R) {
+                const int c = layer_shift<RT>(P, z0 + j);
+                int pa = ma + c, pb = mb + c;
+                if (!interior) {
+                    pa = search_mirror(pa, D);
+                    if (AXIS) pb = search_mirror(pb, D);
+                }
+                if (AXIS == 0) {
+                    const int xi = (pa & m) * mulA + (pa >> s);
+                    va[j] = __ldg(P.p1 + (fa + xi));
+                    vb[j] = __ldg(P.p1 + (fb + xi));
+                } else {
+                    va[j] = __ldg(P.p1 + (fa + (pa & m) * mulA + (pa >> s) * P.planePitch));
+                    vb[j] = __ldg(P.p1 + (fb + (pb & m) * mulA + (pb >> s) * P.planePitch));
+                }
+            }
+        }
+    };
+    auto consume = [&](int z0, const uint32_t (&va)[HR_ZCHUNK], const uint32_t (&vb)[HR_ZCHUNK]) {
+#pragma unroll
+        for (int j = 0; j < HR_ZCHUNK; ++j) {
+            if (z0 + j < R) {
+                uint32_t a = sad4_acc(vb[j] & t.m1, t.v2b, sad4_acc(va[j] & t.m0, t.v2a, 0u));
+                if (WS >= 8) {
+                    a = __reduce_add_sync(0xffffffffu, a);
+                } else {
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    if (WS == 4) {
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    }
+                }
+                if (small) {
+                    /* first-minimum scan, determineLowestLayerKernel.cl:13-18 */
+                    const uint32_t S = window_total(a, layer_shift<RT>(P, z0 + j), cur, count, useNb, nb, P.dS, P.nS);
+                    if (z0 + j == 0 || S < bestS) {
+                        bestS = S;
+                        winner = z0 + j;
+                    }
+                } else if (lane == z0 + j) {
+                    mine = a;
+                }
+            }
+        }
+    };
+    /* the neighbour words of the level (first axis step only; the second reuses them). They come from
+     * the adjacent tiles and may still be in flight: poll them only after this step's sample loads have
+     * been issued. Windows 16 / 32: the warp that will score the window fetches them. */
+    bool scorer = false;
+    int sx0 = 0, sy0 = 0;
+    if (WS == HR_TILE) {
+        scorer = warp == 0;
+        sx0 = t.tx0;
+        sy0 = t.ty0;
+    } else if (WS == 16) {
+        sx0 = t.tx0 + (warp & 2) * 8;
+        sy0 = t.ty0 + (warp >> 3) * 16;
+        scorer = ((warp & 1) | ((warp >> 2) & 1)) == 0 && sx0 < P.lw && sy0 < P.lh;
+    }
+    auto fetch_neighbours = [&]() {
+        if (useNb && AXIS == 0) {
+            if (small) {
+                if (ownWindow) load_neighbours(P, it, WS, x0, y0, t.nw);
+            } else if (WS <= HR_TILE) {
+                if (scorer) load_neighbours(P, it, WS, sx0, sy0, t.nw);
+            }
+        }
+        if (small && useNb) neighbour_axis(t.nw, AXIS, nb);
+    };
+    if constexpr (RT > 0) {
+        uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
+        issue(0, va, vb);
+        fetch_neighbours();
+        consume(0, va, vb);
+#pragma unroll
+        for (int z0 = HR_ZCHUNK; z0 < RT; z0 += HR_ZCHUNK) {
+            uint32_t wa[HR_ZCHUNK], wb[HR_ZCHUNK];
+            issue(z0, wa, wb);
+            consume(z0, wa, wb);
+        }
+    } else {
+        uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
+        issue(0, va, vb);
+        fetch_neighbours();
+        consume(0, va, vb);
+#pragma unroll 1
+        for (int z0 = HR_ZCHUNK; z0 < R; z0 += HR_ZCHUNK) {
+            issue(z0, va, vb);
+            consume(z0, va, vb);
+        }
+    }
+
+    if (!small) {
+        sh.warpTot[warp][lane] = mine;
+        __syncthreads();
+        if (WS > HR_TILE) {
+            if (warp == 0) {
+                uint32_t tt = 0;
+#pragma unroll
+                for (int w = 0; w < HR_NWARPS; ++w) tt += sh.warpTot[w][lane];
+                put_tagged(P.partial + P.bigOff[step] + t.tile * HR_RMAX + lane, P.epoch, tt);
+            }
+            __syncthreads(); /* warpTot is reused by big_finish */
+            return;
+        }
+        if (WS == HR_TILE) {
+            if (warp == 0) {
+                uint32_t tt = 0;
+#pragma unroll
+                for (int w = 0; w < HR_NWARPS; ++w) tt += sh.warpTot[w][lane];
+                const int wz = finalize_warp<AXIS>(P, R, it, WS, lane, tt, t.tx0, t.ty0, cur, false, t.nw);
+                if (lane == 0) sh.winner[0] = wz;
+            }
+        } else if (((warp & 1) | ((warp >> 2) & 1)) == 0) { /* window 16: leader warp of each 2x2 warp group */
+            const uint32_t tt = sh.warpTot[warp][lane] + sh.warpTot[warp + 1][lane] + sh.warpTot[warp + 4][lane] + sh.warpTot[warp + 5][lane];
+            int wz = 0;
+            if (scorer) wz = finalize_warp<AXIS>(P, R, it, WS, lane, tt, sx0, sy0, cur, false, t.nw);
+            if (lane == 0) sh.winner[(warp >> 3) * 2 + ((warp >> 1) & 1)] = wz;
+        }
+        __syncthreads();
+        winner = sh.winner[WS == HR_TILE ? 0 : (warp >> 3) * 2 + ((warp >> 1) & 1)];
+    }
+    if (AXIS) t.oy += P.cand[winner];
+    else t.ox += P.cand[winner];
+    trace_store(P, t, step, winner);
+    /* publish this level's windows (neighbours of the next level / blur) */
+    if (AXIS == 1 && t.m0 && (t.px & (WS - 1)) == 0 && (t.py & (WS - 1)) == 0) {
+        const int lgw = 31 - __clz(WS), nwx = (P.lw + WS - 1) >> lgw;
+        put_tagged(P.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw), P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
+    }
+}
+
+/* Second half of a step whose windows span several tiles: sum the totals of the window's tiles in a
+ * fixed order (warp w takes tiles w, w+16, ... — independent L2 loads, lane = layer) and score. */
+template <int RT, int AXIS>
+__device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp, bool loadNb) {
+    const int R = RT > 0 ? RT : P.R;
+    const int step = it * 2 + AXIS;
+    const int lgw = 31 - __clz(ws), nwx = (P.lw + ws - 1) >> lgw;
+    const int wx = t.tx0 >> lgw, wy = t.ty0 >> lgw;
+    const int lgt = lgw - 5, tpw = 1 << lgt;                     /* tiles per window side */
+    const int ax0 = wx << lgt, ay0 = wy << lgt;
+    const unsigned long long *ps = P.partial + P.bigOff[step] + lane;
+    uint32_t tt = 0;
+    for (int i0 = warp; i0 < tpw * tpw; i0 += 4 * HR_NWARPS) {
+        /* up to four tile totals per pass: issue the loads together, then re-load the ones whose tag is stale */
+        const unsigned long long *q[4];
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * HR_NWARPS;
+            const int tx = ax0 + (i & (tpw - 1)), ty = ay0 + (i >> lgt);
+            q[k] = (i < tpw * tpw && tx < P.tilesX && ty < P.tilesY) ? ps + (ty * P.tilesX + tx) * HR_RMAX : nullptr;
+            v[k] = q[k] ? ld_relaxed_u64(q[k]) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (q[k]) {
+                while ((uint32_t)(v[k] >> 32) != P.epoch) v[k] = ld_relaxed_u64(q[k]);
+                tt += (uint32_t)v[k];
+            }
+        }
+    }
+    sh.warpTot[warp][lane] = tt;
+    __syncthreads();
+    if (warp == 0) {
+        const int cur = AXIS ? t.oy : t.ox;
+        uint32_t sad = 0;
+#pragma unroll
+        for (int w = 0; w < HR_NWARPS; ++w) sad += sh.warpTot[w][lane];
+        const int wz = finalize_warp<AXIS>(P, R, it, ws, lane, sad, wx << lgw, wy << lgw, cur, loadNb, t.nw);
+        if (lane == 0) sh.winner[0] = wz;
+    }
+    __syncthreads();
+    const int winner = sh.winner[0];
+    if (AXIS) t.oy += P.cand[winner];
+    else t.ox += P.cand[winner];
+    trace_store(P, t, step, winner);
+    if (AXIS == 1 && threadIdx.x == 0 && t.tx0 == (wx << lgw) && t.ty0 == (wy << lgw))
+        put_tagged(P.T + P.tOff[it] + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
+}
+
+template <int RT, bool MULTI, bool DBG>
 __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowParams P) {
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nCtas = gridDim.x;
-    const int R = RT > 0 ? RT : P.R;
-    const int s = P.s, m = (1 << s) - 1;
     const size_t ln = (size_t)P.lw * P.lh;
     int stampIdx = 0;
-#define HR_STAMP()                                                                                         \
-    if (P.timeline && tid == 0 && stampIdx < HR_TIMELINE_SLOTS) P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + stampIdx++] = clock64();
+#define HR_STAMP() \
+    if (DBG && P.timeline && tid == 0 && stampIdx < HR_TIMELINE_SLOTS) P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + stampIdx++] = clock64();
     HR_STAMP();
+    if (DBG && P.timeline && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + HR_TIMELINE_SLOTS - 2] = (long long)gt;
+    }
 
-    /* per-thread state of the owned tile: offset pair and the two frame2 words */
-    int ox = 0, oy = 0;
-    uint32_t v2a = 0, v2b = 0;
-    TileGeom g = tile_geom(P, blockIdx.x, warp, lane);
-
-    auto load_frame2 = [&](const TileGeom &gg) {
-        const int cx = hr_min(gg.px, P.lw - 1);
-        v2a = __ldg(P.p2 + hr_min(gg.py, P.lh - 1) * P.planePitch + cx) & gg.m0;
-        v2b = __ldg(P.p2 + hr_min(gg.py + 1, P.lh - 1) * P.planePitch + cx) & gg.m1;
+    Thr t;
+    t.ox = t.oy = 0;
+    t.nw[0] = t.nw[1] = t.nw[2] = t.nw[3] = 0u;
+    auto load_frame2 = [&]() {
+        t.v2a = __ldg(P.p2 + (t.cy0s >> P.s) * P.planePitch + (t.cxs >> P.s)) & t.m0;
+        t.v2b = __ldg(P.p2 + (t.cy1s >> P.s) * P.planePitch + (t.cxs >> P.s)) & t.m1;
     };
     if (!MULTI) {
-        load_frame2(g);
+        thr_place(P, t, blockIdx.x, warp, lane);
+        load_frame2();
     } else {
         int slot = 0;
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-            g = tile_geom(P, tile, warp, lane);
-            load_frame2(g);
-            sh.parked[slot][tid] = make_int4(0, 0, (int)v2a, (int)v2b);
+            thr_place(P, t, tile, warp, lane);
+            load_frame2();
+            sh.parked[slot][tid] = make_int4(0, 0, (int)t.v2a, (int)t.v2b);
         }
     }
-#define HR_UNPARK(slot_, tile_)                                   \
-    if (MULTI) {                                                  \
-        g = tile_geom(P, tile_, warp, lane);                      \
-        const int4 st_ = sh.parked[slot_][tid];                   \
-        ox = st_.x; oy = st_.y; v2a = (uint32_t)st_.z; v2b = (uint32_t)st_.w; \
-    }
-#define HR_PARK(slot_) \
-    if (MULTI) sh.parked[slot_][tid] = make_int4(ox, oy, (int)v2a, (int)v2b);
-
-    for (int it = 0; it < P.iters; ++it) {
-        const int ws = P.first >> it;
-        const int lgw = 31 - __clz(ws);
-        const int nwx = (P.lw + ws - 1) >> lgw;
-        unsigned long long *Tcur = P.T + P.tOff[it];
-        const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
-        const bool small = ws <= 8;      /* warp-local windows                         */
-        const bool big = ws > HR_TILE;   /* windows spanning several tiles (CTAs)      */
-        uint32_t nw[4] = {0u, 0u, 0u, 0u};
-
-        for (int axis = 0; axis < 2; ++axis) {
-            const int step = it * 2 + axis;
-            int slot = 0;
-            for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-                HR_UNPARK(slot, tile);
-                HR_STAMP(); /* step start (after the neighbour-table wait) */
-                const int cur = axis ? oy : ox;
-                /* the thread's own window (warp-local levels only) */
-                const int x0 = g.px & ~(ws - 1), y0 = g.py & ~(ws - 1);
-                uint32_t count = 0;
-                int nb[4] = {0, 0, 0, 0};
-                if (small) {
-                    if (x0 < P.lw && y0 < P.lh) {
-                        count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
-                        if (useNb && (axis == 0 || MULTI)) load_neighbours(P, it, ws, x0, y0, nw);
-                    }
-                    neighbour_axis(nw, axis, nb);
-                }
-                /* sample addressing of this step: fixed part (the axis that does not move) and the moving
-                 * coordinate before the layer shift, for the upper (a) and lower (b) point */
-                const int cx = hr_min(g.px, P.lw - 1), cy0 = hr_min(g.py, P.lh - 1), cy1 = hr_min(g.py + 1, P.lh - 1);
-                int fa, fb, ma, mb;
-                if (axis == 0) {
-                    const int ya = search_mirror((cy0 << s) + oy, P.H), yb = search_mirror((cy1 << s) + oy, P.H);
-                    fa = ((ya & m) << s) * P.planeSize + (ya >> s) * P.planePitch;
-                    fb = ((yb & m) << s) * P.planeSize + (yb >> s) * P.planePitch;
-                    ma = mb = (cx << s) + ox;
-                } else {
-                    const int x = search_mirror((cx << s) + ox, P.W);
-                    fa = fb = (x & m) * P.planeSize + (x >> s);
-                    ma = (cy0 << s) + oy;
-                    mb = (cy1 << s) + oy;
-                }
-                const int cmin = layer_shift<RT>(P, 0), cmax = layer_shift<RT>(P, R - 1);
-                const bool interior = __all_sync(0xffffffffu, hr_min(ma, mb) + cmin >= 0 && hr_max(ma, mb) + cmax < (axis ? P.H : P.W));
-
-                uint32_t bestS = 0xffffffffu, mine = 0u;
-                int winner = 0;
-                auto do_chunk = [&](int z0) {
-                    uint32_t acc[HR_ZCHUNK];
-                    if (interior) eval_chunk<RT, true>(P, R, axis, fa, fb, ma, mb, g.m0, g.m1, v2a, v2b, z0, acc);
-                    else eval_chunk<RT, false>(P, R, axis, fa, fb, ma, mb, g.m0, g.m1, v2a, v2b, z0, acc);
-#pragma unroll
-                    for (int j = 0; j < HR_ZCHUNK; ++j) {
-                        if (z0 + j < R) {
-                            uint32_t a = acc[j];
-                            if (ws >= 8) {
-                                a = __reduce_add_sync(0xffffffffu, a);
-                            } else {
-                                a += __shfl_xor_sync(0xffffffffu, a, 1);
-                                if (ws == 4) {
-                                    a += __shfl_xor_sync(0xffffffffu, a, 2);
-                                    a += __shfl_xor_sync(0xffffffffu, a, 8);
-                                }
-                            }
-                            if (small) {
-                                /* first-minimum scan, determineLowestLayerKernel.cl:13-18 */
-                                const uint32_t S = window_total(a, layer_shift<RT>(P, z0 + j), cur, count, useNb, nb, P.dS, P.nS);
-                                if (z0 + j == 0 || S < bestS) {
-                                    bestS = S;
-                                    winner = z0 + j;
-                                }
-                            } else if (lane == z0 + j) {
-                                mine = a;
-                            }
-                        }
-                    }
-                };
-                if constexpr (RT > 0) {
-#pragma unroll
-                    for (int z0 = 0; z0 < RT; z0 += HR_ZCHUNK) do_chunk(z0);
-                } else {
-#pragma unroll 1
-                    for (int z0 = 0; z0 < R; z0 += HR_ZCHUNK) do_chunk(z0);
-                }
-                HR_STAMP(); /* layers evaluated and reduced */
-                if (!small) {
-                    sh.warpTot[warp][lane] = mine;
-                    __syncthreads();
-                    if (big) {
-                        if (warp == 0) {
-                            uint32_t t = 0;
-#pragma unroll
-                            for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
-                            put_tagged(P.partial + P.bigOff[step] + tile * HR_RMAX + lane, P.epoch, t);
-                        }
-                        __syncthreads(); /* warpTot is reused below */
-                        continue; /* scored below, from the totals of all tiles of the window */
-                    }
-                    if (ws == HR_TILE) {
-                        if (warp == 0) {
-                            uint32_t t = 0;
-#pragma unroll
-                            for (int w = 0; w < HR_NWARPS; ++w) t += sh.warpTot[w][lane];
-                            const int wz = finalize_warp(P, R, it, ws, axis, lane, t, g.tx0, g.ty0, cur);
-                            if (lane == 0) sh.winner[0] = wz;
-                        }
-                    } else if (((warp & 1) | ((warp >> 2) & 1)) == 0) { /* window 16: leader warp of each 2x2 warp group */
-                        const uint32_t t = sh.warpTot[warp][lane] + sh.warpTot[warp + 1][lane] + sh.warpTot[warp + 4][lane] + sh.warpTot[warp + 5][lane];
-                        const int wx0 = g.tx0 + (warp & 2) * 8, wy0 = g.ty0 + (warp >> 3) * 16;
-                        int wz = 0;
-                        if (wx0 < P.lw && wy0 < P.lh) wz = finalize_warp(P, R, it, ws, axis, lane, t, wx0, wy0, cur);
-                        if (lane == 0) sh.winner[(warp >> 3) * 2 + ((warp >> 1) & 1)] = wz;
-                    }
-                    __syncthreads();
-                    winner = sh.winner[ws == HR_TILE ? 0 : (warp >> 3) * 2 + ((warp >> 1) & 1)];
-                }
-                if (axis) oy += P.cand[winner];
-                else ox += P.cand[winner];
-                trace_store(P, g, step, winner);
-                /* publish this level's windows (neighbours of the next level / blur) */
-                if (axis == 1 && g.m0 && g.px == (g.px & ~(ws - 1)) && g.py == (g.py & ~(ws - 1)))
-                    put_tagged(Tcur + (g.py >> lgw) * nwx + (g.px >> lgw), P.epoch, (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16));
-                HR_PARK(slot);
-            }
-            if (big) {
-                slot = 0;
-                for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-                    HR_UNPARK(slot, tile);
-                    const int wx = g.tx0 >> lgw, wy = g.ty0 >> lgw;
-                    /* the tiles of this window */
-                    const int tpw = ws >> 5;
-                    const int ax0 = wx * tpw, ay0 = wy * tpw;
-                    const int ax1 = hr_min(ax0 + tpw, P.tilesX) - 1, ay1 = hr_min(ay0 + tpw, P.tilesY) - 1;
-                    HR_STAMP(); /* tile total published */
-                    {
-                        /* sum the window's tile totals in a fixed order: warp w takes tiles w, w+16, ... (independent
-                         * L2 loads), lane = layer; the 16 warp sums meet in shared memory */
-                        const int wT = ax1 - ax0 + 1, nT = wT * (ay1 - ay0 + 1);
-                        const unsigned long long *ps = P.partial + P.bigOff[step] + lane;
-                        uint32_t t = 0;
-#pragma unroll 4
-                        for (int i = warp; i < nT; i += HR_NWARPS) t += get_tagged(ps + ((ay0 + i / wT) * P.tilesX + ax0 + i % wT) * HR_RMAX, P.epoch);
-                        sh.warpTot[warp][lane] = t;
-                    }
-                    __syncthreads();
-                    if (warp == 0) {
-                        const int cur = axis ? oy : ox;
-                        uint32_t sad = 0;
-#pragma unroll
-                        for (int w = 0; w < HR_NWARPS; ++w) sad += sh.warpTot[w][lane];
-                        const int wz = finalize_warp(P, R, it, ws, axis, lane, sad, wx << lgw, wy << lgw, cur);
-                        if (lane == 0) sh.winner[0] = wz;
-                    }
-                    __syncthreads();
-                    const int winner = sh.winner[0];
-                    if (axis) oy += P.cand[winner];
-                    else ox += P.cand[winner];
-                    trace_store(P, g, step, winner);
-                    if (axis == 1 && tid == 0 && g.tx0 == (wx << lgw) && g.ty0 == (wy << lgw))
-                        put_tagged(Tcur + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)ox | ((uint32_t)(uint16_t)oy << 16));
-                    HR_PARK(slot);
-                    if (MULTI) __syncthreads();
-                }
-            }
-        }
-        HR_STAMP(); /* level done */
-    }
-
-    HR_STAMP(); /* search done */
-    /* raw offsets (offsetArray) */
-    {
+    /* a CTA that owns several tiles (MULTI) parks the per-thread state of each in shared memory */
+    auto for_tiles = [&](auto body) {
         int slot = 0;
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-            HR_UNPARK(slot, tile);
-            if (g.m0) {
-                const size_t idx = (size_t)g.py * P.lw + g.px;
-                P.off[idx] = (int16_t)ox;
-                P.off[ln + idx] = (int16_t)oy;
+            if (MULTI) {
+                thr_place(P, t, tile, warp, lane);
+                const int4 st = sh.parked[slot][tid];
+                t.ox = st.x;
+                t.oy = st.y;
+                t.v2a = (uint32_t)st.z;
+                t.v2b = (uint32_t)st.w;
             }
-            if (g.m1) {
-                const size_t idx = (size_t)(g.py + 1) * P.lw + g.px;
-                P.off[idx] = (int16_t)ox;
-                P.off[ln + idx] = (int16_t)oy;
+            body();
+            if (MULTI) {
+                sh.parked[slot][tid] = make_int4(t.ox, t.oy, (int)t.v2a, (int)t.v2b);
+                __syncthreads();
             }
         }
+    };
+    auto level = [&](auto wsTag, int it, int ws) {
+        constexpr int WS = decltype(wsTag)::value;
+        if constexpr (WS > HR_TILE) {
+            for_tiles([&] { search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp); });
+            HR_STAMP();
+            for_tiles([&] { big_finish<RT, 0>(P, sh, t, it, ws, lane, warp, true); });
+            HR_STAMP();
+            for_tiles([&] { search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp); });
+            HR_STAMP();
+            for_tiles([&] { big_finish<RT, 1>(P, sh, t, it, ws, lane, warp, MULTI); });
+            HR_STAMP();
+        } else {
+            for_tiles([&] {
+                search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp);
+                HR_STAMP();
+                search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp);
+                HR_STAMP();
+            });
+        }
+    };
+    for (int it = 0; it < P.iters; ++it) {
+        const int ws = P.first >> it;
+        if (ws > HR_TILE) level(std::integral_constant<int, 64>(), it, ws);
+        else if (ws == 32) level(std::integral_constant<int, 32>(), it, ws);
+        else if (ws == 16) level(std::integral_constant<int, 16>(), it, ws);
+        else if (ws == 8) level(std::integral_constant<int, 8>(), it, ws);
+        else if (ws == 4) level(std::integral_constant<int, 4>(), it, ws);
+        else level(std::integral_constant<int, 2>(), it, ws);
     }
-#undef HR_UNPARK
-#undef HR_PARK
+    HR_STAMP(); /* search done */
+
+    /* raw offsets (offsetArray) */
+    for_tiles([&] {
+        if (t.m0) {
+            const size_t idx = (size_t)t.py * P.lw + t.px;
+            P.off[idx] = (int16_t)t.ox;
+            P.off[ln + idx] = (int16_t)t.oy;
+        }
+        if (t.m1) {
+            const size_t idx = (size_t)(t.py + 1) * P.lw + t.px;
+            P.off[idx] = (int16_t)t.ox;
+            P.off[ln + idx] = (int16_t)t.oy;
+        }
+    });
 
     /* ------------- blur the raw offsets (K4), reading the last level's window table --------------- */
     {
@@ -413,20 +487,36 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas) {
             const int ttx = tile % P.tilesX, tty = tile / P.tilesX;
             const int tx0 = ttx * HR_TILE, ty0 = tty * HR_TILE;
+            {
+                constexpr int NU = (40 * 40 + NT - 1) / NT;
+                const unsigned long long *q[NU];
+                unsigned long long v[NU];
 #pragma unroll
-            for (int u = 0; u < (40 * 40 + NT - 1) / NT; ++u) {
-                const int i = tid + u * NT;
-                if (i >= 40 * 40) break;
-                const int r = i / 40, c = i - r * 40;
-                int gy = ty0 - 4 + r, gx = tx0 - 4 + c;
-                /* blurFlowKernel.cl:5-12 mirror, clamped for lattices smaller than the halo */
-                if (gy >= P.lh) gy = 2 * P.lh - gy - 1; else if (gy < 0) gy = -gy - 1;
-                if (gx >= P.lw) gx = 2 * P.lw - gx - 1; else if (gx < 0) gx = -gx - 1;
-                gy = hr_min(hr_max(gy, 0), P.lh - 1);
-                gx = hr_min(hr_max(gx, 0), P.lw - 1);
-                const uint32_t v = get_tagged(Tl + (gy >> lgl) * lnwx + (gx >> lgl), P.epoch);
-                tX[i] = (int16_t)(v & 0xffffu);
-                tY[i] = (int16_t)(v >> 16);
+                for (int u = 0; u < NU; ++u) {
+                    const int i = tid + u * NT;
+                    q[u] = nullptr;
+                    v[u] = 0ull;
+                    if (i < 40 * 40) {
+                        const int r = i / 40, c = i - r * 40;
+                        int gy = ty0 - 4 + r, gx = tx0 - 4 + c;
+                        /* blurFlowKernel.cl:5-12 mirror, clamped for lattices smaller than the halo */
+                        if (gy >= P.lh) gy = 2 * P.lh - gy - 1; else if (gy < 0) gy = -gy - 1;
+                        if (gx >= P.lw) gx = 2 * P.lw - gx - 1; else if (gx < 0) gx = -gx - 1;
+                        gy = hr_min(hr_max(gy, 0), P.lh - 1);
+                        gx = hr_min(hr_max(gx, 0), P.lw - 1);
+                        q[u] = Tl + (gy >> lgl) * lnwx + (gx >> lgl);
+                        v[u] = ld_relaxed_u64(q[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int i = tid + u * NT;
+                    if (q[u]) {
+                        while ((uint32_t)(v[u] >> 32) != P.epoch) v[u] = ld_relaxed_u64(q[u]); /* a neighbour tile is still searching */
+                        tX[i] = (int16_t)(v[u] & 0xffffu);
+                        tY[i] = (int16_t)((v[u] >> 16) & 0xffffu);
+                    }
+                }
             }
             __syncthreads();
             for (int i = tid; i < 40 * 32; i += NT) {
@@ -460,6 +550,11 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
         }
     }
     HR_STAMP(); /* blur done */
+    if (DBG && P.timeline && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + HR_TIMELINE_SLOTS - 1] = (long long)gt;
+    }
 #undef HR_STAMP
 }
 

@@ -16,7 +16,9 @@ for _ in range(5): g.calc_flow(R)
 g.set_timeline(True)
 g.calc_flow(R)
 tl = g.get_timeline()
-n = int((tl[0] != 0).sum())
+n = int((tl[0, :120] != 0).sum())
+g0, g1 = tl[:, 126], tl[:, 127]
+print("globaltimer: CTA start skew %d ns, end skew %d ns, first start -> last end %d ns, median CTA life %d ns" % (g0.max() - g0.min(), g1.max() - g1.min(), g1.max() - g0.min(), np.median(g1 - g0)))
 print("stamps per CTA:", n, "ctas", tl.shape[0])
 d = np.diff(tl[:, :n], axis=1)
 print("total cycles (median over CTAs): %d" % np.median(tl[:, n - 1] - tl[:, 0]))
