@@ -126,6 +126,11 @@ int hr_blur_flow(HrContext *ctx, const int16_t *rawHost, int16_t *blurredHost);
 int hr_set_trace(HrContext *ctx, int enable);
 int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers);
 
+/* Parity tap: out[i] = MUFU.RCP((float)i) for 0 <= i < n, the reciprocal that `/` (div.full.f32) of the
+ * reference's level mapping (HR/Kernels/warpFrameKernel.cl:1-7) multiplies by on an NVIDIA device.
+ * The CPU oracle's NVIDIA-OpenCL arithmetic reads it from tests/golden/mufu_rcp_table.npy. */
+int hr_debug_rcp_table(float *out, int n);
+
 /* Developer tap: SM-clock stamps taken by thread 0 of every search CTA at fixed points of the launch
  * (step start, layers reduced, window published / complete, level done, search done, blur done).
  * stamps: int64 [min(maxCtas, searchCtas)][HR_TIMELINE_SLOTS]; unused slots are 0. Blocking. */

@@ -61,6 +61,7 @@ ABI = {
     "hr_blur_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hr_debug_rcp_table": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_set_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hr_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -113,6 +114,14 @@ def _ptr(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     raise TypeError("unsupported buffer type %r" % type(a))
+
+
+def debug_rcp_table(n=1024):
+    """MUFU.RCP(i) for i in range(n), read back from the GPU (parity tap)."""
+    out = np.zeros(n, np.float32)
+    if load_library().hr_debug_rcp_table(_ptr(out), n):
+        raise HrError(load_library().hr_last_error(None).decode())
+    return out
 
 
 class HrCuda:

@@ -58,8 +58,7 @@ struct WarpParams {
     const T *f2y, *f2uv;     /* sourceFrame21 = newest frame                                      */
     T *outY, *outUV;
     const int16_t *flow;     /* blurred offsets [2][lh][lw]                                       */
-    const uint8_t *lut;      /* [2][256] 8-bit levels LUT (Y then UV)                             */
-    int lw, lh, H, W, aW, s, mode, lutIdentity;
+    int lw, lh, H, W, aW, s, mode;
     float t12, t21, black, white;
 };
 

@@ -48,10 +48,6 @@ struct HrContext {
     int traceOn;
     long long *timeline;
     int timelineOn;
-    uint8_t *lut;
-    int *lutIdentityDev;
-    int lutIdentity, lutValid;
-    float lutBlack, lutWhite;
     int useFastWarp;
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
@@ -124,8 +120,6 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->partial);
     cudaFree(ctx->trace);
     cudaFree(ctx->timeline);
-    cudaFree(ctx->lut);
-    cudaFree(ctx->lutIdentityDev);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
     if (ctx->evFlowEnd) cudaEventDestroy(ctx->evFlowEnd);
     if (ctx->evWarpStart) cudaEventDestroy(ctx->evWarpStart);
@@ -207,8 +201,6 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->T, (size_t)(words ? words : 32) * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->partial, (size_t)(bwords ? bwords : 32) * sizeof(unsigned long long)));
-    CU(cudaMalloc(&ctx->lut, 512));
-    CU(cudaMalloc(&ctx->lutIdentityDev, sizeof(int)));
     CU(cudaMemset(ctx->frameBuf[0], 0, ctx->frameBytes));
     CU(cudaMemset(ctx->frameBuf[1], 0, ctx->frameBytes));
     CU(cudaMemset(ctx->outBuf, 0, ctx->frameBytes));
@@ -310,6 +302,26 @@ extern "C" int hr_set_trace(HrContext *ctx, int enable) {
         CU(cudaMemset(ctx->trace, 0, n));
     }
     ctx->traceOn = enable ? 1 : 0;
+    return 0;
+}
+
+__global__ void rcp_table_kernel(float *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rcp_approx((float)i);
+}
+
+/* Parity tap: MUFU.RCP((float)i), 0 <= i < n — the reciprocal inside div.full.f32, which the warp's
+ * level mapping uses. tests/golden/make_rcp_table.py stores it for the CPU-side checks. */
+extern "C" int hr_debug_rcp_table(float *out, int n) {
+    HrContext *ctx = NULL;
+    if (!out || n < 1) return 1;
+    float *d = NULL;
+    CU(cudaMalloc(&d, (size_t)n * sizeof(float)));
+    rcp_table_kernel<<<(n + 255) / 256, 256>>>(d, n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(NULL, "CUDA error in hr_debug_rcp_table: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -492,19 +504,6 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     return 0;
 }
 
-static int ensure_lut(HrContext *ctx, float black, float white) {
-    if (ctx->lutValid && ctx->lutBlack == black && ctx->lutWhite == white) return 0;
-    levels_lut_kernel<<<1, 256, 0, ctx->stream>>>(ctx->lut, ctx->lutIdentityDev, black, white);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    CU(cudaMemcpyAsync(&ctx->lutIdentity, ctx->lutIdentityDev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->lutBlack = black;
-    ctx->lutWhite = white;
-    ctx->lutValid = 1;
-    return 0;
-}
-
 template <typename T>
 static int launch_warp(HrContext *ctx, float t, int mode, float black, float white) {
     WarpParams<T> P;
@@ -515,7 +514,6 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.outY = (T *)ctx->outY;
     P.outUV = (T *)ctx->outUV;
     P.flow = ctx->blur;
-    P.lut = ctx->lut;
     P.lw = ctx->lw;
     P.lh = ctx->lh;
     P.H = ctx->H;
@@ -523,16 +521,20 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.aW = ctx->aW;
     P.s = ctx->s;
     P.mode = mode;
-    P.lutIdentity = ctx->lutIdentity;
     P.t12 = t;            /* opticalFlowCalc.c:215-216, float */
     P.t21 = 1.0f - t;
     P.black = black;
     P.white = white;
-    const int rows = ctx->H + (ctx->H >> 1);
+    /* thread = 4 samples x HR_WARP_ROWS rows; row groups of the luma plane, then of the chroma plane */
+    const int groups = (ctx->H + HR_WARP_ROWS - 1) / HR_WARP_ROWS + ((ctx->H >> 1) + HR_WARP_ROWS - 1) / HR_WARP_ROWS;
     dim3 block(32, 8);
-    dim3 grid((ctx->aW + 127) / 128, (rows + 7) / 8);
-    /* 32-bit accesses of the fast path need 4-byte aligned rows */
-    int fast = ctx->useFastWarp && (ctx->W % 4 == 0) && (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 4 == 0);
+    dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
+    /* the block path: 4x4 blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in
+     * [0,1], level denominators for which div.full.f32 is MUFU.RCP * x (hr_warp.cuh) */
+    const float den1 = white - black, den2 = white;
+    const int denOk = fabsf(den1) >= 1.17549435e-38f && fabsf(den1) <= 8.50705917e37f && fabsf(den2) >= 1.17549435e-38f && fabsf(den2) <= 8.50705917e37f;
+    int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
+               (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], ctx->stream));
     warp_blend_kernel<T><<<grid, block, 0, ctx->stream>>>(P, fast);
     CU(cudaGetLastError());
@@ -552,7 +554,6 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
     }
     if (mode < 0 || mode > 6) return fail(ctx, "hr_warp: unknown output mode %d", mode);
     if (bind_device(ctx)) return 1;
-    if (ensure_lut(ctx, black, white)) return 1;
     CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
     return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, t, mode, black, white) : launch_warp<uint16_t>(ctx, t, mode, black, white);
 }

@@ -1,9 +1,33 @@
+/*
+ * hr_warp.cuh — K5: flip lookup + bidirectional warp + time-weighted blend + output levels + the
+ * seven output modes, luma and chroma planes in ONE launch (warpFrameKernel.cl:114-182, two
+ * launches in the reference, opticalFlowCalc.c:229-232).
+ *
+ * Arithmetic: the float expressions are evaluated exactly as the reference kernel executes them on
+ * an NVIDIA OpenCL device (PTX of the unmodified .cl source, tools/dump_ref_ptx.py):
+ *     blend   = fma(f1, 1-t, f2 * t)                       (a*s21 + b*s12 contracted once)
+ *     luma    = ((v - black) * rcp(white - black)) * 255    ('/' is div.full.f32 = MUFU.RCP + FMUL)
+ *     chroma  = fma((v - 128) * rcp(white), 255, 128)
+ *     round() = trunc(x + copysign(0.5, x)) with the add rounded toward zero (== roundf)
+ * so 8-bit output is bit-identical to the reference run on the same GPU (tests/
+ * test_gpu_vs_reference_opencl.py); the IEEE/no-contraction reading of the source differs from it
+ * by at most +-1 LSB per operation. The library is compiled with -fmad=false, every fma below is
+ * explicit.
+ *
+ * Work decomposition (HBM-bound: 2 frames read + 1 frame written per launch):
+ *   thread = 4 samples x 4 rows of one plane. For resolution scalars >= 2 (every frame higher than
+ *   540 lines) the 4x4 block lies inside one lattice cell, so the two flow vectors (o12 at the cell,
+ *   o21 through the flip indirection) and both displacements are computed ONCE per thread; each row
+ *   is then two unaligned 4-sample source runs (two aligned 32/64-bit loads + funnel shift each),
+ *   a 4-sample blend and one 32-bit (NV12) / 64-bit (P010) store; a warp stores 128 / 256
+ *   contiguous bytes per row. u8<->f32 conversions go through the 2^23 magic number (PRMT + FADD,
+ *   full-rate pipes) instead of I2F/F2I. Frame borders, modes 3/4/6, resolution scalars < 2 and
+ *   out-of-range level denominators take the per-sample path warp_sample(), which computes the same
+ *   numbers.
+ */
 #pragma once
 #include "hr_common.cuh"
 
-/* ------------------------------------------------------------------------------------------ */
-/* warp + flip + blend + levels + output modes (K5)                                              */
-/* ------------------------------------------------------------------------------------------ */
 /* warpFrameKernel.cl:10-18 */
 __device__ __forceinline__ int warp_mirror(int pos, int dim) {
     int res = pos;
@@ -11,31 +35,59 @@ __device__ __forceinline__ int warp_mirror(int pos, int dim) {
     else if (pos < 1) res = -pos + 1;
     return hr_min(hr_max(res, 1), dim - 2);
 }
+/* '/' of the reference as compiled for NVIDIA OpenCL devices: div.full.f32 */
+__device__ __forceinline__ float div_full(float a, float b) {
+    float r;
+    asm("div.full.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float b) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return r;
+}
+/* div.full.f32 is MUFU.RCP(b) * a while |b| is inside this range (outside it pre-scales both) */
+__device__ __forceinline__ bool div_full_is_rcp_mul(float b) { return fabsf(b) >= 1.17549435e-38f && fabsf(b) <= 8.50705917e37f; }
+
 __device__ __forceinline__ unsigned sat_u8(float v) { return __float2uint_rz(fmaxf(fminf(v, 255.0f), 0.0f)); }
+/* (unsigned char)(float) of OpenCL C as NVIDIA compiles it: cvt.rzi.u16.f32, low byte stored */
+__device__ __forceinline__ unsigned cvt_uchar(float v) {
+    unsigned short r;
+    asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return (unsigned)r & 255u;
+}
 
 /* warpFrameKernel.cl:1-7 */
-__device__ __forceinline__ unsigned levels_y8(float v, float black, float white) { return sat_u8((v - black) / (white - black) * 255.0f); }
-__device__ __forceinline__ unsigned levels_uv8(float v, float white) { return sat_u8((v - 128.0f) / white * 255.0f + 128.0f); }
-/* P010, by construction */
-__device__ __forceinline__ unsigned levels_y16(float v, float black, float white) {
-    const float b16 = black / 255.0f * 65472.0f, w16 = white / 255.0f * 65472.0f;
-    return __float2uint_rz(fmaxf(fminf((v - b16) / (w16 - b16) * 65472.0f, 65472.0f), 0.0f)) & 0xFFC0u;
+__device__ __forceinline__ unsigned levels_y8(float v, float black, float white) { return sat_u8(div_full(v - black, white - black) * 255.0f); }
+__device__ __forceinline__ unsigned levels_uv8(float v, float white) { return sat_u8(__fmaf_rn(div_full(v - 128.0f, white), 255.0f, 128.0f)); }
+
+/* P010 output levels, defined by construction: the 8-bit knobs are mapped onto the
+ * MSB-aligned 10-bit range (65472 = 1023 << 6), the division is a multiplication by the correctly
+ * rounded reciprocal, and the result is rounded to the nearest 10-bit code (so that the default
+ * levels are an exact identity). */
+struct Levels16 {
+    float b16, rY, rUV;
+};
+__device__ __forceinline__ Levels16 make_levels16(float black, float white) {
+    Levels16 L;
+    L.b16 = __fmul_rn(__fdiv_rn(black, 255.0f), 65472.0f);
+    const float w16 = __fmul_rn(__fdiv_rn(white, 255.0f), 65472.0f);
+    L.rY = __fdiv_rn(1.0f, w16 - L.b16);
+    L.rUV = __fdiv_rn(1.0f, w16);
+    return L;
 }
-__device__ __forceinline__ unsigned levels_uv16(float v, float white) {
-    const float w16 = white / 255.0f * 65472.0f;
-    return __float2uint_rz(fmaxf(fminf((v - 32768.0f) / w16 * 65472.0f + 32768.0f, 65472.0f), 0.0f)) & 0xFFC0u;
+__device__ __forceinline__ unsigned levels_y16(float v, const Levels16 &L) {
+    const float x = fmaxf(fminf((v - L.b16) * L.rY * 65472.0f, 65472.0f), 0.0f);
+    return (__float2uint_rz(x) + 32u) & 0xFFC0u;
+}
+__device__ __forceinline__ unsigned levels_uv16(float v, const Levels16 &L) {
+    const float x = fmaxf(fminf(__fmaf_rn((v - 32768.0f) * L.rUV, 65472.0f, 32768.0f), 65472.0f), 0.0f);
+    return (__float2uint_rz(x) + 32u) & 0xFFC0u;
 }
 
-__global__ void levels_lut_kernel(uint8_t *lut, int *identity, float black, float white) {
-    const int v = threadIdx.x;
-    const unsigned y = levels_y8((float)v, black, white), c = levels_uv8((float)v, white);
-    lut[v] = (uint8_t)y;
-    lut[256 + v] = (uint8_t)c;
-    const int same = __syncthreads_and(y == (unsigned)v && c == (unsigned)v);
-    if (v == 0) *identity = same;
-}
-
-/* warpFrameKernel.cl:21-111 */
+/* warpFrameKernel.cl:21-111. The hue comes from CUDA's atan2f/fmodf (the OpenCL built-ins are a
+ * different polynomial: +-1 on the 8-bit channels, tests allow it); the scaling and the RGB->YUV
+ * products follow the reference's contraction pattern. */
 __device__ unsigned visualize_flow(int offsetX, int offsetY, unsigned currPixel, int channel, int resImpact) {
     offsetX = (int)(int16_t)offsetX;
     offsetY = (int)(int16_t)offsetY;
@@ -49,26 +101,28 @@ __device__ unsigned visualize_flow(int offsetX, int offsetY, unsigned currPixel,
         if (angle_deg < 0) angle_deg += 360.0f;
         angle_deg = fmodf(angle_deg, 360.0f);
         if (angle_deg < 0) angle_deg += 360.0f;
-        const float hue = angle_deg / 360.0f;
+        const float hue = div_full(angle_deg, 360.0f);
         const int h_i = (int)(hue * 6.0f);
-        const float f = hue * 6.0f - (float)h_i;
+        const float f = __fmaf_rn(hue, 6.0f, -(float)h_i);
         const float q = 1.0f - f;
         switch (h_i % 6) {
-            case 0: r = 255; g = __float2uint_rz(f * 255.0f) & 255u; b = 0; break;
-            case 1: r = __float2uint_rz(q * 255.0f) & 255u; g = 255; b = 0; break;
-            case 2: r = 0; g = 255; b = __float2uint_rz(f * 255.0f) & 255u; break;
-            case 3: r = 0; g = __float2uint_rz(q * 255.0f) & 255u; b = 255; break;
-            case 4: r = __float2uint_rz(f * 255.0f) & 255u; g = 0; b = 255; break;
-            case 5: r = 255; g = 0; b = __float2uint_rz(q * 255.0f) & 255u; break;
+            case 0: r = 255; g = cvt_uchar(f * 255.0f); b = 0; break;
+            case 1: r = cvt_uchar(q * 255.0f); g = 255; b = 0; break;
+            case 2: r = 0; g = 255; b = cvt_uchar(f * 255.0f); break;
+            case 3: r = 0; g = cvt_uchar(q * 255.0f); b = 255; break;
+            case 4: r = cvt_uchar(f * 255.0f); g = 0; b = 255; break;
+            case 5: r = 255; g = 0; b = cvt_uchar(q * 255.0f); break;
             default: r = g = b = 0; break;
         }
-        r = sat_u8((float)r / 255.0f * (float)(ax + ay) * (float)resImpact);
-        g = sat_u8((float)g / 255.0f * (float)ay * 2.0f * (float)resImpact);
-        b = sat_u8((float)b / 255.0f * (float)(ax + ay) * (float)resImpact);
+        const float gq = div_full((float)g, 255.0f) * (float)ay;
+        r = sat_u8(div_full((float)r, 255.0f) * (float)(ax + ay) * (float)resImpact);
+        g = sat_u8(__fmaf_rn(div_full((float)g, 255.0f), (float)ay, gq) * (float)resImpact);
+        b = sat_u8(div_full((float)b, 255.0f) * (float)(ax + ay) * (float)resImpact);
     }
-    if (channel == 0) return ((sat_u8((float)r * 0.299f + (float)g * 0.587f + (float)b * 0.114f) >> 1) + (currPixel >> 1)) & 255u;
-    if (channel == 1) return sat_u8((float)r * -0.168736f + (float)g * -0.331264f + (float)b * 0.5f + 128.0f);
-    return sat_u8((float)r * 0.5f + (float)g * -0.418688f + (float)b * -0.081312f + 128.0f);
+    const float fr = (float)r, fg = (float)g, fb = (float)b;
+    if (channel == 0) return ((sat_u8(__fmaf_rn(fb, 0.114f, __fmaf_rn(fr, 0.299f, fg * 0.587f))) >> 1) + (currPixel >> 1)) & 255u;
+    if (channel == 1) return sat_u8(__fmaf_rn(fb, 0.5f, __fmaf_rn(fr, -0.168736f, fg * -0.331264f)) + 128.0f);
+    return sat_u8(__fmaf_rn(fb, -0.081312f, __fmaf_rn(fr, 0.5f, fg * -0.418688f)) + 128.0f);
 }
 
 template <typename T>
@@ -92,39 +146,40 @@ __device__ __forceinline__ CellFlow cell_flow(const WarpParams<T> &P, int adjCx,
     const int s = P.s;
     const int scx = cz ? ((adjCx >> s) & ~1) : (adjCx >> s);
     const int scy = cz ? ((adjCy >> s) << 1) : (adjCy >> s);
-    const size_t ln = (size_t)P.lw * P.lh;
+    const int ln = P.lw * P.lh;
+    const int i12 = scy * P.lw + scx;
     CellFlow f;
-    f.x12 = __ldg(P.flow + (size_t)scy * P.lw + scx);
-    f.y12 = __ldg(P.flow + ln + (size_t)scy * P.lw + scx);
+    f.x12 = __ldg(P.flow + i12);
+    f.y12 = __ldg(P.flow + ln + i12);
     const int fy = hr_min(hr_max(scy - (f.y12 >> s), 0), P.lh - 1);
     const int fx = hr_min(hr_max(scx - (f.x12 >> s), 0), P.lw - 1);
-    f.x21 = __ldg(P.flow + (size_t)fy * P.lw + fx);
-    f.y21 = __ldg(P.flow + ln + (size_t)fy * P.lw + fx);
+    const int i21 = fy * P.lw + fx;
+    f.x21 = __ldg(P.flow + i21);
+    f.y21 = __ldg(P.flow + ln + i21);
     return f;
 }
 
+/* blend + mode 3 + levels of one sample pair (warpFrameKernel.cl:175-180) */
 template <typename T>
 __device__ __forceinline__ unsigned finish_blend(const WarpParams<T> &P, unsigned a, unsigned b, int cz, int cx, const CellFlow &f) {
+    const float bl = __fmaf_rn((float)a, P.t21, (float)b * P.t12);
     if (!SampleTraits<T>::is16) {
-        unsigned v = __float2uint_rz((float)a * P.t21 + (float)b * P.t12);
-        if (P.mode == 3) {
-            v = visualize_flow(-f.x12, -f.y12, v & 255u, cz + (cx & (cz ? 1 : 0)), P.s <= 2 ? 4 : 1);
-            return cz ? levels_uv8((float)v, P.white) : levels_y8((float)v, P.black, P.white);
-        }
-        v &= 255u;
-        return P.lutIdentity ? v : (unsigned)__ldg(P.lut + (cz ? 256 : 0) + v);
+        unsigned v = cvt_uchar(bl);
+        if (P.mode == 3) v = visualize_flow(-f.x12, -f.y12, v, cz + (cx & (cz ? 1 : 0)), P.s <= 2 ? 4 : 1);
+        return cz ? levels_uv8((float)v, P.white) : levels_y8((float)v, P.black, P.white);
     } else {
-        const unsigned v = __float2uint_rz(fminf((float)a * P.t21 + (float)b * P.t12, 65535.0f));
+        const unsigned v = __float2uint_rz(fmaxf(fminf(bl, 65535.0f), 0.0f));
         if (P.mode == 3) {
             const unsigned v8 = visualize_flow(-f.x12, -f.y12, v >> 8, cz + (cx & (cz ? 1 : 0)), P.s <= 2 ? 4 : 1);
             const unsigned l8 = cz ? levels_uv8((float)v8, P.white) : levels_y8((float)v8, P.black, P.white);
             return l8 << 8;
         }
-        return cz ? levels_uv16((float)v, P.white) : levels_y16((float)v, P.black, P.white);
+        const Levels16 L = make_levels16(P.black, P.white);
+        return cz ? levels_uv16((float)v, L) : levels_y16((float)v, L);
     }
 }
 
-/* One output sample, every mode: the general path (frame borders, modes 3/4/6, tiny frames). */
+/* One output sample, every mode: frame borders, modes 3/4/6, small frames (warpFrameKernel.cl:119-181). */
 template <typename T>
 __device__ unsigned warp_sample(const WarpParams<T> &P, int cx, int cy, int cz) {
     const T *s12 = cz ? P.f1uv : P.f1y;
@@ -164,93 +219,172 @@ __device__ unsigned warp_sample(const WarpParams<T> &P, int cx, int cy, int cz) 
     return finish_blend(P, (unsigned)s12[i12], (unsigned)s21[i21], cz, cx, f);
 }
 
-/* Four consecutive samples starting at an arbitrary sample address, from aligned 32-bit loads. */
-__device__ __forceinline__ uint32_t load4_u8(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-    const unsigned shft = (unsigned)(a & 3) * 8;
-    const uint32_t lo = __ldg(q);
-    const uint32_t hi = shft ? __ldg(q + 1) : 0u;
-    return __funnelshift_r(lo, hi, shft);
-}
-/* 8 consecutive bytes from an arbitrary byte address (chroma with odd displacement) */
-__device__ __forceinline__ uint2 load8_u8(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-    const unsigned shft = (unsigned)(a & 3) * 8;
-    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
-    const uint32_t w2 = shft ? __ldg(q + 2) : 0u;
-    return make_uint2(__funnelshift_r(w0, w1, shft), __funnelshift_r(w1, w2, shft));
-}
+/* ---- the block path ------------------------------------------------------------------------------ */
+#define HR_WARP_ROWS 4 /* rows per thread; a 4x4 block lies inside one lattice cell when s >= 2 */
 
-/* Interior fast path, NV12: the four samples of a 4-aligned quad share one lattice cell
- * (s >= 2), so each source is one translated run. Chroma keeps U/V parity: with an odd
- * displacement d the U bytes come from cx+d-1 and the V bytes from cx+d+1
- * (warpFrameKernel.cl:171 `(newCx & ~1) + (cx & 1)`). Returns false when a border is touched. */
-__device__ __forceinline__ bool fetch_quad_u8(const uint8_t *plane, int dimX, int aW, int cx0, int row, int d, int cz, uint32_t &out) {
-    if (cx0 + d < 1 || cx0 + 3 + d > aW - 2) return false;
-    const uint8_t *base = plane + (size_t)row * dimX;
-    if (!cz || !(d & 1)) {
-        out = load4_u8(base + cx0 + d);
-    } else {
-        const uint2 w = load8_u8(base + cx0 + d - 1);
-        out = __byte_perm(w.x, w.y, 0x5230);
-    }
-    return true;
+/* four consecutive samples from an arbitrary (sample-aligned) address, built from aligned loads */
+__device__ __forceinline__ uint32_t load_run4(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t lo = __ldg(q);
+    const uint32_t hi = sh ? __ldg(q + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ uint2 load_run4(const uint16_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 2) * 8;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+    const uint32_t w2 = sh ? __ldg(q + 2) : 0u;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+/* chroma with an odd displacement d: U samples come from column cx+d-1, V samples from cx+d+1
+ * (warpFrameKernel.cl:171 `(newCx & ~1) + (cx & 1)`): six samples starting at cx0+d-1, picked 0,3,2,5 */
+__device__ __forceinline__ uint32_t load_run4_uv_odd(const uint8_t *p /* = row + cx0 + d - 1 */) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+    const uint32_t w2 = sh ? __ldg(q + 2) : 0u;
+    return __byte_perm(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), 0x5230);
+}
+__device__ __forceinline__ uint2 load_run4_uv_odd(const uint16_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 2) * 8;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const uint32_t w3 = sh ? __ldg(q + 3) : 0u;
+    const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh);
+    /* samples 0,3 | 2,5 */
+    return make_uint2(__byte_perm(s0, s1, 0x7610), __byte_perm(s1, s2, 0x7610));
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) warp_blend_kernel(const WarpParams<T> P, int useFast) {
-    const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int row = blockIdx.y * blockDim.y + threadIdx.y;
-    if (cx0 >= P.aW || row >= P.H + (P.H >> 1)) return;
-    const int cz = row >= P.H;
-    const int cy = cz ? row - P.H : row;
-    T *outRow = (cz ? P.outUV : P.outY) + (size_t)cy * P.W;
+struct RunType;
+template <>
+struct RunType<uint8_t> {
+    typedef uint32_t type;
+};
+template <>
+struct RunType<uint16_t> {
+    typedef uint2 type;
+};
 
-    if (!SampleTraits<T>::is16 && useFast && P.s >= 2 && cx0 + 3 < P.aW && (P.mode <= 2 || P.mode == 5)) {
-        const uint8_t *s12 = (const uint8_t *)(cz ? P.f1uv : P.f1y);
-        const uint8_t *s21 = (const uint8_t *)(cz ? P.f2uv : P.f2y);
+/* u8 / u16 -> f32 and back through the 2^23 magic number (exact for 0 <= v < 2^23) */
+#define HR_MAGIC 8388608.0f
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)k)) - HR_MAGIC;
+}
+__device__ __forceinline__ float half_to_float(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, k ? 0x7532u : 0x7510u)) - HR_MAGIC;
+}
+/* trunc(x) for 0 <= x < 2^23 as the bits 0x4B000000 | trunc(x) */
+__device__ __forceinline__ uint32_t trunc_bits(float x) { return __float_as_uint(__fadd_rz(x, HR_MAGIC)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) warp_blend_kernel(const WarpParams<T> P, int useFast) {
+    constexpr bool is16 = SampleTraits<T>::is16;
+    const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int lumaGroups = (P.H + HR_WARP_ROWS - 1) / HR_WARP_ROWS;
+    const int rg = blockIdx.y * blockDim.y + threadIdx.y;
+    const int cz = rg >= lumaGroups;
+    const int cy0 = (cz ? rg - lumaGroups : rg) * HR_WARP_ROWS;
+    const int planeH = cz ? (P.H >> 1) : P.H;
+    if (cx0 >= P.aW || cy0 >= planeH) return;
+    const T *s12 = cz ? P.f1uv : P.f1y;
+    const T *s21 = cz ? P.f2uv : P.f2y;
+    T *out = cz ? P.outUV : P.outY;
+    const int nrows = hr_min(HR_WARP_ROWS, planeH - cy0);
+
+    bool done = false;
+    if (useFast && cx0 + 3 < P.aW) {
         const int half = P.aW >> 1;
         if (P.mode == 5 && cx0 + 3 < half) {
-            *reinterpret_cast<uint32_t *>(outRow + cx0) = *reinterpret_cast<const uint32_t *>(s12 + (size_t)cy * P.W + cx0);
-            return;
-        }
-        if (!(P.mode == 5 && cx0 < half)) {
-            const CellFlow f = cell_flow(P, cx0, cy, cz);
-            const int dY = cz ? (P.H >> 1) : P.H;
+            /* left half of SideBySide1: frame1 as it is (warpFrameKernel.cl:131-133) */
+            for (int r = 0; r < nrows; ++r) {
+                const size_t o = (size_t)(cy0 + r) * P.W + cx0;
+                if (is16) *reinterpret_cast<uint2 *>(out + o) = *reinterpret_cast<const uint2 *>(s12 + o);
+                else *reinterpret_cast<uint32_t *>(out + o) = *reinterpret_cast<const uint32_t *>(s12 + o);
+            }
+            done = true;
+        } else if (!(P.mode == 5 && cx0 < half)) {
+            const CellFlow f = cell_flow(P, cx0, cy0, cz);
             const float ys = cz ? 0.5f : 1.0f;
             const int d12 = (int)roundf((float)f.x12 * P.t12), d21 = -(int)roundf((float)f.x21 * P.t21);
-            const int ny12 = warp_mirror(cy + (int)roundf((float)f.y12 * P.t12 * ys), dY);
-            const int ny21 = warp_mirror(cy - (int)roundf((float)f.y21 * P.t21 * ys), dY);
-            uint32_t a = 0, b = 0;
-            bool ok = true;
-            if (P.mode != 1) ok = fetch_quad_u8(s12, P.W, P.aW, cx0, ny12, d12, cz, a);
-            if (ok && P.mode != 0) ok = fetch_quad_u8(s21, P.W, P.aW, cx0, ny21, d21, cz, b);
-            if (ok) {
-                uint32_t o;
-                if (P.mode == 0) o = a;
-                else if (P.mode == 1) o = b;
-                else {
-                    o = 0;
+            const int e12 = (int)roundf((float)f.y12 * P.t12 * ys), e21 = -(int)roundf((float)f.y21 * P.t21 * ys);
+            /* every source column inside [1, aW-2]: the mirror/clamp of warpFrameKernel.cl:10-18 is the identity */
+            const bool in12 = P.mode == 1 || (cx0 + d12 >= 1 && cx0 + 3 + d12 <= P.aW - 2);
+            const bool in21 = P.mode == 0 || (cx0 + d21 >= 1 && cx0 + 3 + d21 <= P.aW - 2);
+            if (in12 && in21) {
+                const bool odd12 = cz && (d12 & 1), odd21 = cz && (d21 & 1);
+                const float rY = rcp_approx(P.white - P.black), rUV = rcp_approx(P.white);
+                const Levels16 L = make_levels16(P.black, P.white);
+                /* phase 1: the source runs of all rows (independent loads in flight together) */
+                typedef typename RunType<T>::type Run;
+                Run ra[HR_WARP_ROWS], rb[HR_WARP_ROWS];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned av = (a >> (8 * k)) & 255u, bv = (b >> (8 * k)) & 255u;
-                        unsigned v = __float2uint_rz((float)av * P.t21 + (float)bv * P.t12) & 255u;
-                        if (!P.lutIdentity) v = __ldg(P.lut + (cz ? 256 : 0) + v);
-                        o |= v << (8 * k);
+                for (int r = 0; r < HR_WARP_ROWS; ++r) {
+                    const int cy = hr_min(cy0 + r, planeH - 1);
+                    const T *p12 = s12 + (size_t)warp_mirror(cy + e12, planeH) * P.W + cx0 + d12;
+                    const T *p21 = s21 + (size_t)warp_mirror(cy + e21, planeH) * P.W + cx0 + d21;
+                    ra[r] = rb[r] = Run();
+                    if (P.mode != 1) ra[r] = odd12 ? load_run4_uv_odd(p12 - 1) : load_run4(p12);
+                    if (P.mode != 0) rb[r] = odd21 ? load_run4_uv_odd(p21 - 1) : load_run4(p21);
+                }
+                /* phase 2: blend, levels, store */
+#pragma unroll
+                for (int r = 0; r < HR_WARP_ROWS; ++r) {
+                    if (r >= nrows) break;
+                    T *po = out + (size_t)(cy0 + r) * P.W + cx0;
+                    if constexpr (!is16) {
+                        const uint32_t a = ra[r], b = rb[r];
+                        uint32_t o;
+                        if (P.mode == 0) o = a;
+                        else if (P.mode == 1) o = b;
+                        else {
+                            uint32_t res[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                /* (uchar)(f1*s21 + f2*s12), then levels: warpFrameKernel.cl:175-180 */
+                                const float bl = __fmaf_rn(byte_to_float(a, k), P.t21, byte_to_float(b, k) * P.t12);
+                                const float v = __uint_as_float(trunc_bits(bl)) - HR_MAGIC;
+                                const float x = cz ? __fmaf_rn((v - 128.0f) * rUV, 255.0f, 128.0f) : ((v - P.black) * rY) * 255.0f;
+                                res[k] = trunc_bits(fmaxf(fminf(x, 255.0f), 0.0f));
+                            }
+                            o = __byte_perm(__byte_perm(res[0], res[1], 0x0040), __byte_perm(res[2], res[3], 0x0040), 0x5410);
+                        }
+                        *reinterpret_cast<uint32_t *>(po) = o;
+                    } else {
+                        const uint2 a = ra[r], b = rb[r];
+                        uint2 o;
+                        if (P.mode == 0) o = a;
+                        else if (P.mode == 1) o = b;
+                        else {
+                            uint32_t res[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t wa = k < 2 ? a.x : a.y, wb = k < 2 ? b.x : b.y;
+                                const float bl = __fmaf_rn(half_to_float(wa, k & 1), P.t21, half_to_float(wb, k & 1) * P.t12);
+                                const float v = __uint_as_float(trunc_bits(fminf(bl, 65535.0f))) - HR_MAGIC;
+                                res[k] = cz ? levels_uv16(v, L) : levels_y16(v, L);
+                            }
+                            o = make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
+                        }
+                        *reinterpret_cast<uint2 *>(po) = o;
                     }
                 }
-                *reinterpret_cast<uint32_t *>(outRow + cx0) = o;
-                return;
+                done = true;
             }
         }
     }
-    /* general path */
+    if (done) return;
+    /* per-sample path */
+    for (int r = 0; r < nrows; ++r) {
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int cx = cx0 + k;
-        if (cx < P.aW) outRow[cx] = (T)warp_sample(P, cx, cy, cz);
+        for (int k = 0; k < 4; ++k) {
+            const int cx = cx0 + k;
+            if (cx < P.aW) out[(size_t)(cy0 + r) * P.W + cx] = (T)warp_sample(P, cx, cy0 + r, cz);
+        }
     }
 }
-

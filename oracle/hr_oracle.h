@@ -41,6 +41,19 @@ extern "C" {
 
 #define HRO_MAX_STEPS 32
 
+/* How K5's float expressions are rounded. OpenCL C leaves this to the device compiler (contraction
+ * allowed, '/' accurate to 2.5 ulp), so "the reference's result" exists per device:
+ *   HRO_ARITH_IEEE  the literal reading: every operation rounded on its own, correctly rounded '/'.
+ *   HRO_ARITH_NVCL  what the NVIDIA OpenCL compiler makes of the unmodified warpFrameKernel.cl
+ *                   (PTX dumped on the B200 by tools/dump_ref_ptx.py): a*b+c*d -> fma(a, b, c*d),
+ *                   x/y*255+128 -> fma(x/y, 255, 128), '/' -> div.full.f32 = x * MUFU.RCP(y).
+ *                   Needs the MUFU.RCP table (hro_set_rcp_table; tests/golden/mufu_rcp_table.npy was
+ *                   read back from the B200). Bit-identical to the reference run on that GPU for
+ *                   modes 0,1,2,4,5,6; mode 3 within +-1 (the hue uses libm's atan2f/fmodf).
+ * Integer results (flow, positions) do not depend on it. */
+#define HRO_ARITH_IEEE 0
+#define HRO_ARITH_NVCL 1
+
 typedef struct HrOracle HrOracle;
 
 /* frameHeight, frameWidth (= stride in samples), actualWidth: opticalFlowCalc.c:323-336 */
@@ -56,6 +69,10 @@ int hro_num_steps(const HrOracle *o); /* 2 * iterations */
 int hro_update_frame(HrOracle *o, const void *y, const void *uv);
 /* opticalFlowCalc.c:126-203. Returns 0 on success. */
 int hro_calc_flow(HrOracle *o, int searchRadius, int deltaScalar, int neighborBiasScalar);
+/* table[i] = MUFU.RCP((float)i), 0 <= i < n; the pointer is kept, not copied */
+void hro_set_rcp_table(const float *table, int n);
+/* Returns 1 if NVCL is asked for without a table. Default: HRO_ARITH_IEEE. */
+int hro_set_arith(HrOracle *o, int arith);
 /* opticalFlowCalc.c:205-234 + warpFrameKernel.cl. Returns 1 when t > 1. */
 int hro_warp(HrOracle *o, float t, int mode, float black, float white);
 /* opticalFlowCalc.c:109-124 */

@@ -11,7 +11,11 @@ import numpy as np
 
 HERE = pathlib.Path(__file__).resolve().parent
 LIB = HERE / "libhr_oracle.so"
+# MUFU.RCP(i), i = 0..1023, read back from the B200 (tests/golden/make_rcp_table.py)
+RCP_TABLE = HERE.parent / "tests" / "golden" / "mufu_rcp_table.npy"
+ARITH_IEEE, ARITH_NVCL = 0, 1
 _lib = None
+_rcp = None
 
 
 def build(force=False):
@@ -44,8 +48,20 @@ def lib():
         L.hro_blur_flow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.hro_blur_flow.restype = None
         L.hro_num_threads.restype = C.c_int
+        L.hro_set_rcp_table.argtypes = [C.c_void_p, C.c_int]
+        L.hro_set_rcp_table.restype = None
+        L.hro_set_arith.argtypes = [C.c_void_p, C.c_int]
         _lib = L
+        if RCP_TABLE.exists():
+            global _rcp
+            _rcp = np.ascontiguousarray(np.load(RCP_TABLE), np.float32)
+            L.hro_set_rcp_table(C.c_void_p(_rcp.ctypes.data), int(_rcp.size))
     return _lib
+
+
+def have_nvcl():
+    lib()
+    return _rcp is not None
 
 
 def _p(a):
@@ -54,7 +70,8 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=0):
+    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=0, arith=None):
+        """arith: ARITH_IEEE, ARITH_NVCL, or None = NVCL when the MUFU.RCP table is available."""
         self.L = lib()
         aw = frameWidth if actualWidth is None else actualWidth
         self.o = self.L.hro_create(frameHeight, frameWidth, aw, pixfmt)
@@ -67,6 +84,9 @@ class Oracle:
         self.s = self.L.hro_res_scalar(self.o)
         self.steps = self.L.hro_num_steps(self.o)
         self.radius = 0
+        self.arith = (ARITH_NVCL if _rcp is not None else ARITH_IEEE) if arith is None else arith
+        if self.L.hro_set_arith(self.o, self.arith):
+            raise RuntimeError("NVCL arithmetic needs tests/golden/mufu_rcp_table.npy")
 
     def close(self):
         if self.o:

@@ -2,8 +2,13 @@
 B200 through the NVIDIA OpenCL ICD (oracle/_ref, built by oracle/build_ref.py).
 
 This is what pins the oracle: (a) oracle == reference, (b) CUDA path == reference, on the same
-inputs. Flow offsets bit-exact; pixels within +-1 LSB (OpenCL may contract to FMA and its
-division is not correctly rounded).
+inputs. Flow offsets bit-exact. Pixels: OpenCL C lets the device compiler contract a*b+c to an fma
+and makes '/' only 2.5-ulp accurate, so the reference's pixels exist per device. The CUDA path and
+the oracle's NVCL arithmetic restate what the NVIDIA OpenCL compiler emits for the unmodified kernel
+(oracle/hr_oracle.h), so against THIS reference run they must be bit-identical in every mode but
+HSV (mode 3: the hue goes through the atan2/fmod built-ins; the CUDA ones turned out bit-identical
+to the OpenCL ones on the tested inputs, libm's differ in the last ulp: +-1 on rare pixels allowed).
+The oracle's IEEE reading of the source stays within +-2 of it.
 """
 import json
 import os
@@ -80,16 +85,24 @@ def test_warp_modes_equal_reference(hr, oracle, synth, ref, w, h, stride):
             oy, ouv = o.download()
             g.warp(t, mode, black, white)
             gy, guv, _ = g.download()
-            # +-1 LSB on the blended value (OpenCL may contract a*s+b*t to an FMA and its division is
-            # not correctly rounded); the levels map then scales that by its gain 255/(white-black),
-            # so with the 16/219 preset (gain 1.26) a 1-LSB blend difference can surface as 2.
-            gain = 255.0 / (white - black)
-            tol = 0 if mode in (0, 1, 4) else int(np.ceil(gain)) + (1 if mode == 3 else 0)
+            tol = 1 if mode == 3 else 0
             for nm, a, b in (("oracle Y", oy, ry), ("oracle UV", ouv, ruv), ("cuda Y", gy, ry), ("cuda UV", guv, ruv)):
                 _cmp("mode %d t=%.1f %s vs reference" % (mode, t, nm), a[:, :w], b[:, :w], tol)
-                if tol > 1:   # differences above 1 LSB must stay isolated pixels
+                if tol:   # HSV: differences must stay rare
                     d = np.abs(a[:, :w].astype(int) - b[:, :w].astype(int))
-                    assert (d > 1).mean() < 1e-4, "mode %d t=%.1f %s: too many pixels off by more than 1" % (mode, t, nm)
+                    assert (d > 0).mean() < 0.001, "mode %d t=%.1f %s: %.3f%% of the pixels differ" % (mode, t, nm, 100 * (d > 0).mean())
+            # the literal IEEE reading of the kernel source: within +-2 (one LSB from the blend's contraction,
+            # one from the reciprocal inside '/'), scaled by the level gain
+            if mode in (2, 5, 6):
+                i = oracle.Oracle(h, stride, w, arith=oracle.ARITH_IEEE)
+                i.update_frame(*c.frame(2))
+                i.update_frame(*c.frame(3))
+                i.set_blurred_offsets(r.get_offsets()[1])
+                i.warp(t, mode, black, white)
+                iy, iuv = i.download()
+                gain = int(np.ceil(255.0 / (white - black)))
+                _cmp("mode %d t=%.1f IEEE oracle Y vs reference" % (mode, t), iy[:, :w], ry[:, :w], 1 + gain)
+                _cmp("mode %d t=%.1f IEEE oracle UV vs reference" % (mode, t), iuv[:, :w], ruv[:, :w], 1 + gain)
     r.close()
 
 
@@ -108,9 +121,8 @@ def test_warp_large_flow_equals_reference(hr, oracle, synth, ref):
         oy, ouv = o.download()
         g.warp(0.6, mode)
         gy, guv, _ = g.download()
-        tol = 0 if mode in (0, 1) else 1
         for nm, a, b in (("oracle Y", oy, ry), ("oracle UV", ouv, ruv), ("cuda Y", gy, ry), ("cuda UV", guv, ruv)):
-            _cmp("mode %d %s vs reference" % (mode, nm), a, b, tol)
+            _cmp("mode %d %s vs reference" % (mode, nm), a, b, 0)
     r.close()
 
 

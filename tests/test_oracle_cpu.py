@@ -136,8 +136,9 @@ def test_warp_rejects_t_above_one(oracle):
 
 
 def test_default_levels_are_identity_and_presets_are_not(oracle, synth):
+    """The literal (IEEE) reading of warpFrameKernel.cl:1-7."""
     (y, uv), (y2, uv2) = _pair(synth, 640, 360)
-    o = oracle.Oracle(360, 640)
+    o = oracle.Oracle(360, 640, arith=oracle.ARITH_IEEE)
     o.update_frame(y, uv)
     o.update_frame(y2, uv2)
     o.calc_flow(5)
@@ -149,3 +150,36 @@ def test_default_levels_are_identity_and_presets_are_not(oracle, synth):
     exp = np.clip((yy - np.float32(16)) / np.float32(219 - 16) * np.float32(255), 0, 255).astype(np.uint8)
     assert np.array_equal(b[0][:, :640], exp[:, :640])
     assert not np.array_equal(a[0], b[0])
+
+
+def test_nvidia_opencl_arithmetic_stays_within_two_of_the_ieee_reading(oracle, synth):
+    """HRO_ARITH_NVCL (fma contraction + div.full = x * MUFU.RCP(y), oracle/hr_oracle.h) against the
+    literal IEEE reading: one LSB from the blend, one from the reciprocal; with default levels the luma
+    map v -> trunc(v * rcp(255) * 255) loses one LSB wherever the product falls short of v."""
+    assert oracle.have_nvcl(), "tests/golden/mufu_rcp_table.npy is missing"
+    (y, uv), (y2, uv2) = _pair(synth, 640, 360)
+    outs = {}
+    for ar in (oracle.ARITH_IEEE, oracle.ARITH_NVCL):
+        o = oracle.Oracle(360, 640, arith=ar)
+        o.update_frame(y, uv)
+        o.update_frame(y2, uv2)
+        o.calc_flow(5)
+        for key, args in (("id", (0.4, 2, 0.0, 255.0)), ("preset", (0.6, 2, 16.0, 219.0)), ("m0", (0.4, 0, 0.0, 255.0))):
+            o.warp(*args)
+            outs[(ar, key)] = o.download()
+    for key, tol in (("id", 2), ("preset", 3), ("m0", 0)):
+        for pl in (0, 1):
+            d = np.abs(outs[(0, key)][pl].astype(int) - outs[(1, key)][pl].astype(int))
+            assert d.max() <= tol, (key, pl, int(d.max()))
+    # identity levels in NVCL arithmetic: rcp(255) is one ulp short, so most luma values drop by one
+    d = outs[(0, "id")][0].astype(int) - outs[(1, "id")][0].astype(int)
+    assert (d >= 0).all() and (d == 1).mean() > 0.5
+
+
+def test_rcp_table_is_within_one_ulp(oracle):
+    t = np.load(oracle.RCP_TABLE)
+    assert t.dtype == np.float32 and t.size == 1024
+    ref = np.float32(1.0) / np.arange(1, 1024, dtype=np.float32)
+    ulp = np.abs(t[1:].view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1
+    assert t[255] < ref[254]            # the reason the reference's default luma levels are not an identity on NVIDIA devices
