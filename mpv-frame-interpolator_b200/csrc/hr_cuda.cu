@@ -354,15 +354,29 @@ extern "C" int hr_set_profiling(HrContext *ctx, int enable) {
 }
 
 /* pack the newest frame (slot 1) into its phase-planar copy */
+template <typename T>
+static void launch_pack_t(HrContext *ctx) {
+    const T *y = (const T *)ctx->fy[1], *uv = (const T *)ctx->fuv[1];
+    const bool vec = ctx->s <= 4 && ctx->W % 16 == 0 && (((uintptr_t)y | (uintptr_t)uv) % 16 == 0);
+    if (vec) {
+        dim3 block(128), grid((ctx->W / 16 + 127) / 128, (ctx->H + 1) / 2);
+        switch (ctx->s) {
+#define HR_PCASE(S_) case S_: pack_frame16_kernel<T, S_><<<grid, block, 0, ctx->stream>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->planePitch, ctx->planeSize); break;
+            HR_PCASE(0) HR_PCASE(1) HR_PCASE(2) HR_PCASE(3) HR_PCASE(4)
+#undef HR_PCASE
+        }
+    } else {
+        const int bx = ctx->s <= 3 ? 128 : 64;
+        dim3 block(bx, 1 << ctx->s);
+        dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
+        pack_frame_kernel<T><<<grid, block, 0, ctx->stream>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+    }
+}
 static int launch_pack(HrContext *ctx) {
-    const int bx = ctx->s <= 3 ? 128 : 64;
-    dim3 block(bx, 1 << ctx->s);
-    dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
+    if (ctx->s > 6) return fail(ctx, "frames of more than %d lines are not supported", MAX_CALC_RES << 6);
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[4], ctx->stream));
-    if (ctx->bps == 1)
-        pack_frame_kernel<uint8_t><<<grid, block, 0, ctx->stream>>>((const uint8_t *)ctx->fy[1], (const uint8_t *)ctx->fuv[1], ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
-    else
-        pack_frame_kernel<uint16_t><<<grid, block, 0, ctx->stream>>>((const uint16_t *)ctx->fy[1], (const uint16_t *)ctx->fuv[1], ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+    if (ctx->bps == 1) launch_pack_t<uint8_t>(ctx);
+    else launch_pack_t<uint16_t>(ctx);
     CU(cudaGetLastError());
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[5], ctx->stream));

@@ -260,6 +260,27 @@ __device__ __forceinline__ uint2 load_run4_uv_odd(const uint16_t *p) {
     return make_uint2(__byte_perm(s0, s1, 0x7610), __byte_perm(s1, s2, 0x7610));
 }
 
+/* four samples at a frame border: each through the mirror + clamp of warpFrameKernel.cl:10-18 and,
+ * for chroma, the pair alignment of :171 */
+__device__ __forceinline__ uint32_t load_run4_border(const uint8_t *row, int cx0, int d, int aW, int cz) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nx = warp_mirror(cx0 + k + d, aW);
+        v |= (uint32_t)__ldg(row + (cz ? (nx & ~1) + (k & 1) : nx)) << (8 * k);
+    }
+    return v;
+}
+__device__ __forceinline__ uint2 load_run4_border(const uint16_t *row, int cx0, int d, int aW, int cz) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nx = warp_mirror(cx0 + k + d, aW);
+        v[k] = __ldg(row + (cz ? (nx & ~1) + (k & 1) : nx));
+    }
+    return make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+}
+
 template <typename T>
 struct RunType;
 template <>
@@ -270,6 +291,50 @@ template <>
 struct RunType<uint16_t> {
     typedef uint2 type;
 };
+
+/* two fp32 values in one 64-bit register pair: sm_100 executes add/mul/fma on both per instruction
+ * (FADD2 / FMUL2 / FFMA2), each half rounded exactly like the scalar instruction */
+typedef unsigned long long F2;
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ F2 f2_bits(uint32_t lo, uint32_t hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ float f2_lo(F2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float f2_hi(F2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add_rz(F2 a, F2 b) {
+    F2 r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 /* u8 / u16 -> f32 and back through the 2^23 magic number (exact for 0 <= v < 2^23) */
 #define HR_MAGIC 8388608.0f
@@ -283,7 +348,7 @@ __device__ __forceinline__ float half_to_float(uint32_t w, int k) {
 __device__ __forceinline__ uint32_t trunc_bits(float x) { return __float_as_uint(__fadd_rz(x, HR_MAGIC)); }
 
 template <typename T>
-__global__ void __launch_bounds__(256) warp_blend_kernel(const WarpParams<T> P, int useFast) {
+__global__ void __launch_bounds__(256, 6) warp_blend_kernel(const WarpParams<T> P, int useFast) {
     constexpr bool is16 = SampleTraits<T>::is16;
     const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int lumaGroups = (P.H + HR_WARP_ROWS - 1) / HR_WARP_ROWS;
@@ -313,69 +378,96 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const WarpParams<T> P, 
             const float ys = cz ? 0.5f : 1.0f;
             const int d12 = (int)roundf((float)f.x12 * P.t12), d21 = -(int)roundf((float)f.x21 * P.t21);
             const int e12 = (int)roundf((float)f.y12 * P.t12 * ys), e21 = -(int)roundf((float)f.y21 * P.t21 * ys);
-            /* every source column inside [1, aW-2]: the mirror/clamp of warpFrameKernel.cl:10-18 is the identity */
-            const bool in12 = P.mode == 1 || (cx0 + d12 >= 1 && cx0 + 3 + d12 <= P.aW - 2);
-            const bool in21 = P.mode == 0 || (cx0 + d21 >= 1 && cx0 + 3 + d21 <= P.aW - 2);
-            if (in12 && in21) {
-                const bool odd12 = cz && (d12 & 1), odd21 = cz && (d21 & 1);
-                const float rY = rcp_approx(P.white - P.black), rUV = rcp_approx(P.white);
-                const Levels16 L = make_levels16(P.black, P.white);
-                /* phase 1: the source runs of all rows (independent loads in flight together) */
-                typedef typename RunType<T>::type Run;
-                Run ra[HR_WARP_ROWS], rb[HR_WARP_ROWS];
+            /* every source column inside [1, aW-2]: the mirror/clamp of warpFrameKernel.cl:10-18 is the identity
+             * and the four samples are one run; otherwise (frame border) they are fetched one by one */
+            const bool in12 = cx0 + d12 >= 1 && cx0 + 3 + d12 <= P.aW - 2;
+            const bool in21 = cx0 + d21 >= 1 && cx0 + 3 + d21 <= P.aW - 2;
+            const bool odd12 = cz && (d12 & 1), odd21 = cz && (d21 & 1);
+            /* rows: inside [1, planeH-2] for all four rows -> consecutive source rows */
+            const bool rows12 = cy0 + e12 >= 1 && cy0 + HR_WARP_ROWS - 1 + e12 <= planeH - 2;
+            const bool rows21 = cy0 + e21 >= 1 && cy0 + HR_WARP_ROWS - 1 + e21 <= planeH - 2;
+            /* phase 1: the source runs of all rows (independent loads in flight together) */
+            typedef typename RunType<T>::type Run;
+            Run ra[HR_WARP_ROWS], rb[HR_WARP_ROWS];
 #pragma unroll
-                for (int r = 0; r < HR_WARP_ROWS; ++r) {
-                    const int cy = hr_min(cy0 + r, planeH - 1);
-                    const T *p12 = s12 + (size_t)warp_mirror(cy + e12, planeH) * P.W + cx0 + d12;
-                    const T *p21 = s21 + (size_t)warp_mirror(cy + e21, planeH) * P.W + cx0 + d21;
-                    ra[r] = rb[r] = Run();
-                    if (P.mode != 1) ra[r] = odd12 ? load_run4_uv_odd(p12 - 1) : load_run4(p12);
-                    if (P.mode != 0) rb[r] = odd21 ? load_run4_uv_odd(p21 - 1) : load_run4(p21);
+            for (int r = 0; r < HR_WARP_ROWS; ++r) {
+                const int cy = hr_min(cy0 + r, planeH - 1);
+                ra[r] = rb[r] = Run();
+                if (P.mode != 1) {
+                    const T *row = s12 + (rows12 ? cy + e12 : warp_mirror(cy + e12, planeH)) * P.W;
+                    if (in12) ra[r] = odd12 ? load_run4_uv_odd(row + cx0 + d12 - 1) : load_run4(row + cx0 + d12);
+                    else ra[r] = load_run4_border(row, cx0, d12, P.aW, cz);
                 }
-                /* phase 2: blend, levels, store */
+                if (P.mode != 0) {
+                    const T *row = s21 + (rows21 ? cy + e21 : warp_mirror(cy + e21, planeH)) * P.W;
+                    if (in21) rb[r] = odd21 ? load_run4_uv_odd(row + cx0 + d21 - 1) : load_run4(row + cx0 + d21);
+                    else rb[r] = load_run4_border(row, cx0, d21, P.aW, cz);
+                }
+            }
+            /* phase 2: blend, levels, store — two samples per instruction (FMUL2 / FFMA2 / FADD2) */
+            const F2 t12 = f2_make(P.t12, P.t12), t21 = f2_make(P.t21, P.t21);
+            const F2 negMagic = f2_make(-HR_MAGIC, -HR_MAGIC), magic = f2_make(HR_MAGIC, HR_MAGIC);
+            if constexpr (!is16) {
+                /* luma ((v - black) * rY) * 255, chroma fma((v - 128) * rUV, 255, 128): hr_warp.cuh header */
+                const float sub = cz ? 128.0f : P.black, rcp = cz ? rcp_approx(P.white) : rcp_approx(P.white - P.black);
+                const F2 nsub = f2_make(-sub, -sub), r2 = f2_make(rcp, rcp), k255 = f2_make(255.0f, 255.0f), k128 = f2_make(128.0f, 128.0f);
+                /* the clamp to [0,255] is only needed when the level map can leave that range */
+                const float xlo = cz ? __fmaf_rn((0.0f - sub) * rcp, 255.0f, 128.0f) : ((0.0f - sub) * rcp) * 255.0f;
+                const float xhi = cz ? __fmaf_rn((255.0f - sub) * rcp, 255.0f, 128.0f) : ((255.0f - sub) * rcp) * 255.0f;
+                const bool clampNeeded = !(fminf(xlo, xhi) >= 0.0f && fmaxf(xlo, xhi) < 256.0f);
 #pragma unroll
                 for (int r = 0; r < HR_WARP_ROWS; ++r) {
                     if (r >= nrows) break;
-                    T *po = out + (size_t)(cy0 + r) * P.W + cx0;
-                    if constexpr (!is16) {
-                        const uint32_t a = ra[r], b = rb[r];
-                        uint32_t o;
-                        if (P.mode == 0) o = a;
-                        else if (P.mode == 1) o = b;
-                        else {
-                            uint32_t res[4];
+                    uint32_t o;
+                    if (P.mode == 0) o = ra[r];
+                    else if (P.mode == 1) o = rb[r];
+                    else {
+                        uint32_t res[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                /* (uchar)(f1*s21 + f2*s12), then levels: warpFrameKernel.cl:175-180 */
-                                const float bl = __fmaf_rn(byte_to_float(a, k), P.t21, byte_to_float(b, k) * P.t12);
-                                const float v = __uint_as_float(trunc_bits(bl)) - HR_MAGIC;
-                                const float x = cz ? __fmaf_rn((v - 128.0f) * rUV, 255.0f, 128.0f) : ((v - P.black) * rY) * 255.0f;
-                                res[k] = trunc_bits(fmaxf(fminf(x, 255.0f), 0.0f));
-                            }
-                            o = __byte_perm(__byte_perm(res[0], res[1], 0x0040), __byte_perm(res[2], res[3], 0x0040), 0x5410);
+                        for (int k = 0; k < 4; k += 2) {
+                            const F2 a = f2_add(f2_bits(__byte_perm(ra[r], 0x4B000000u, 0x7540u + k), __byte_perm(ra[r], 0x4B000000u, 0x7541u + k)), negMagic);
+                            const F2 b = f2_add(f2_bits(__byte_perm(rb[r], 0x4B000000u, 0x7540u + k), __byte_perm(rb[r], 0x4B000000u, 0x7541u + k)), negMagic);
+                            /* (uchar)(f1*s21 + f2*s12): warpFrameKernel.cl:175-176 */
+                            const F2 v = f2_add(f2_add_rz(f2_fma(a, t21, f2_mul(b, t12)), magic), negMagic);
+                            F2 x = f2_mul(f2_add(v, nsub), r2);
+                            x = cz ? f2_fma(x, k255, k128) : f2_mul(x, k255);
+                            if (clampNeeded) x = f2_make(fmaxf(fminf(f2_lo(x), 255.0f), 0.0f), fmaxf(fminf(f2_hi(x), 255.0f), 0.0f));
+                            x = f2_add_rz(x, magic);
+                            res[k] = __float_as_uint(f2_lo(x));
+                            res[k + 1] = __float_as_uint(f2_hi(x));
                         }
-                        *reinterpret_cast<uint32_t *>(po) = o;
-                    } else {
-                        const uint2 a = ra[r], b = rb[r];
-                        uint2 o;
-                        if (P.mode == 0) o = a;
-                        else if (P.mode == 1) o = b;
-                        else {
-                            uint32_t res[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t wa = k < 2 ? a.x : a.y, wb = k < 2 ? b.x : b.y;
-                                const float bl = __fmaf_rn(half_to_float(wa, k & 1), P.t21, half_to_float(wb, k & 1) * P.t12);
-                                const float v = __uint_as_float(trunc_bits(fminf(bl, 65535.0f))) - HR_MAGIC;
-                                res[k] = cz ? levels_uv16(v, L) : levels_y16(v, L);
-                            }
-                            o = make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
-                        }
-                        *reinterpret_cast<uint2 *>(po) = o;
+                        o = __byte_perm(__byte_perm(res[0], res[1], 0x0040), __byte_perm(res[2], res[3], 0x0040), 0x5410);
                     }
+                    *reinterpret_cast<uint32_t *>(out + (cy0 + r) * P.W + cx0) = o;
                 }
-                done = true;
+            } else {
+                const Levels16 L = make_levels16(P.black, P.white);
+#pragma unroll
+                for (int r = 0; r < HR_WARP_ROWS; ++r) {
+                    if (r >= nrows) break;
+                    const uint2 a = ra[r], b = rb[r];
+                    uint2 o;
+                    if (P.mode == 0) o = a;
+                    else if (P.mode == 1) o = b;
+                    else {
+                        uint32_t res[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k += 2) {
+                            const uint32_t wa = k < 2 ? a.x : a.y, wb = k < 2 ? b.x : b.y;
+                            const F2 fa = f2_add(f2_bits(__byte_perm(wa, 0x4B000000u, 0x7510u), __byte_perm(wa, 0x4B000000u, 0x7532u)), negMagic);
+                            const F2 fb = f2_add(f2_bits(__byte_perm(wb, 0x4B000000u, 0x7510u), __byte_perm(wb, 0x4B000000u, 0x7532u)), negMagic);
+                            F2 bl = f2_fma(fa, t21, f2_mul(fb, t12));
+                            bl = f2_make(fminf(f2_lo(bl), 65535.0f), fminf(f2_hi(bl), 65535.0f));
+                            const F2 v = f2_add(f2_add_rz(bl, magic), negMagic);
+                            res[k] = cz ? levels_uv16(f2_lo(v), L) : levels_y16(f2_lo(v), L);
+                            res[k + 1] = cz ? levels_uv16(f2_hi(v), L) : levels_y16(f2_hi(v), L);
+                        }
+                        o = make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
+                    }
+                    *reinterpret_cast<uint2 *>(out + (cy0 + r) * P.W + cx0) = o;
+                }
             }
+            done = true;
         }
     }
     if (done) return;
