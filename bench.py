@@ -10,7 +10,7 @@ One "step" = one source frame of a 24->60 stream through the hot path:
   e2e        the same metric through the reference-facing call sequence with HOST buffers:
              updateFrame (H2D) / calculateOpticalFlow / warpFrames / downloadFrame (D2H) per output.
   roofline   dominant kernel of the step by device time, timed with CUDA events on the launch
-             stream in a separate instrumented pass over the same steps.
+             stream over whole loops of the same steps (by difference: search only / + pack / + warps).
   cpu_baseline   the CPU oracle (C restatement of the reference kernels, OpenMP) on a bounded
              sample of the same workload, rank 0, N=1 only.
 
@@ -273,29 +273,41 @@ def run_ours(args):
         launches = g.launch_count() - l0
         ms = e0.elapsed_time(e1)
 
-    # ---- instrumented pass: per-kernel device time over the same steps ---------------------------
+    # ---- per-kernel device time, by difference -------------------------------------------------------
+    # One CUDA event pair around a single ~5-40 us launch adds several us of front-end latency to it, so
+    # the three kernels are timed over whole loops instead (two events per loop, stream kept full):
+    #   A: search only            B: pack + search            C: pack + search + warps (= the timed region)
+    #   search = A / n,  pack = (B - A) / n,  warp = (C - B) / (number of warps)
     with torch.cuda.stream(stream):
-        ev = {"pack": [], "search": [], "warp": []}
-
-        def timed(kind, fn):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            fn()
-            b.record(stream)
-            ev[kind].append((a, b))
-
         nk = min(K, 100)
-        for i in range(nk):
-            y, uv = ring[(W_ + i) % nring]
-            timed("pack", lambda: g.update_frame_device(y, uv, borrow=True))
-            timed("search", lambda: g.calc_flow(radius, 8, 6, blocking=False))
-            for t in ts[W_ + i]:
-                oy, ouv = out_ring[oi[0] % len(out_ring)]
-                oi[0] += 1
-                g.set_output_device(oy, ouv)
-                timed("warp", lambda: g.warp(t, mode))
-        barrier()
-        kms = {k: [a.elapsed_time(b) for a, b in v] for k, v in ev.items()}
+
+        def loop(with_pack, with_warp):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(2):                      # first repetition warms the variant up
+                if rep == 1:
+                    e0.record(stream)
+                nw = 0
+                for i in range(nk):
+                    if with_pack:
+                        y, uv = ring[(W_ + i) % nring]
+                        g.update_frame_device(y, uv, borrow=True)
+                    g.calc_flow(radius, 8, 6, blocking=False)
+                    if with_warp:
+                        for t in ts[W_ + i]:
+                            oy, ouv = out_ring[oi[0] % len(out_ring)]
+                            oi[0] += 1
+                            g.set_output_device(oy, ouv)
+                            g.warp(t, mode)
+                            nw += 1
+            e1.record(stream)
+            barrier()
+            return e0.elapsed_time(e1), nw
+
+        tA, _ = loop(False, False)
+        tB, _ = loop(True, False)
+        tC, nwarps = loop(True, True)
+        kms = {"search": [tA / nk], "pack": [max(tB - tA, 0.0) / nk], "warp": [max(tC - tB, 0.0) / max(1, nwarps)] * max(1, nwarps)}
+        kcount = {"search": nk, "pack": nk, "warp": nwarps}
     g.set_output_device(None, None)
 
     # ---- end-to-end through the reference-facing interface, host buffers -------------------------
@@ -351,7 +363,7 @@ def run_ours(args):
     if rank == 0:
         pk, pk_src = peaks()
         avg = {k: float(np.mean(v)) if v else 0.0 for k, v in kms.items()}            # ms per launch
-        per_step = {"pack": avg["pack"], "search": avg["search"], "warp": avg["warp"] * (len(kms["warp"]) / max(1, len(kms["search"])))}
+        per_step = {"pack": avg["pack"], "search": avg["search"], "warp": avg["warp"] * (kcount["warp"] / max(1, kcount["search"]))}
         dom = max(per_step, key=per_step.get)
         wbytes = warp_bytes(w, h, bps, lw, lh)
         # algorithmic bytes per launch

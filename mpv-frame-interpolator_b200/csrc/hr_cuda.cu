@@ -539,8 +539,11 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.t21 = 1.0f - t;
     P.black = black;
     P.white = white;
-    /* thread = 4 samples x HR_WARP_ROWS rows; row groups of the luma plane, then of the chroma plane */
-    const int groups = (ctx->H + HR_WARP_ROWS - 1) / HR_WARP_ROWS + ((ctx->H >> 1) + HR_WARP_ROWS - 1) / HR_WARP_ROWS;
+    /* thread = 4 samples x ROWS rows (8 when the lattice cell is at least 8 rows tall, else 4); row groups of
+     * the luma plane, then of the chroma plane */
+    const int ROWS = ctx->s >= 3 ? 8 : 4;
+    const int lumaGroups = (ctx->H + ROWS - 1) / ROWS;
+    const int groups = lumaGroups + ((ctx->H >> 1) + ROWS - 1) / ROWS;
     dim3 block(32, 8);
     dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
     /* the block path: 4x4 blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in
@@ -550,7 +553,8 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
                (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], ctx->stream));
-    warp_blend_kernel<T><<<grid, block, 0, ctx->stream>>>(P, fast);
+    if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups);
+    else warp_blend_kernel<T, 4><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups);
     CU(cudaGetLastError());
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[3], ctx->stream));

@@ -220,7 +220,6 @@ __device__ unsigned warp_sample(const WarpParams<T> &P, int cx, int cy, int cz) 
 }
 
 /* ---- the block path ------------------------------------------------------------------------------ */
-#define HR_WARP_ROWS 4 /* rows per thread; a 4x4 block lies inside one lattice cell when s >= 2 */
 
 /* four consecutive samples from an arbitrary (sample-aligned) address, built from aligned loads */
 __device__ __forceinline__ uint32_t load_run4(const uint8_t *p) {
@@ -347,20 +346,125 @@ __device__ __forceinline__ float half_to_float(uint32_t w, int k) {
 /* trunc(x) for 0 <= x < 2^23 as the bits 0x4B000000 | trunc(x) */
 __device__ __forceinline__ uint32_t trunc_bits(float x) { return __float_as_uint(__fadd_rz(x, HR_MAGIC)); }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 6) warp_blend_kernel(const WarpParams<T> P, int useFast) {
+/* blend + levels of four 8-bit sample pairs (one 32-bit word each) -> four output bytes.
+ * (uchar)(f1*s21 + f2*s12), then luma ((v - black) * rY) * 255 / chroma fma((v - 128) * rUV, 255, 128):
+ * warpFrameKernel.cl:1-7,175-180 as compiled for NVIDIA OpenCL devices (header of this file). */
+struct Blend8 {
+    F2 t12, t21, negMagic, magic, nsub, rcp, k255, k128;
+    bool chroma, clampNeeded;
+};
+__device__ __forceinline__ Blend8 make_blend8(float t12, float t21, float black, float white, int cz) {
+    Blend8 B;
+    const float sub = cz ? 128.0f : black, rcp = cz ? rcp_approx(white) : rcp_approx(white - black);
+    B.t12 = f2_make(t12, t12);
+    B.t21 = f2_make(t21, t21);
+    B.negMagic = f2_make(-HR_MAGIC, -HR_MAGIC);
+    B.magic = f2_make(HR_MAGIC, HR_MAGIC);
+    B.nsub = f2_make(-sub, -sub);
+    B.rcp = f2_make(rcp, rcp);
+    B.k255 = f2_make(255.0f, 255.0f);
+    B.k128 = f2_make(128.0f, 128.0f);
+    B.chroma = cz != 0;
+    /* the clamp to [0,255] is only needed when the level map can leave that range (it is monotonic) */
+    const float xlo = cz ? __fmaf_rn((0.0f - sub) * rcp, 255.0f, 128.0f) : ((0.0f - sub) * rcp) * 255.0f;
+    const float xhi = cz ? __fmaf_rn((255.0f - sub) * rcp, 255.0f, 128.0f) : ((255.0f - sub) * rcp) * 255.0f;
+    B.clampNeeded = !(fminf(xlo, xhi) >= 0.0f && fmaxf(xlo, xhi) < 256.0f);
+    return B;
+}
+template <bool CLAMP>
+__device__ __forceinline__ uint32_t blend8_quad(const Blend8 &B, uint32_t wa, uint32_t wb) {
+    uint32_t res[4];
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+        const F2 a = f2_add(f2_bits(__byte_perm(wa, 0x4B000000u, 0x7540u + k), __byte_perm(wa, 0x4B000000u, 0x7541u + k)), B.negMagic);
+        const F2 b = f2_add(f2_bits(__byte_perm(wb, 0x4B000000u, 0x7540u + k), __byte_perm(wb, 0x4B000000u, 0x7541u + k)), B.negMagic);
+        const F2 v = f2_add(f2_add_rz(f2_fma(a, B.t21, f2_mul(b, B.t12)), B.magic), B.negMagic);
+        F2 x = f2_mul(f2_add(v, B.nsub), B.rcp);
+        x = B.chroma ? f2_fma(x, B.k255, B.k128) : f2_mul(x, B.k255);
+        if (CLAMP) x = f2_make(fmaxf(fminf(f2_lo(x), 255.0f), 0.0f), fmaxf(fminf(f2_hi(x), 255.0f), 0.0f));
+        x = f2_add_rz(x, B.magic);
+        res[k] = __float_as_uint(f2_lo(x));
+        res[k + 1] = __float_as_uint(f2_hi(x));
+    }
+    return __byte_perm(__byte_perm(res[0], res[1], 0x0040), __byte_perm(res[2], res[3], 0x0040), 0x5410);
+}
+/* the same for four 16-bit pairs (P010) */
+__device__ __forceinline__ uint2 blend16_quad(const F2 &t12, const F2 &t21, const Levels16 &L, int cz, uint2 a, uint2 b) {
+    const F2 negMagic = f2_make(-HR_MAGIC, -HR_MAGIC), magic = f2_make(HR_MAGIC, HR_MAGIC);
+    uint32_t res[4];
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+        const uint32_t wa = k < 2 ? a.x : a.y, wb = k < 2 ? b.x : b.y;
+        const F2 fa = f2_add(f2_bits(__byte_perm(wa, 0x4B000000u, 0x7510u), __byte_perm(wa, 0x4B000000u, 0x7532u)), negMagic);
+        const F2 fb = f2_add(f2_bits(__byte_perm(wb, 0x4B000000u, 0x7510u), __byte_perm(wb, 0x4B000000u, 0x7532u)), negMagic);
+        F2 bl = f2_fma(fa, t21, f2_mul(fb, t12));
+        bl = f2_make(fminf(f2_lo(bl), 65535.0f), fminf(f2_hi(bl), 65535.0f));
+        const F2 v = f2_add(f2_add_rz(bl, magic), negMagic);
+        res[k] = cz ? levels_uv16(f2_lo(v), L) : levels_y16(f2_lo(v), L);
+        res[k + 1] = cz ? levels_uv16(f2_hi(v), L) : levels_y16(f2_hi(v), L);
+    }
+    return make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
+}
+
+/* ROWS consecutive source rows of one 4-sample column, for a run that lies inside the frame: the first
+ * word and the alignment are computed once, every row is two (chroma, odd displacement: three) aligned
+ * 32-bit loads and a funnel shift. o = sample offset of the run's first sample in the plane. */
+template <int ROWS>
+__device__ __forceinline__ void load_rows_interior(const uint8_t *plane, int o, int W, bool odd, uint32_t (&out)[ROWS]) {
+    if (odd) o -= 1; /* six samples from cx0+d-1, picked 0,3,2,5 (see load_run4_uv_odd) */
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(plane) + (o >> 2);
+    const unsigned sh = (unsigned)(o & 3) * 8;
+    const int W4 = W >> 2;
+    if (!odd) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) out[r] = __funnelshift_r(__ldg(q + r * W4), __ldg(q + r * W4 + 1), sh);
+    } else {
+        const bool third = (o & 3) == 3;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t w0 = __ldg(q + r * W4), w1 = __ldg(q + r * W4 + 1), w2 = third ? __ldg(q + r * W4 + 2) : 0u;
+            out[r] = __byte_perm(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), 0x5230);
+        }
+    }
+}
+template <int ROWS>
+__device__ __forceinline__ void load_rows_interior(const uint16_t *plane, int o, int W, bool odd, uint2 (&out)[ROWS]) {
+    if (odd) o -= 1;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(plane) + (o >> 1);
+    const unsigned sh = (unsigned)(o & 1) * 16;
+    const int W2 = W >> 1;
+    if (!odd) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t w0 = __ldg(q + r * W2), w1 = __ldg(q + r * W2 + 1), w2 = sh ? __ldg(q + r * W2 + 2) : 0u;
+            out[r] = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t w0 = __ldg(q + r * W2), w1 = __ldg(q + r * W2 + 1), w2 = __ldg(q + r * W2 + 2), w3 = sh ? __ldg(q + r * W2 + 3) : 0u;
+            const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh);
+            out[r] = make_uint2(__byte_perm(s0, s1, 0x7610), __byte_perm(s1, s2, 0x7610));
+        }
+    }
+}
+
+/* ROWS = rows per thread (4, or 8 when the lattice cell is at least 8 rows tall): thread = 4 samples x
+ * ROWS rows. lumaGroups = ceil(H / ROWS): row groups of the luma plane come first, then the chroma plane's. */
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 4 ? 6 : 4) warp_blend_kernel(const WarpParams<T> P, int useFast, int lumaGroups) {
     constexpr bool is16 = SampleTraits<T>::is16;
+    typedef typename RunType<T>::type Run;
     const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int lumaGroups = (P.H + HR_WARP_ROWS - 1) / HR_WARP_ROWS;
     const int rg = blockIdx.y * blockDim.y + threadIdx.y;
     const int cz = rg >= lumaGroups;
-    const int cy0 = (cz ? rg - lumaGroups : rg) * HR_WARP_ROWS;
+    const int cy0 = (cz ? rg - lumaGroups : rg) * ROWS;
     const int planeH = cz ? (P.H >> 1) : P.H;
     if (cx0 >= P.aW || cy0 >= planeH) return;
     const T *s12 = cz ? P.f1uv : P.f1y;
     const T *s21 = cz ? P.f2uv : P.f2y;
     T *out = cz ? P.outUV : P.outY;
-    const int nrows = hr_min(HR_WARP_ROWS, planeH - cy0);
+    const int nrows = hr_min(ROWS, planeH - cy0);
 
     bool done = false;
     if (useFast && cx0 + 3 < P.aW) {
@@ -383,89 +487,56 @@ __global__ void __launch_bounds__(256, 6) warp_blend_kernel(const WarpParams<T> 
             const bool in12 = cx0 + d12 >= 1 && cx0 + 3 + d12 <= P.aW - 2;
             const bool in21 = cx0 + d21 >= 1 && cx0 + 3 + d21 <= P.aW - 2;
             const bool odd12 = cz && (d12 & 1), odd21 = cz && (d21 & 1);
-            /* rows: inside [1, planeH-2] for all four rows -> consecutive source rows */
-            const bool rows12 = cy0 + e12 >= 1 && cy0 + HR_WARP_ROWS - 1 + e12 <= planeH - 2;
-            const bool rows21 = cy0 + e21 >= 1 && cy0 + HR_WARP_ROWS - 1 + e21 <= planeH - 2;
-            /* phase 1: the source runs of all rows (independent loads in flight together) */
-            typedef typename RunType<T>::type Run;
-            Run ra[HR_WARP_ROWS], rb[HR_WARP_ROWS];
+            /* rows inside [1, planeH-2] for all rows of the block -> consecutive source rows */
+            const bool rows12 = cy0 + e12 >= 1 && cy0 + ROWS - 1 + e12 <= planeH - 2;
+            const bool rows21 = cy0 + e21 >= 1 && cy0 + ROWS - 1 + e21 <= planeH - 2;
+            Run ra[ROWS], rb[ROWS];
+            if (in12 && in21 && rows12 && rows21 && P.mode >= 2) {
+                /* the common case: both source blocks lie inside the frame */
+                load_rows_interior<ROWS>(s12, (cy0 + e12) * P.W + cx0 + d12, P.W, odd12, ra);
+                load_rows_interior<ROWS>(s21, (cy0 + e21) * P.W + cx0 + d21, P.W, odd21, rb);
+            } else {
 #pragma unroll
-            for (int r = 0; r < HR_WARP_ROWS; ++r) {
-                const int cy = hr_min(cy0 + r, planeH - 1);
-                ra[r] = rb[r] = Run();
-                if (P.mode != 1) {
-                    const T *row = s12 + (rows12 ? cy + e12 : warp_mirror(cy + e12, planeH)) * P.W;
-                    if (in12) ra[r] = odd12 ? load_run4_uv_odd(row + cx0 + d12 - 1) : load_run4(row + cx0 + d12);
-                    else ra[r] = load_run4_border(row, cx0, d12, P.aW, cz);
-                }
-                if (P.mode != 0) {
-                    const T *row = s21 + (rows21 ? cy + e21 : warp_mirror(cy + e21, planeH)) * P.W;
-                    if (in21) rb[r] = odd21 ? load_run4_uv_odd(row + cx0 + d21 - 1) : load_run4(row + cx0 + d21);
-                    else rb[r] = load_run4_border(row, cx0, d21, P.aW, cz);
+                for (int r = 0; r < ROWS; ++r) {
+                    const int cy = hr_min(cy0 + r, planeH - 1);
+                    ra[r] = rb[r] = Run();
+                    if (P.mode != 1) {
+                        const T *row = s12 + (size_t)warp_mirror(cy + e12, planeH) * P.W;
+                        if (in12) ra[r] = odd12 ? load_run4_uv_odd(row + cx0 + d12 - 1) : load_run4(row + cx0 + d12);
+                        else ra[r] = load_run4_border(row, cx0, d12, P.aW, cz);
+                    }
+                    if (P.mode != 0) {
+                        const T *row = s21 + (size_t)warp_mirror(cy + e21, planeH) * P.W;
+                        if (in21) rb[r] = odd21 ? load_run4_uv_odd(row + cx0 + d21 - 1) : load_run4(row + cx0 + d21);
+                        else rb[r] = load_run4_border(row, cx0, d21, P.aW, cz);
+                    }
                 }
             }
-            /* phase 2: blend, levels, store — two samples per instruction (FMUL2 / FFMA2 / FADD2) */
-            const F2 t12 = f2_make(P.t12, P.t12), t21 = f2_make(P.t21, P.t21);
-            const F2 negMagic = f2_make(-HR_MAGIC, -HR_MAGIC), magic = f2_make(HR_MAGIC, HR_MAGIC);
+            /* blend, levels, store — two samples per instruction (FMUL2 / FFMA2 / FADD2) */
+            T *po = out + cy0 * P.W + cx0;
             if constexpr (!is16) {
-                /* luma ((v - black) * rY) * 255, chroma fma((v - 128) * rUV, 255, 128): hr_warp.cuh header */
-                const float sub = cz ? 128.0f : P.black, rcp = cz ? rcp_approx(P.white) : rcp_approx(P.white - P.black);
-                const F2 nsub = f2_make(-sub, -sub), r2 = f2_make(rcp, rcp), k255 = f2_make(255.0f, 255.0f), k128 = f2_make(128.0f, 128.0f);
-                /* the clamp to [0,255] is only needed when the level map can leave that range */
-                const float xlo = cz ? __fmaf_rn((0.0f - sub) * rcp, 255.0f, 128.0f) : ((0.0f - sub) * rcp) * 255.0f;
-                const float xhi = cz ? __fmaf_rn((255.0f - sub) * rcp, 255.0f, 128.0f) : ((255.0f - sub) * rcp) * 255.0f;
-                const bool clampNeeded = !(fminf(xlo, xhi) >= 0.0f && fmaxf(xlo, xhi) < 256.0f);
+                if (P.mode < 2) {
 #pragma unroll
-                for (int r = 0; r < HR_WARP_ROWS; ++r) {
-                    if (r >= nrows) break;
-                    uint32_t o;
-                    if (P.mode == 0) o = ra[r];
-                    else if (P.mode == 1) o = rb[r];
-                    else {
-                        uint32_t res[4];
+                    for (int r = 0; r < ROWS; ++r)
+                        if (r < nrows) *reinterpret_cast<uint32_t *>(po + r * P.W) = P.mode == 0 ? ra[r] : rb[r];
+                } else {
+                    const Blend8 B = make_blend8(P.t12, P.t21, P.black, P.white, cz);
+                    if (B.clampNeeded) {
 #pragma unroll
-                        for (int k = 0; k < 4; k += 2) {
-                            const F2 a = f2_add(f2_bits(__byte_perm(ra[r], 0x4B000000u, 0x7540u + k), __byte_perm(ra[r], 0x4B000000u, 0x7541u + k)), negMagic);
-                            const F2 b = f2_add(f2_bits(__byte_perm(rb[r], 0x4B000000u, 0x7540u + k), __byte_perm(rb[r], 0x4B000000u, 0x7541u + k)), negMagic);
-                            /* (uchar)(f1*s21 + f2*s12): warpFrameKernel.cl:175-176 */
-                            const F2 v = f2_add(f2_add_rz(f2_fma(a, t21, f2_mul(b, t12)), magic), negMagic);
-                            F2 x = f2_mul(f2_add(v, nsub), r2);
-                            x = cz ? f2_fma(x, k255, k128) : f2_mul(x, k255);
-                            if (clampNeeded) x = f2_make(fmaxf(fminf(f2_lo(x), 255.0f), 0.0f), fmaxf(fminf(f2_hi(x), 255.0f), 0.0f));
-                            x = f2_add_rz(x, magic);
-                            res[k] = __float_as_uint(f2_lo(x));
-                            res[k + 1] = __float_as_uint(f2_hi(x));
-                        }
-                        o = __byte_perm(__byte_perm(res[0], res[1], 0x0040), __byte_perm(res[2], res[3], 0x0040), 0x5410);
+                        for (int r = 0; r < ROWS; ++r)
+                            if (r < nrows) *reinterpret_cast<uint32_t *>(po + r * P.W) = blend8_quad<true>(B, ra[r], rb[r]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r)
+                            if (r < nrows) *reinterpret_cast<uint32_t *>(po + r * P.W) = blend8_quad<false>(B, ra[r], rb[r]);
                     }
-                    *reinterpret_cast<uint32_t *>(out + (cy0 + r) * P.W + cx0) = o;
                 }
             } else {
                 const Levels16 L = make_levels16(P.black, P.white);
+                const F2 t12 = f2_make(P.t12, P.t12), t21 = f2_make(P.t21, P.t21);
 #pragma unroll
-                for (int r = 0; r < HR_WARP_ROWS; ++r) {
-                    if (r >= nrows) break;
-                    const uint2 a = ra[r], b = rb[r];
-                    uint2 o;
-                    if (P.mode == 0) o = a;
-                    else if (P.mode == 1) o = b;
-                    else {
-                        uint32_t res[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k += 2) {
-                            const uint32_t wa = k < 2 ? a.x : a.y, wb = k < 2 ? b.x : b.y;
-                            const F2 fa = f2_add(f2_bits(__byte_perm(wa, 0x4B000000u, 0x7510u), __byte_perm(wa, 0x4B000000u, 0x7532u)), negMagic);
-                            const F2 fb = f2_add(f2_bits(__byte_perm(wb, 0x4B000000u, 0x7510u), __byte_perm(wb, 0x4B000000u, 0x7532u)), negMagic);
-                            F2 bl = f2_fma(fa, t21, f2_mul(fb, t12));
-                            bl = f2_make(fminf(f2_lo(bl), 65535.0f), fminf(f2_hi(bl), 65535.0f));
-                            const F2 v = f2_add(f2_add_rz(bl, magic), negMagic);
-                            res[k] = cz ? levels_uv16(f2_lo(v), L) : levels_y16(f2_lo(v), L);
-                            res[k + 1] = cz ? levels_uv16(f2_hi(v), L) : levels_y16(f2_hi(v), L);
-                        }
-                        o = make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
-                    }
-                    *reinterpret_cast<uint2 *>(out + (cy0 + r) * P.W + cx0) = o;
-                }
+                for (int r = 0; r < ROWS; ++r)
+                    if (r < nrows) *reinterpret_cast<uint2 *>(po + r * P.W) = P.mode == 0 ? ra[r] : P.mode == 1 ? rb[r] : blend16_quad(t12, t21, L, cz, ra[r], rb[r]);
             }
             done = true;
         }
