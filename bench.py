@@ -349,16 +349,16 @@ def run_ours(args):
         hr.freeOFC(ofc)
         del npdt
 
-    # ---- reduce over ranks -----------------------------------------------------------------------
-    tot_outs, max_ms = outs, ms
+    # ---- reduce over ranks (sharding.py: the N > 1 host logic, covered on CPU by tests/test_sharding_cpu.py) ----
+    from hopperrender_b200 import sharding
+
+    dev = torch.device("cuda", local)
+    tot_outs, max_s = sharding.reduce_throughput(outs, ms * 1e-3, dist, dev)
+    max_ms = max_s * 1e3
     e_outs, e_dt = (e2e[0], e2e[1]) if e2e else (0, 1.0)
-    if dist:
-        t = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        c = torch.tensor([outs, e_outs, launches], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        max_ms, e_dt = float(t[0]), float(t[1])
-        tot_outs, e_outs, launches = int(c[0]), int(c[1]), int(c[2])
+    if e2e:
+        e_outs, e_dt = sharding.reduce_throughput(e_outs, e_dt, dist, dev)
+    launches, _ = sharding.reduce_throughput(launches, 0.0, dist, dev)
 
     if rank == 0:
         pk, pk_src = peaks()

@@ -14,11 +14,14 @@
  *   video/filter/HopperRender/Kernels/warpFrameKernel.cl:1-182               (K5)
  *   video/filter/HopperRender/opticalFlowCalc.c:96-107,126-234,323-364       (driver)
  *
- * PARITY PIN STATUS: the reference ships no golden vectors, known-answer tests or
- * fixtures for this path. This restatement is pinned instead
- * against the reference kernels THEMSELVES, compiled from /root/reference by the
- * recipe oracle/build_ref.py into oracle/_ref/ (see that file's header) and compared
- * in tests/test_oracle_vs_ref.py; fixtures generated that way live in tests/golden/.
+ * PARITY PIN STATUS: pinned. The reference ships no golden vectors, known-answer tests or
+ * fixtures for this path, so the pin is the reference ITSELF: its unmodified
+ * opticalFlowCalc.c + .cl kernels are built from /root/reference by oracle/build_ref.py into
+ * oracle/_ref/ and executed on the B200 through the NVIDIA OpenCL ICD (oracle/ref_opencl.py).
+ *   - tests/golden/reference_vectors.npz (made on the GPU box by tests/golden/make_reference_vectors.py)
+ *     holds that run's offsets, window sums and output digests for five seeded cases;
+ *     tests/test_oracle_golden_cpu.py checks this restatement against them bit for bit, no GPU needed.
+ *   - tests/test_gpu_vs_reference_opencl.py compares oracle, reference and CUDA path live on the GPU box.
  *
  * Deliberate deviations from reference UB, identical in the
  * CUDA path:
