@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bands", action="store_true",
+                    help="split every frame into spatial bands over the N ranks (8K config, SURVEY.md §8e): strong scaling, "
+                         "bands uploaded/warped/downloaded per GPU, the other bands pulled by NVLink P2P")
     return ap.parse_args()
 
 
@@ -215,18 +218,28 @@ def run_ours(args):
     nring = max(8, (2 * L2_BYTES) // frame_bytes + 2)
     nring = min(nring, 96)
     clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
-    base = [clip.frame(k) for k in range(8)]
+    nbase = 8 if frame_bytes < (64 << 20) else 4
+    base = [clip.frame(k) for k in range(nbase)]
     stream = torch.cuda.Stream()
     g = hr.HrCuda(h, w, w, pixfmt, device=local)
     g.set_stream(stream.cuda_stream)
     lw, lh = g.info.lowWidth, g.info.lowHeight
+    banded = bool(args.bands) and world > 1
+    r0, r1 = 0, h
+    if banded:
+        from hopperrender_b200 import sharding
+
+        rows = sharding.band_rows(h, world, g.info.resScalar)
+        hr.connect_bands_distributed(g, dist, rows)
+        r0, r1 = rows[rank]
+        nring = max(8, min(96, nring * world))      # a rank keeps only its band of every ring frame
     with torch.cuda.stream(stream):
         ring = []
         for k in range(nring):
-            y, uv = base[k % 8]
-            # a different roll per slot keeps slots distinct without regenerating textures
-            ring.append((torch.from_numpy(np.ascontiguousarray(y)).to("cuda", non_blocking=False).view(tdtype),
-                         torch.from_numpy(np.ascontiguousarray(uv)).to("cuda", non_blocking=False).view(tdtype)))
+            y, uv = base[k % nbase]
+            # banded: only this rank's rows live on this GPU
+            ring.append((torch.from_numpy(np.ascontiguousarray(y[r0:r1])).to("cuda", non_blocking=False).view(tdtype),
+                         torch.from_numpy(np.ascontiguousarray(uv[r0 >> 1:r1 >> 1])).to("cuda", non_blocking=False).view(tdtype)))
         out_ring = [(torch.empty((h, w), dtype=tdtype, device="cuda"), torch.empty((h // 2, w), dtype=tdtype, device="cuda")) for _ in range(max(4, (L2_BYTES // frame_bytes) + 2))]
     stream.synchronize()
     K, W_ = args.steps, max(3, args.warmup)
@@ -235,9 +248,16 @@ def run_ours(args):
 
     oi = [0]
 
-    def step_device(i):
+    def feed(i):
         y, uv = ring[i % nring]
-        g.update_frame_device(y, uv, borrow=True)
+        if banded:
+            g.band_upload(y, uv, device=True)       # own band (device copy) ...
+            g.band_gather(blocking=False)           # ... the others by P2P, then pack
+        else:
+            g.update_frame_device(y, uv, borrow=True)
+
+    def step_device(i):
+        feed(i)
         g.calc_flow(radius, 8, 6, blocking=False)
         for t in ts[i]:
             oy, ouv = out_ring[oi[0] % len(out_ring)]
@@ -254,7 +274,7 @@ def run_ours(args):
 
     # ---- device-resident timed region ---------------------------------------------------------
     with torch.cuda.stream(stream):
-        g.update_frame_device(*ring[nring - 1], borrow=True)
+        feed(nring - 1)
         for i in range(W_):
             step_device(i)
         barrier()
@@ -289,8 +309,7 @@ def run_ours(args):
                 nw = 0
                 for i in range(nk):
                     if with_pack:
-                        y, uv = ring[(W_ + i) % nring]
-                        g.update_frame_device(y, uv, borrow=True)
+                        feed(W_ + i)
                     g.calc_flow(radius, 8, 6, blocking=False)
                     if with_warp:
                         for t in ts[W_ + i]:
@@ -319,25 +338,36 @@ def run_ours(args):
         ofc.opticalFlowSearchRadius = radius
         npdt = np.uint16 if pixfmt else np.uint8
         hring = []
-        for k in range(8):
+        for k in range(nbase):
             y, uv = base[k]
-            ty = torch.from_numpy(np.ascontiguousarray(y)).pin_memory()
-            tuv = torch.from_numpy(np.ascontiguousarray(uv)).pin_memory()
+            ty = torch.from_numpy(np.ascontiguousarray(y[r0:r1])).pin_memory()
+            tuv = torch.from_numpy(np.ascontiguousarray(uv[r0 >> 1:r1 >> 1])).pin_memory()
             hring.append((ty, tuv))
-        hout = (torch.empty((h, w), dtype=tdtype).pin_memory(), torch.empty((h // 2, w), dtype=tdtype).pin_memory())
+        hout = (torch.empty((r1 - r0, w), dtype=tdtype).pin_memory(), torch.empty(((r1 >> 1) - (r0 >> 1), w), dtype=tdtype).pin_memory())
         Ke = min(K, 100)
         We = min(W_, 5)
+        if banded:
+            hr.connect_bands_distributed(ofc.impl, dist, rows)
+
+        def update_host(ty, tuv):
+            if banded:                                      # a rank moves only its band over PCIe
+                ofc.impl.band_upload(ty, tuv)
+                ofc.impl.band_gather(blocking=True)
+            else:
+                assert not hr.updateFrame(ofc, [ty, tuv])
 
         def step_host(i):
-            ty, tuv = hring[i % 8]
-            assert not hr.updateFrame(ofc, [ty, tuv])
+            update_host(*hring[i % nbase])
             assert not hr.calculateOpticalFlow(ofc)
             for t in ts[i]:
                 assert not hr.warpFrames(ofc, t, mode)
-                assert not hr.downloadFrame(ofc, [hout[0], hout[1]])
+                if banded:
+                    ofc.impl.band_download(hout[0], hout[1])
+                else:
+                    assert not hr.downloadFrame(ofc, [hout[0], hout[1]])
             return len(ts[i])
 
-        hr.updateFrame(ofc, [hring[7][0], hring[7][1]])
+        update_host(*hring[nbase - 1])
         for i in range(We):
             step_host(i)
         barrier()
@@ -358,6 +388,9 @@ def run_ours(args):
     e_outs, e_dt = (e2e[0], e2e[1]) if e2e else (0, 1.0)
     if e2e:
         e_outs, e_dt = sharding.reduce_throughput(e_outs, e_dt, dist, dev)
+    if banded:          # every rank produced a band of the SAME frames: count each frame once
+        tot_outs //= world
+        e_outs //= world
     launches, _ = sharding.reduce_throughput(launches, 0.0, dist, dev)
 
     if rank == 0:
@@ -365,7 +398,7 @@ def run_ours(args):
         avg = {k: float(np.mean(v)) if v else 0.0 for k, v in kms.items()}            # ms per launch
         per_step = {"pack": avg["pack"], "search": avg["search"], "warp": avg["warp"] * (kcount["warp"] / max(1, kcount["search"]))}
         dom = max(per_step, key=per_step.get)
-        wbytes = warp_bytes(w, h, bps, lw, lh)
+        wbytes = int(warp_bytes(w, h, bps, lw, lh) * ((r1 - r0) / h))   # a band's launch moves the band's rows
         # algorithmic bytes per launch
         alg = {
             "warp": wbytes,
@@ -385,10 +418,11 @@ def run_ours(args):
             roof["search"]["note"] = "latency/ALU bound (16 dependent steps, grid barriers): HBM fraction is not the limiter, see DESIGN.md"
         line = {
             "metric": "interpolated frames/s", "value": tot_outs / (max_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
-            "steps": K, "warmup": W_, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "steps": K, "warmup": W_, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "strong" if banded else "weak", "vs_baseline": None,
             "dtype": "u8" if pixfmt == 0 else "u16", "data": "synthetic",
             "config": {"workload": args.workload, "frame": "%dx%d" % (w, h), "search_radius": radius, "mode": mode,
-                       "streams_per_gpu": 1, "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (nring, nring * frame_bytes >> 20),
+                       "streams_per_gpu": 1, "partition": ("%d spatial bands, NVLink P2P gather" % world) if banded else ("independent streams" if world > 1 else "none"),
+                       "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (nring, nring * frame_bytes >> 20),
                        "flow_ms_per_pair": avg["search"], "interp_only_frames_per_s": None},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -397,8 +431,9 @@ def run_ours(args):
             "dominant_kernel": dom,
         }
         if e2e:
-            line["e2e"] = {"value": e_outs / e_dt, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
-                           "d2h_bytes_per_step": int(frame_bytes * (e2e[0] / e2e[2])), "steps": e2e[2],
+            band_frac = (r1 - r0) / h
+            line["e2e"] = {"value": e_outs / e_dt, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes * band_frac),
+                           "d2h_bytes_per_step": int(frame_bytes * band_frac * (e2e[0] / e2e[2])), "steps": e2e[2],
                            "api": "initOpticalFlowCalc/updateFrame/calculateOpticalFlow/warpFrames/downloadFrame, pinned host planes, blocking like the reference"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

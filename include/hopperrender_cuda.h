@@ -113,6 +113,31 @@ int hr_get_output_device(HrContext *ctx, void **dYPlane, void **dUvPlane);
  * (NULL, NULL restores the internal buffer). */
 int hr_set_output_device(HrContext *ctx, void *dYPlane, void *dUvPlane);
 
+/* ---- spatial bands (no reference counterpart: the reference drives one device,
+ * HR/opticalFlowCalc.c:279-305). N contexts, one per GPU, created for the FULL frame geometry; context
+ * `rank` owns the rows [row0[rank], row1[rank]) of every frame: it uploads, warps and downloads only those
+ * rows, and pulls the other bands from its peers' frame slots over NVLink P2P, so that every GPU holds
+ * the whole frame pair for the flow search (replicated, bit-identical on every GPU). Bands must tile
+ * the frame in order; all but the last end on a multiple of 2^(resScalar+1) rows.
+ * Call order per source frame, on every rank: hr_band_upload ... then hr_band_gather (a driver of
+ * several ranks in one process calls upload on all of them before the first gather); then
+ * hr_calc_flow / hr_warp (warps the band only) / hr_band_download as usual. */
+#define HR_MAX_BANDS 16
+#define HR_IPC_HANDLE_BYTES 64
+int hr_band_configure(HrContext *ctx, int rank, int world, const int *row0, const int *row1);
+/* what a peer must map: frame slot 0, frame slot 1, mailbox — as pointers (same process) ... */
+int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **mailbox);
+/* ... or as three CUDA IPC handles (another process) */
+int hr_band_export_ipc(HrContext *ctx, unsigned char *handles /* 3 * HR_IPC_HANDLE_BYTES */);
+int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **mailbox);
+/* peerDevice >= 0: same-process peer on that device (peer access is enabled); < 0: pointers from IPC */
+int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *mailbox);
+/* updateFrame, banded, in two phases (see above). yBand / uvBand: first luma / chroma row of the band. */
+int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvBand, int sourceIsDevice);
+int hr_band_gather(HrContext *ctx, int blocking);
+/* downloadFrame of the band's rows only */
+int hr_band_download(HrContext *ctx, void *yBand, void *uvBand, double *seconds);
+
 /* ---- parity taps (tests only; nothing on the playback path calls them). Blocking.
  * raw / blurred: int16 [2][lowHeight][lowWidth], X plane then Y plane = offsetArray /
  * blurredOffsetArray (HR/opticalFlowCalc.c:397-398). Either pointer may be NULL. */

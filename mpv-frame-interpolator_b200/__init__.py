@@ -56,6 +56,14 @@ ABI = {
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_band_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hr_band_local_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "hr_band_export_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hr_band_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "hr_band_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hr_band_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hr_band_gather": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_band_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hr_get_offsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_set_blurred_offsets": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hr_blur_flow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -238,6 +246,118 @@ class HrCuda:
 
     def launch_count(self):
         return int(self.lib.hr_get_launch_count(self.h))
+
+
+    # ---- spatial bands (include/hopperrender_cuda.h, "spatial bands") ----
+    def band_configure(self, rank, world, rows):
+        r0 = (C.c_int * world)(*[a for a, _ in rows])
+        r1 = (C.c_int * world)(*[b for _, b in rows])
+        self._chk(self.lib.hr_band_configure(self.h, rank, world, r0, r1))
+        self.band = (rank, world, list(rows))
+
+    def band_local_pointers(self):
+        a, b, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.lib.hr_band_local_pointers(self.h, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, m.value
+
+    def band_export_ipc(self):
+        buf = C.create_string_buffer(3 * 64)
+        self._chk(self.lib.hr_band_export_ipc(self.h, buf))
+        return bytes(buf.raw)
+
+    def band_open_ipc(self, handles):
+        a, b, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        buf = C.create_string_buffer(handles, 3 * 64)
+        self._chk(self.lib.hr_band_open_ipc(self.h, buf, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, m.value
+
+    def band_connect(self, peer_rank, ptrs, peer_device=-1):
+        self._chk(self.lib.hr_band_connect(self.h, peer_rank, peer_device, C.c_void_p(ptrs[0]), C.c_void_p(ptrs[1]), C.c_void_p(ptrs[2])))
+
+    def band_upload(self, y_band, uv_band, device=False):
+        self._chk(self.lib.hr_band_upload(self.h, _ptr(y_band), _ptr(uv_band), 1 if device else 0))
+
+    def band_gather(self, blocking=True):
+        self._chk(self.lib.hr_band_gather(self.h, 1 if blocking else 0))
+
+    def band_download(self, y_band, uv_band):
+        sec = C.c_double(0.0)
+        self._chk(self.lib.hr_band_download(self.h, _ptr(y_band), _ptr(uv_band), C.byref(sec)))
+        return sec.value
+
+
+class BandGroup:
+    """One frame stream split into spatial bands over several contexts IN ONE PROCESS (one per entry of
+    `devices`; the same device may appear more than once, e.g. to exercise the protocol on one GPU).
+    Presents the six calls of the optical-flow-calc interface for whole frames: updateFrame uploads every
+    band to its own GPU and gathers the rest by P2P, the flow runs replicated, warp + download work band
+    by band and write straight into the caller's full-size planes. SURVEY.md §8e."""
+
+    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=PIXFMT_NV12, devices=(0, 1)):
+        from . import sharding
+        self.H, self.W = frameHeight, frameWidth
+        self.world = len(devices)
+        self.ctx = [HrCuda(frameHeight, frameWidth, actualWidth, pixfmt, d) for d in devices]
+        self.rows = sharding.band_rows(frameHeight, self.world, self.ctx[0].info.resScalar)
+        for r, c in enumerate(self.ctx):
+            c.band_configure(r, self.world, self.rows)
+        ptrs = [c.band_local_pointers() for c in self.ctx]
+        for r, c in enumerate(self.ctx):
+            for p in range(self.world):
+                if p != r:
+                    c.band_connect(p, ptrs[p], devices[p])
+        self.devices = list(devices)
+        self.dtype = self.ctx[0].dtype
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def _band_views(self, y, uv, r):
+        r0, r1 = self.rows[r]
+        return y[r0:r1], uv[r0 >> 1:r1 >> 1]
+
+    def update_frame(self, y, uv, blocking=True):
+        for r, c in enumerate(self.ctx):          # phase 1 on every rank first
+            c.band_upload(*self._band_views(y, uv, r))
+        for c in self.ctx:                        # then phase 2
+            c.band_gather(blocking=False)
+        if blocking:
+            for c in self.ctx:
+                c.synchronize()
+
+    def calc_flow(self, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6):
+        for c in self.ctx:
+            c.calc_flow(radius, deltaScalar, neighborBiasScalar, blocking=False)
+        for c in self.ctx:
+            c.synchronize()
+
+    def warp(self, t, mode=BlendedFrame, black=0.0, white=255.0):
+        for c in self.ctx:
+            c.warp(t, mode, black, white)
+
+    def download(self, y=None, uv=None):
+        if y is None:
+            y = np.empty((self.H, self.W), self.dtype)
+        if uv is None:
+            uv = np.empty((self.H // 2, self.W), self.dtype)
+        for r, c in enumerate(self.ctx):
+            c.band_download(*self._band_views(y, uv, r))
+        return y, uv
+
+
+def connect_bands_distributed(ctx, dist, rows):
+    """One process per GPU (torchrun): configure `ctx` as band `rank` and map every peer's frame slots and
+    mailbox through CUDA IPC handles exchanged once, at set-up, over the process group (control plane
+    only; the frames themselves move by P2P copies)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ctx.band_configure(rank, world, rows)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.band_export_ipc())
+    for p in range(world):
+        if p != rank:
+            ctx.band_connect(p, ctx.band_open_ipc(handles[p]), -1)
+    dist.barrier()
 
 
 class OpticalFlowCalc:

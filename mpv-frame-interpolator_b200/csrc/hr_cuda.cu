@@ -50,6 +50,15 @@ struct HrContext {
     int timelineOn;
     int useFastWarp;
 
+    /* spatial bands: this context owns rows [bandRow0[bandRank], bandRow1[bandRank]) */
+    int bandWorld, bandRank;
+    int bandRow0[HR_MAX_BANDS], bandRow1[HR_MAX_BANDS];
+    unsigned char *peerSlot[HR_MAX_BANDS][2];       /* the peers' two frame slots, mapped into this process   */
+    unsigned long long *peerMail[HR_MAX_BANDS];     /* the peers' mailboxes: [0] uploaded, [1] consumed        */
+    unsigned long long *mail;                       /* own mailbox (device memory)                             */
+    unsigned long long bandFrames;                  /* frames uploaded so far                                  */
+    int bandPending;                                /* hr_band_upload done, hr_band_gather outstanding        */
+
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
     int profiling;
@@ -119,6 +128,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->T);
     cudaFree(ctx->partial);
     cudaFree(ctx->trace);
+    cudaFree(ctx->mail);
     cudaFree(ctx->timeline);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
     if (ctx->evFlowEnd) cudaEventDestroy(ctx->evFlowEnd);
@@ -542,8 +552,15 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     /* thread = 4 samples x ROWS rows (8 when the lattice cell is at least 8 rows tall, else 4); row groups of
      * the luma plane, then of the chroma plane */
     const int ROWS = ctx->s >= 3 ? 8 : 4;
-    const int lumaGroups = (ctx->H + ROWS - 1) / ROWS;
-    const int groups = lumaGroups + ((ctx->H >> 1) + ROWS - 1) / ROWS;
+    int r0 = 0, r1 = ctx->H;
+    if (ctx->bandWorld > 1) {
+        r0 = ctx->bandRow0[ctx->bandRank];
+        r1 = ctx->bandRow1[ctx->bandRank];
+    }
+    /* band boundaries are multiples of 2^(s+1) rows, so luma and chroma row groups do not straddle them */
+    const int lumaG0 = r0 / ROWS, lumaGroups = (r1 + ROWS - 1) / ROWS - lumaG0;
+    const int chromaG0 = (r0 >> 1) / ROWS, chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - chromaG0;
+    const int groups = lumaGroups + chromaGN;
     dim3 block(32, 8);
     dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
     /* the block path: 4x4 blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in
@@ -553,8 +570,8 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
                (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], ctx->stream));
-    if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups);
-    else warp_blend_kernel<T, 4><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups);
+    if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups, lumaG0, chromaG0, chromaGN);
+    else warp_blend_kernel<T, 4><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups, lumaG0, chromaG0, chromaGN);
     CU(cudaGetLastError());
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[3], ctx->stream));
@@ -589,6 +606,208 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
             cudaGetLastError(); /* no warp was recorded yet */
+            ms = 0.f;
+        }
+        *seconds = (double)ms * 1e-3;
+    }
+    return 0;
+}
+
+
+/* ---------------------------------------------------------------------------------------------------
+ * Spatial bands: N contexts, one per GPU, each owning a band of rows of every frame.
+ * A band owner uploads, warps and downloads only its rows; the rows of the other bands are pulled from
+ * the peers' frame slots over NVLink P2P (peer-mapped pointers, in-process or through CUDA IPC), so
+ * that every GPU holds the whole frame pair for the (replicated, bit-identical) flow search.
+ * Hand-off between GPUs: every context has a two-counter mailbox in device memory — frames whose band
+ * is uploaded, frames whose gather is complete — written by a one-thread kernel on the owner's stream
+ * (st.release.sys) and polled by a one-thread kernel on the reader's stream (ld.acquire.sys). No NCCL,
+ * no host synchronisation on the data path.
+ * ------------------------------------------------------------------------------------------------- */
+__global__ void band_signal_kernel(unsigned long long *p, unsigned long long v) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__global__ void band_wait_kernel(const unsigned long long *p, unsigned long long target) {
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v < target) __nanosleep(200);
+    } while (v < target);
+}
+
+extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int *row0, const int *row1) {
+    if (!ctx || !row0 || !row1) return 1;
+    if (world < 1 || world > HR_MAX_BANDS || rank < 0 || rank >= world) return fail(ctx, "hr_band_configure: rank %d / world %d out of range (max %d bands)", rank, world, HR_MAX_BANDS);
+    if (bind_device(ctx)) return 1;
+    const int unit = 1 << (ctx->s + 1);
+    int expect = 0;
+    for (int r = 0; r < world; ++r) {
+        if (row0[r] != expect || row1[r] <= row0[r] || (r + 1 < world && row1[r] % unit != 0))
+            return fail(ctx, "hr_band_configure: band %d = [%d, %d) must continue the previous band and end on a multiple of %d rows", r, row0[r], row1[r], unit);
+        expect = row1[r];
+        ctx->bandRow0[r] = row0[r];
+        ctx->bandRow1[r] = row1[r];
+    }
+    if (expect != ctx->H) return fail(ctx, "hr_band_configure: the bands cover %d rows, the frame has %d", expect, ctx->H);
+    if (!ctx->mail) {
+        CU(cudaMalloc(&ctx->mail, 256));
+        CU(cudaMemset(ctx->mail, 0, 256));
+    }
+    ctx->bandWorld = world;
+    ctx->bandRank = rank;
+    ctx->bandFrames = 0;
+    ctx->bandPending = 0;
+    for (int r = 0; r < HR_MAX_BANDS; ++r) {
+        ctx->peerSlot[r][0] = ctx->peerSlot[r][1] = NULL;
+        ctx->peerMail[r] = NULL;
+    }
+    ctx->peerSlot[rank][0] = ctx->frameBuf[0];
+    ctx->peerSlot[rank][1] = ctx->frameBuf[1];
+    ctx->peerMail[rank] = ctx->mail;
+    return 0;
+}
+
+/* The three device allocations a peer needs to see: frame slot 0, frame slot 1, mailbox. */
+extern "C" int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **mailbox) {
+    if (!ctx || !ctx->mail) return 1;
+    if (slot0) *slot0 = ctx->frameBuf[0];
+    if (slot1) *slot1 = ctx->frameBuf[1];
+    if (mailbox) *mailbox = ctx->mail;
+    return 0;
+}
+extern "C" int hr_band_export_ipc(HrContext *ctx, unsigned char *handles /* 3 x HR_IPC_HANDLE_BYTES */) {
+    if (!ctx || !handles) return 1;
+    if (!ctx->mail) return fail(ctx, "hr_band_export_ipc: configure the bands first");
+    if (bind_device(ctx)) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == HR_IPC_HANDLE_BYTES, "IPC handle size");
+    void *ptrs[3] = {ctx->frameBuf[0], ctx->frameBuf[1], ctx->mail};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(handles + i * HR_IPC_HANDLE_BYTES, &h, HR_IPC_HANDLE_BYTES);
+    }
+    return 0;
+}
+extern "C" int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **mailbox) {
+    if (!ctx || !handles || !slot0 || !slot1 || !mailbox) return 1;
+    if (bind_device(ctx)) return 1;
+    void **outs[3] = {slot0, slot1, mailbox};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + i * HR_IPC_HANDLE_BYTES, HR_IPC_HANDLE_BYTES);
+        CU(cudaIpcOpenMemHandle(outs[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return 0;
+}
+/* pointers must be valid in this process and on this device (same process: enable peer access first —
+ * done here when peerDevice >= 0; another process: hr_band_open_ipc) */
+extern "C" int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *mailbox) {
+    if (!ctx) return 1;
+    if (peerRank < 0 || peerRank >= ctx->bandWorld || peerRank == ctx->bandRank) return fail(ctx, "hr_band_connect: bad peer rank %d", peerRank);
+    if (!slot0 || !slot1 || !mailbox) return fail(ctx, "hr_band_connect: NULL pointer");
+    if (bind_device(ctx)) return 1;
+    if (peerDevice >= 0 && peerDevice != ctx->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ctx->device, peerDevice));
+        if (!can) return fail(ctx, "hr_band_connect: device %d cannot access device %d", ctx->device, peerDevice);
+        cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    ctx->peerSlot[peerRank][0] = (unsigned char *)slot0;
+    ctx->peerSlot[peerRank][1] = (unsigned char *)slot1;
+    ctx->peerMail[peerRank] = (unsigned long long *)mailbox;
+    return 0;
+}
+
+/* Phase 1 of a banded updateFrame: upload (or copy from device memory) the rows of this context's band
+ * of the new frame and tell the peers. yBand / uvBand point at the band's first luma row / first chroma
+ * row. Enqueue-only for device sources; host sources are copied asynchronously (pinned memory advised). */
+extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvBand, int sourceIsDevice) {
+    if (!ctx) return 1;
+    if (ctx->bandWorld < 1 || !ctx->mail) return fail(ctx, "hr_band_upload: bands are not configured");
+    if (ctx->bandPending) return fail(ctx, "hr_band_upload: the previous frame was not gathered (hr_band_gather)");
+    if (!yBand || !uvBand) return fail(ctx, "hr_band_upload: NULL plane");
+    for (int r = 0; r < ctx->bandWorld; ++r)
+        if (!ctx->peerMail[r]) return fail(ctx, "hr_band_upload: peer %d is not connected", r);
+    if (bind_device(ctx)) return 1;
+    CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
+    int slot;
+    rotate_slots(ctx, &slot);
+    const unsigned long long n = ctx->bandFrames; /* this is frame n; frame n-2 lived in the same slot */
+    if (n >= 2) {
+        for (int r = 0; r < ctx->bandWorld; ++r) {
+            if (r == ctx->bandRank) continue;
+            band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 1, n - 1); /* peer r has gathered frame n-2 */
+            ctx->launches++;
+        }
+    }
+    unsigned char *dst = ctx->frameBuf[slot];
+    const size_t rowBytes = (size_t)ctx->W * ctx->bps, ylen = (size_t)ctx->H * rowBytes;
+    const int r0 = ctx->bandRow0[ctx->bandRank], r1 = ctx->bandRow1[ctx->bandRank];
+    const cudaMemcpyKind kind = sourceIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(dst + (size_t)r0 * rowBytes, yBand, (size_t)(r1 - r0) * rowBytes, kind, ctx->stream));
+    CU(cudaMemcpyAsync(dst + ylen + (size_t)(r0 >> 1) * rowBytes, uvBand, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes, kind, ctx->stream));
+    band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 0, n + 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->fy[1] = dst;
+    ctx->fuv[1] = dst + ylen;
+    ctx->fslot[1] = slot;
+    ctx->bandPending = 1;
+    return 0;
+}
+
+/* Phase 2: pull the other bands of the new frame from the peers (P2P copies, each after the peer's upload
+ * has been signalled), tell the peers, pack the frame for the search. blocking != 0: waits for the stream
+ * like updateFrame does. */
+extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
+    if (!ctx) return 1;
+    if (!ctx->bandPending) return fail(ctx, "hr_band_gather: no upload outstanding");
+    if (bind_device(ctx)) return 1;
+    const int slot = ctx->fslot[1];
+    const unsigned long long n = ctx->bandFrames;
+    unsigned char *dst = ctx->frameBuf[slot];
+    const size_t rowBytes = (size_t)ctx->W * ctx->bps, ylen = (size_t)ctx->H * rowBytes;
+    for (int k = 1; k < ctx->bandWorld; ++k) {
+        const int r = (ctx->bandRank + k) % ctx->bandWorld; /* staggered, so that not everybody reads rank 0 first */
+        band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 0, n + 1);
+        ctx->launches++;
+        const unsigned char *src = ctx->peerSlot[r][slot];
+        const int r0 = ctx->bandRow0[r], r1 = ctx->bandRow1[r];
+        CU(cudaMemcpyAsync(dst + (size_t)r0 * rowBytes, src + (size_t)r0 * rowBytes, (size_t)(r1 - r0) * rowBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dst + ylen + (size_t)(r0 >> 1) * rowBytes, src + ylen + (size_t)(r0 >> 1) * rowBytes, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 1, n + 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (launch_pack(ctx)) return 1;
+    ctx->framesSeen++;
+    ctx->bandFrames = n + 1;
+    ctx->bandPending = 0;
+    if (blocking) CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* downloadFrame for a band: only this context's rows, to host pointers of the band's first rows */
+extern "C" int hr_band_download(HrContext *ctx, void *yBand, void *uvBand, double *seconds) {
+    if (!ctx) return 1;
+    if (ctx->bandWorld < 1) return fail(ctx, "hr_band_download: bands are not configured");
+    if (!yBand || !uvBand) return fail(ctx, "hr_band_download: NULL plane");
+    if (bind_device(ctx)) return 1;
+    const size_t rowBytes = (size_t)ctx->W * ctx->bps;
+    const int r0 = ctx->bandRow0[ctx->bandRank], r1 = ctx->bandRow1[ctx->bandRank];
+    CU(cudaMemcpyAsync(yBand, (const unsigned char *)ctx->outY + (size_t)r0 * rowBytes, (size_t)(r1 - r0) * rowBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(uvBand, (const unsigned char *)ctx->outUV + (size_t)(r0 >> 1) * rowBytes, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evDlEnd));
+    if (seconds) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
+            cudaGetLastError();
             ms = 0.f;
         }
         *seconds = (double)ms * 1e-3;

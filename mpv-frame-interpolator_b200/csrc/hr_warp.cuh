@@ -452,13 +452,17 @@ __device__ __forceinline__ void load_rows_interior(const uint16_t *plane, int o,
 /* ROWS = rows per thread (4, or 8 when the lattice cell is at least 8 rows tall): thread = 4 samples x
  * ROWS rows. lumaGroups = ceil(H / ROWS): row groups of the luma plane come first, then the chroma plane's. */
 template <typename T, int ROWS>
-__global__ void __launch_bounds__(256, ROWS == 4 ? 6 : 4) warp_blend_kernel(const WarpParams<T> P, int useFast, int lumaGroups) {
+__global__ void __launch_bounds__(256, ROWS == 4 ? 6 : 4) warp_blend_kernel(const WarpParams<T> P, int useFast, int lumaGroups, int lumaG0, int chromaG0,
+                                                                            int chromaGN) {
+    /* the launch covers lumaGroups row groups of the luma plane starting at group lumaG0, then chromaGN groups
+     * of the chroma plane starting at chromaG0 (whole frame: 0, all, 0, all; a spatial band: its rows only) */
     constexpr bool is16 = SampleTraits<T>::is16;
     typedef typename RunType<T>::type Run;
     const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int rg = blockIdx.y * blockDim.y + threadIdx.y;
     const int cz = rg >= lumaGroups;
-    const int cy0 = (cz ? rg - lumaGroups : rg) * ROWS;
+    if (cz && rg - lumaGroups >= chromaGN) return;
+    const int cy0 = (cz ? chromaG0 + rg - lumaGroups : lumaG0 + rg) * ROWS;
     const int planeH = cz ? (P.H >> 1) : P.H;
     if (cx0 >= P.aW || cy0 >= planeH) return;
     const T *s12 = cz ? P.f1uv : P.f1y;
