@@ -10,7 +10,9 @@
 #define MAX_SEARCH_RADIUS 16
 
 /* Performance */
+#ifndef AUTO_SEARCH_RADIUS_ADJUST   /* -DAUTO_SEARCH_RADIUS_ADJUST=0 pins the radius (reproducible runs) */
 #define AUTO_SEARCH_RADIUS_ADJUST 1
+#endif
 #define UPPER_PERF_BUFFER 1.4
 #define LOWER_PERF_BUFFER 1.6
 

@@ -74,6 +74,24 @@ def main():
                     % (",".join('"%s"' % k for k in KERNELS), len(KERNELS)))
         subprocess.run([CC, "-O1", "-fPIC", "-shared", "-o", str(OUT / "libhr_ref_kernels.so"), str(c)], check=True)
     print("build_ref: built", OUT / "libhr_ref_ofc.so", "and", OUT / "libhr_ref_kernels.so")
+    # 3. the reference FILTER (vf_HopperRender.c, unmodified) on top of this repository's optical-flow-calc
+    #    layer and CUDA library: oracle/filter_host_sim.c supplies the slice of mpv's filter runtime it needs
+    #    (oracle/mpv_shim). The radius auto-adjust is compiled out so that runs are reproducible.
+    root = HERE.parent
+    pkg_hr = root / "mpv-frame-interpolator_b200" / "mpv" / "video" / "filter" / "HopperRender"
+    csrc = root / "mpv-frame-interpolator_b200" / "csrc"
+    if (csrc / "libhopperrender_cuda.so").exists():
+        # -include: this repository's opticalFlowCalc.h comes first and owns the include guard, so the
+        # reference's OpenCL flavour of that header (same directory as the filter source) stays empty
+        cmd = [CC, "-O2", "-std=gnu11", "-w", "-fPIC", "-shared", "-include", str(pkg_hr / "opticalFlowCalc.h"),
+               "-I", str(pkg_hr), "-I", str(HERE / "mpv_shim"), "-I", str(root / "include"),
+               "-o", str(OUT / "libhr_filter_sim.so"),
+               str(REF / "vf_HopperRender.c"), str(HERE / "filter_host_sim.c"), str(pkg_hr / "opticalFlowCalc.c"),
+               "-L", str(csrc), "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../mpv-frame-interpolator_b200/csrc", "-lm", "-lpthread"]
+        subprocess.run(cmd, check=True)
+        print("build_ref: built", OUT / "libhr_filter_sim.so", "(reference filter + this repo's OFC layer)")
+    else:
+        print("build_ref: libhopperrender_cuda.so not built yet — filter host sim skipped")
     return 0
 
 

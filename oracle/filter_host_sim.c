@@ -1,0 +1,216 @@
+/*
+ * filter_host_sim.c — drives the REFERENCE FILTER (video/filter/HopperRender/vf_HopperRender.c, compiled
+ * unmodified from /root/reference by oracle/build_ref.py) on top of THIS repository's optical-flow-calc
+ * layer (mpv-frame-interpolator_b200/mpv/video/filter/HopperRender/opticalFlowCalc.c -> the CUDA C ABI),
+ * outside an mpv build. It implements the slice of mpv's filter runtime declared in
+ * mpv_shim/hr_mpv_shim.h and a small push/run/pop API for the tests (tests/test_gpu_filter_host.py):
+ * that is the drop-in claim made executable — the reference's own filter code, its six calls into
+ * opticalFlowCalc.h, our library underneath. Test infrastructure only (oracle/).
+ */
+#include "mpv_shim/hr_mpv_shim.h"
+
+extern const struct mp_user_filter_entry vf_HopperRender; /* vf_HopperRender.c:719-720 */
+
+/* ---- talloc / images -------------------------------------------------------------------------- */
+void talloc_free(void *p) { free(p); }
+
+static struct mp_image *image_alloc(int w, int h) {
+    struct mp_image *img = calloc(1, sizeof(*img));
+    const int stride = (w + 63) & ~63; /* mpv aligns strides to 64 bytes (video/mp_image.h:35) */
+    img->w = w;
+    img->h = h;
+    img->imgfmt = IMGFMT_NV12;
+    img->storage = malloc((size_t)stride * h * 3 / 2 + 64);
+    img->planes[0] = img->storage;
+    img->planes[1] = img->storage + (size_t)stride * h;
+    img->stride[0] = img->stride[1] = stride;
+    img->refcount = malloc(sizeof(int));
+    *img->refcount = 1;
+    return img;
+}
+struct mp_image *mp_image_new_ref(struct mp_image *img) {
+    struct mp_image *r = malloc(sizeof(*r));
+    *r = *img;
+    ++*img->refcount;
+    return r;
+}
+void mp_image_unrefp(struct mp_image **p) {
+    struct mp_image *img = p ? *p : NULL;
+    if (!img) return;
+    if (--*img->refcount == 0) {
+        free(img->storage);
+        free(img->refcount);
+    }
+    free(img);
+    *p = NULL;
+}
+void mp_image_copy_attributes(struct mp_image *dst, struct mp_image *src) {
+    dst->pts = src->pts;
+    dst->nominal_fps = src->nominal_fps;
+}
+struct mp_image_pool {
+    int unused;
+};
+struct mp_image_pool *mp_image_pool_new(void *tparent) {
+    (void)tparent;
+    return calloc(1, sizeof(struct mp_image_pool));
+}
+struct mp_image *mp_image_pool_get(struct mp_image_pool *pool, int fmt, int w, int h) {
+    (void)pool;
+    (void)fmt;
+    return image_alloc(w, h);
+}
+void mp_image_pool_clear(struct mp_image_pool *pool) { (void)pool; }
+
+bool mp_frame_is_signaling(struct mp_frame frame) { return frame.type == MP_FRAME_EOF; }
+
+/* ---- pins: one slot each -------------------------------------------------------------------------- */
+struct mp_pin {
+    struct mp_frame slot;
+    bool has;
+    int role; /* 0 filter input, 1 filter output, 2 autoconvert input, 3 autoconvert output */
+    struct mp_filter_sim *sim;
+};
+#define SIM_MAX_OUT 64
+struct mp_filter_sim {
+    struct mp_filter *f;
+    struct mp_pin in, out, conv_in, conv_out;
+    struct mp_pin *fpins[2], *cpins[2];
+    struct mp_filter conv_filter;
+    struct mp_autoconvert conv;
+    struct mp_stream_info info;
+    struct mp_image *outputs[SIM_MAX_OUT];
+    int n_out;
+    bool progress, failed;
+    void *opts;
+};
+static struct mp_filter_sim *g_sim; /* the instance under construction (mp_filter_create has no user pointer) */
+
+struct mp_filter *mp_filter_create(struct mp_filter *parent, const struct mp_filter_info *info) {
+    (void)parent;
+    struct mp_filter *f = calloc(1, sizeof(*f));
+    f->info = info;
+    f->priv = calloc(1, info->priv_size);
+    f->sim = g_sim;
+    g_sim->f = f;
+    g_sim->fpins[0] = &g_sim->in;
+    g_sim->fpins[1] = &g_sim->out;
+    f->pins = f->ppins = g_sim->fpins;
+    g_sim->in.role = 0;
+    g_sim->out.role = 1;
+    g_sim->conv_in.role = 2;
+    g_sim->conv_out.role = 3;
+    g_sim->in.sim = g_sim->out.sim = g_sim->conv_in.sim = g_sim->conv_out.sim = g_sim;
+    return f;
+}
+struct mp_pin *mp_filter_add_pin(struct mp_filter *f, enum mp_pin_dir dir, const char *name) {
+    (void)name;
+    f->num_pins++;
+    return dir == MP_PIN_IN ? &f->sim->in : &f->sim->out;
+}
+void mp_filter_internal_mark_progress(struct mp_filter *f) { f->sim->progress = true; }
+void mp_filter_internal_mark_failed(struct mp_filter *f) { f->sim->failed = true; }
+
+bool mp_pin_in_needs_data(struct mp_pin *p) {
+    if (p->role == 1) return p->sim->n_out < SIM_MAX_OUT; /* the harness drains the output list */
+    if (p->role == 2) return !p->sim->conv_out.has;       /* pass-through autoconvert */
+    return !p->has;
+}
+bool mp_pin_can_transfer_data(struct mp_pin *dst, struct mp_pin *src) { return src->has && mp_pin_in_needs_data(dst); }
+struct mp_frame mp_pin_out_read(struct mp_pin *p) {
+    struct mp_frame fr = p->has ? p->slot : (struct mp_frame){MP_FRAME_NONE, NULL};
+    p->has = false;
+    return fr;
+}
+bool mp_pin_in_write(struct mp_pin *p, struct mp_frame frame) {
+    if (frame.type == MP_FRAME_NONE) return true;
+    struct mp_filter_sim *s = p->sim;
+    if (p->role == 1) {
+        if (frame.type == MP_FRAME_VIDEO && s->n_out < SIM_MAX_OUT) s->outputs[s->n_out++] = frame.data;
+        return true;
+    }
+    if (p->role == 2) { /* autoconvert: the harness only feeds NV12, so conversion is the identity */
+        s->conv_out.slot = frame;
+        s->conv_out.has = true;
+        s->progress = true;
+        return true;
+    }
+    p->slot = frame;
+    p->has = true;
+    return true;
+}
+
+static double sim_display_fps(struct mp_stream_info *i) { return i->display_fps; }
+struct mp_stream_info *mp_filter_find_stream_info(struct mp_filter *f) { return &f->sim->info; }
+struct mp_autoconvert *mp_autoconvert_create(struct mp_filter *parent) {
+    struct mp_filter_sim *s = parent->sim;
+    s->cpins[0] = &s->conv_in;
+    s->cpins[1] = &s->conv_out;
+    s->conv_filter.pins = s->conv_filter.ppins = s->cpins;
+    s->conv_filter.sim = s;
+    s->conv.f = &s->conv_filter;
+    return &s->conv;
+}
+void mp_autoconvert_add_imgfmt(struct mp_autoconvert *c, int imgfmt, int subfmt) {
+    (void)c;
+    (void)imgfmt;
+    (void)subfmt;
+}
+
+/* ---- harness API ------------------------------------------------------------------------------------ */
+struct mp_filter_sim *hr_sim_create(int frameOutput, double displayFps) {
+    struct mp_filter_sim *s = calloc(1, sizeof(*s));
+    s->info.get_display_fps = sim_display_fps;
+    s->info.display_fps = displayFps; /* what --vo=null --vo-null-fps reports, f_output_chain.c:357-364 */
+    /* options block as filters/user_filters.c:174-190 would fill it from vf_opts_fields */
+    const m_option_t *o = vf_HopperRender.desc.options;
+    s->opts = calloc(1, 64);
+    *(int *)((char *)s->opts + o[0].offset) = frameOutput < o[0].min || frameOutput > o[0].max ? o[0].defval : frameOutput;
+    g_sim = s;
+    struct mp_filter *f = vf_HopperRender.create(NULL, s->opts);
+    g_sim = NULL;
+    if (!f) {
+        free(s);
+        return NULL;
+    }
+    return s;
+}
+const char *hr_sim_filter_name(void) { return vf_HopperRender.desc.name; }
+
+/* feed one NV12 source frame (tightly packed planes of w x h) and run the filter until it stalls;
+ * returns the number of output frames waiting, or -1 if the filter marked itself failed */
+int hr_sim_push(struct mp_filter_sim *s, const unsigned char *y, const unsigned char *uv, int w, int h, double pts, double nominalFps) {
+    struct mp_image *img = image_alloc(w, h);
+    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * w, w);
+    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * w, w);
+    img->pts = pts;
+    img->nominal_fps = nominalFps;
+    s->in.slot = MAKE_FRAME(MP_FRAME_VIDEO, img);
+    s->in.has = true;
+    do { /* filters/filter.c:211-263: run process() while somebody reports progress */
+        s->progress = false;
+        s->f->info->process(s->f);
+    } while (s->progress && !s->failed);
+    return s->failed ? -1 : s->n_out;
+}
+/* oldest waiting output frame -> tightly packed planes; returns 0, or 1 when none is waiting */
+int hr_sim_pop(struct mp_filter_sim *s, unsigned char *y, unsigned char *uv, double *pts, int *stride) {
+    if (s->n_out == 0) return 1;
+    struct mp_image *img = s->outputs[0];
+    memmove(s->outputs, s->outputs + 1, sizeof(s->outputs[0]) * (size_t)(--s->n_out));
+    for (int r = 0; r < img->h; ++r) memcpy(y + (size_t)r * img->w, img->planes[0] + (size_t)r * img->stride[0], img->w);
+    for (int r = 0; r < img->h / 2; ++r) memcpy(uv + (size_t)r * img->w, img->planes[1] + (size_t)r * img->stride[1], img->w);
+    if (pts) *pts = img->pts;
+    if (stride) *stride = img->stride[0];
+    mp_image_unrefp(&img);
+    return 0;
+}
+void hr_sim_command_speed(struct mp_filter_sim *s, double speed) {
+    struct mp_filter_command c = {MP_FILTER_COMMAND_TEXT, speed};
+    s->f->info->command(s->f, &c);
+}
+void hr_sim_reset(struct mp_filter_sim *s) { s->f->info->reset(s->f); }
+void hr_sim_destroy(struct mp_filter_sim *s) {
+    s->f->info->destroy(s->f);
+    free(s);
+}
