@@ -77,6 +77,24 @@ const char *hr_last_error(const HrContext *ctx); /* ctx may be NULL: error of th
 int hr_set_stream(HrContext *ctx, void *cudaStream);
 int hr_synchronize(HrContext *ctx);
 
+/* Pipelined mode (no reference counterpart: the reference has one in-order queue and blocks
+ * once per source frame and once per output frame, HR/opticalFlowCalc.c:98-100,112-114). When enabled, the
+ * enqueue-only calls (hr_update_frame_device with borrow = 1, hr_calc_flow with seconds = NULL, hr_warp into
+ * planes set by hr_set_output_device, hr_step_device) place independent work of consecutive frame pairs on
+ * internal streams: the packed copy of frame k is built while the search of pair k runs, the warps of one pair
+ * run side by side, the search of pair k+1 runs beside the warps of pair k (two flow buffers). Results are
+ * bit-identical to the serial mode. Outputs in caller-owned planes are complete after hr_synchronize, or — for
+ * work that the caller enqueues on the context's stream — after hr_pipeline_join. Calls that block or touch
+ * host memory (hr_update_frame, hr_download, the taps) behave as before. Ignored while bands are configured. */
+int hr_set_pipeline(HrContext *ctx, int enable);
+int hr_pipeline_join(HrContext *ctx);
+/* One source frame of a device-resident stream in one call (offline / batch interpolation):
+ * hr_update_frame_device + hr_calc_flow + nWarps x hr_warp, warp i with blendingScalars[i] into the caller-owned
+ * planes outY[i], outUV[i]. The first frame of a stream only primes the pair. Enqueue-only. */
+int hr_step_device(HrContext *ctx, const void *dYPlane, const void *dUvPlane, int borrow, int searchRadius, int deltaScalar,
+                   int neighborBiasScalar, int nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel,
+                   float whiteLevel, void *const *outY, void *const *outUV);
+
 /* ---- updateFrame, HR/opticalFlowCalc.c:96-107: blocking upload of the Y plane
  * (frameHeight*stride samples) and the interleaved UV plane (frameHeight/2*stride samples) from
  * HOST memory into the older frame slot, then swap, so that slot 1 is the newest frame. Also

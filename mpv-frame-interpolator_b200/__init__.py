@@ -51,6 +51,10 @@ ABI = {
     "hr_synchronize": (C.c_int, [C.c_void_p]),
     "hr_update_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_update_frame_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hr_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_pipeline_join": (C.c_int, [C.c_void_p]),
+    "hr_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                 C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_calc_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "hr_warp": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]),
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
@@ -175,6 +179,22 @@ class HrCuda:
 
     def update_frame_device(self, dy, duv, borrow=False):
         self._chk(self.lib.hr_update_frame_device(self.h, _ptr(dy), _ptr(duv), 1 if borrow else 0))
+
+    def set_pipeline(self, on=True):
+        self._chk(self.lib.hr_set_pipeline(self.h, 1 if on else 0))
+
+    def pipeline_join(self):
+        self._chk(self.lib.hr_pipeline_join(self.h))
+
+    def step_device(self, dy, duv, ts, outs, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6, mode=BlendedFrame,
+                    black=0.0, white=255.0, borrow=True):
+        """One source frame of a device-resident stream: update + flow + len(ts) warps into outs[i] = (dY, dUV)."""
+        n = len(ts)
+        tarr = (C.c_float * max(n, 1))(*[float(t) for t in ts])
+        oy = (C.c_void_p * max(n, 1))(*[_ptr(o[0]) for o in outs[:n]])
+        ouv = (C.c_void_p * max(n, 1))(*[_ptr(o[1]) for o in outs[:n]])
+        self._chk(self.lib.hr_step_device(self.h, _ptr(dy), _ptr(duv), 1 if borrow else 0, radius, deltaScalar, neighborBiasScalar, n, tarr,
+                                          int(mode), float(black), float(white), oy, ouv))
 
     def calc_flow(self, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6, blocking=True):
         sec = C.c_double(0.0)

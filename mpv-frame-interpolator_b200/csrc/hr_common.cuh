@@ -34,7 +34,9 @@
 
 struct FlowParams {
     const uint32_t *p1;      /* packed previous frame (frame1): all phase planes                 */
-    const uint32_t *p2;      /* packed newest frame (frame2): only phase plane (0,0) is read      */
+    const void *f2y, *f2uv;  /* newest frame (frame2) as it arrived, NV12 / P010: read at the lattice points only, so
+                              * that its packed copy (needed as frame1 of the NEXT pair) can be built concurrently */
+    int bps;                 /* bytes per sample of f2y / f2uv (1 or 2; the search uses the top 8 bits)  */
     int planePitch;          /* words per packed plane row                                       */
     int planeSize;           /* words per packed plane                                           */
     int W, H, s, lw, lh;
@@ -48,6 +50,7 @@ struct FlowParams {
     uint32_t epoch;          /* tag of this launch (never 0, differs from the previous launch)     */
     int16_t *off;            /* raw offsets  [2][lh][lw]  (offsetArray)                           */
     int16_t *blur;           /* blurred      [2][lh][lw]  (blurredOffsetArray)                    */
+    uint32_t *blurXY;        /* the same, one word per lattice point: x | y << 16 (read by the warp)  */
     uint8_t *trace;          /* optional [steps][lh][lw] winning layer per point, or NULL         */
     long long *timeline;     /* optional [ctas][HR_TIMELINE_SLOTS] clock64 stamps of thread 0, or NULL */
 };
@@ -58,6 +61,7 @@ struct WarpParams {
     const T *f2y, *f2uv;     /* sourceFrame21 = newest frame                                      */
     T *outY, *outUV;
     const int16_t *flow;     /* blurred offsets [2][lh][lw]                                       */
+    const uint32_t *flowXY;  /* the same as one word per lattice point: x | y << 16                  */
     int lw, lh, H, W, aW, s, mode;
     float t12, t21, black, white;
 };

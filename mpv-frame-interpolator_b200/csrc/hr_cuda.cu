@@ -12,6 +12,7 @@
 #include "hr_pack.cuh"
 #include "hr_search.cuh"
 #include "hr_warp.cuh"
+#include "hr_warp_fast.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -20,6 +21,8 @@
 #include <string.h>
 
 #define MAX_CALC_RES 270 /* video/filter/HopperRender/config.h:2 */
+#define HR_WARP_STREAMS 3
+#define HR_MAX_WARP_EVENTS 8
 
 struct HrContext {
     int H, W, aW, pixfmt, bps;
@@ -37,6 +40,7 @@ struct HrContext {
     uint8_t *outBuf;
     void *outY, *outUV;            /* current output planes (internal or caller's)              */
     int16_t *off, *blur;
+    uint32_t *blurXY;              /* blurred flow, x | y << 16 per lattice point (what the warp reads)     */
     unsigned long long *T;
     int tOff[HR_MAX_LEVELS];
     int tWords;
@@ -49,6 +53,8 @@ struct HrContext {
     long long *timeline;
     int timelineOn;
     int useFastWarp;
+    int haveRcp8;                  /* MUFU.RCP of the 8-bit level denominators, cached per knob setting     */
+    float rcp8Den[2], rcp8[2];
 
     /* spatial bands: this context owns rows [bandRow0[bandRank], bandRow1[bandRank]) */
     int bandWorld, bandRank;
@@ -58,6 +64,21 @@ struct HrContext {
     unsigned long long *mail;                       /* own mailbox (device memory)                             */
     unsigned long long bandFrames;                  /* frames uploaded so far                                  */
     int bandPending;                                /* hr_band_upload done, hr_band_gather outstanding        */
+
+    /* pipelined mode (hr_set_pipeline): independent work of consecutive frame pairs overlaps on internal streams —
+     * pack(k) || search(k) (the search reads frame 2 as it arrived), the warps of one pair on HR_WARP_STREAMS
+     * streams, search(k+1) || warps(k) (two flow buffers). Dependencies are CUDA events, never host waits. */
+    int pipeline;
+    cudaStream_t sPack, sSearch, sWarp[HR_WARP_STREAMS];
+    cudaEvent_t evIn;                          /* main stream: the newest frame's planes are complete          */
+    cudaEvent_t evPack[2];                     /* by packed-buffer identity: its pack kernel is done           */
+    cudaEvent_t evSearch[2];                   /* by flow buffer: the search that filled it is done            */
+    cudaEvent_t evWarp[2][HR_MAX_WARP_EVENTS]; /* by flow buffer: the warps reading it                         */
+    int nWarpEv[2], haveSearch[2], havePack[2], packedId[2];
+    int flowCur;                               /* flow buffer of the most recent search                        */
+    int16_t *blurB[2];
+    uint32_t *blurXYB[2];
+    unsigned warpRR;
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
@@ -91,6 +112,10 @@ static int bind_device(HrContext *ctx) {
     return 0;
 }
 
+static int sync_all(HrContext *ctx);
+static int pipe_join(HrContext *ctx);
+static int pipe_on(const HrContext *ctx);
+
 extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
 
 extern "C" const char *hr_last_error(const HrContext *ctx) { return ctx ? ctx->err : g_createErr; }
@@ -118,6 +143,20 @@ extern "C" int hr_destroy(HrContext *ctx) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    if (ctx->sPack) cudaStreamDestroy(ctx->sPack);
+    if (ctx->sSearch) cudaStreamDestroy(ctx->sSearch);
+    for (int i = 0; i < HR_WARP_STREAMS; ++i)
+        if (ctx->sWarp[i]) cudaStreamDestroy(ctx->sWarp[i]);
+    if (ctx->evIn) cudaEventDestroy(ctx->evIn);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
+        if (ctx->evSearch[b]) cudaEventDestroy(ctx->evSearch[b]);
+        for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i)
+            if (ctx->evWarp[b][i]) cudaEventDestroy(ctx->evWarp[b][i]);
+    }
+    cudaFree(ctx->blurB[1]);
+    cudaFree(ctx->blurXYB[1]);
     cudaFree(ctx->frameBuf[0]);
     cudaFree(ctx->frameBuf[1]);
     cudaFree(ctx->packed[0]);
@@ -125,6 +164,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->outBuf);
     cudaFree(ctx->off);
     cudaFree(ctx->blur);
+    cudaFree(ctx->blurXY);
     cudaFree(ctx->T);
     cudaFree(ctx->partial);
     cudaFree(ctx->trace);
@@ -209,6 +249,7 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMalloc(&ctx->packed[1], ctx->packedBytes));
     CU(cudaMalloc(&ctx->off, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->blurXY, ln * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->T, (size_t)(words ? words : 32) * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->partial, (size_t)(bwords ? bwords : 32) * sizeof(unsigned long long)));
     CU(cudaMemset(ctx->frameBuf[0], 0, ctx->frameBytes));
@@ -218,9 +259,14 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMemset(ctx->packed[1], 0, ctx->packedBytes));
     CU(cudaMemset(ctx->off, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blur, 0, 2 * ln * sizeof(int16_t)));
+    CU(cudaMemset(ctx->blurXY, 0, ln * sizeof(uint32_t)));
     CU(cudaMemset(ctx->T, 0, (size_t)(words ? words : 32) * sizeof(unsigned long long)));
     CU(cudaMemset(ctx->partial, 0, (size_t)(bwords ? bwords : 32) * sizeof(unsigned long long)));
     ctx->epoch = 0;
+    ctx->blurB[0] = ctx->blur;
+    ctx->blurXYB[0] = ctx->blurXY;
+    ctx->packedId[0] = 0;
+    ctx->packedId[1] = 1;
     ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 8 + 516;
     for (int i = 0; i < 2; ++i) {
         ctx->fy[i] = ctx->frameBuf[i];
@@ -291,7 +337,7 @@ extern "C" int hr_get_info(const HrContext *ctx, HrInfo *info) {
 extern "C" int hr_set_stream(HrContext *ctx, void *cudaStream) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (sync_all(ctx)) return 1;
     ctx->stream = cudaStream ? (cudaStream_t)cudaStream : ctx->ownStream;
     return 0;
 }
@@ -299,8 +345,7 @@ extern "C" int hr_set_stream(HrContext *ctx, void *cudaStream) {
 extern "C" int hr_synchronize(HrContext *ctx) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
-    CU(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return sync_all(ctx);
 }
 
 extern "C" int hr_set_trace(HrContext *ctx, int enable) {
@@ -365,13 +410,13 @@ extern "C" int hr_set_profiling(HrContext *ctx, int enable) {
 
 /* pack the newest frame (slot 1) into its phase-planar copy */
 template <typename T>
-static void launch_pack_t(HrContext *ctx) {
+static void launch_pack_t(HrContext *ctx, cudaStream_t st) {
     const T *y = (const T *)ctx->fy[1], *uv = (const T *)ctx->fuv[1];
     const bool vec = ctx->s <= 4 && ctx->W % 16 == 0 && (((uintptr_t)y | (uintptr_t)uv) % 16 == 0);
     if (vec) {
         dim3 block(128), grid((ctx->W / 16 + 127) / 128, (ctx->H + 1) / 2);
         switch (ctx->s) {
-#define HR_PCASE(S_) case S_: pack_frame16_kernel<T, S_><<<grid, block, 0, ctx->stream>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->planePitch, ctx->planeSize); break;
+#define HR_PCASE(S_) case S_: pack_frame16_kernel<T, S_><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->planePitch, ctx->planeSize); break;
             HR_PCASE(0) HR_PCASE(1) HR_PCASE(2) HR_PCASE(3) HR_PCASE(4)
 #undef HR_PCASE
         }
@@ -379,18 +424,32 @@ static void launch_pack_t(HrContext *ctx) {
         const int bx = ctx->s <= 3 ? 128 : 64;
         dim3 block(bx, 1 << ctx->s);
         dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
-        pack_frame_kernel<T><<<grid, block, 0, ctx->stream>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+        pack_frame_kernel<T><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
     }
 }
 static int launch_pack(HrContext *ctx) {
     if (ctx->s > 6) return fail(ctx, "frames of more than %d lines are not supported", MAX_CALC_RES << 6);
-    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[4], ctx->stream));
-    if (ctx->bps == 1) launch_pack_t<uint8_t>(ctx);
-    else launch_pack_t<uint16_t>(ctx);
+    cudaStream_t st = ctx->stream;
+    const int id = ctx->packedId[1];
+    if (pipe_on(ctx)) {
+        /* on its own stream, next to the search of the same pair (which does not read this copy): after the
+         * frame has arrived and after the previous search, the last reader of the buffer being overwritten */
+        st = ctx->sPack;
+        CU(cudaEventRecord(ctx->evIn, ctx->stream));
+        CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
+        if (ctx->haveSearch[ctx->flowCur]) CU(cudaStreamWaitEvent(st, ctx->evSearch[ctx->flowCur], 0));
+    }
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[4], st));
+    if (ctx->bps == 1) launch_pack_t<uint8_t>(ctx, st);
+    else launch_pack_t<uint16_t>(ctx, st);
     CU(cudaGetLastError());
     if (ctx->profiling) {
-        CU(cudaEventRecord(ctx->evK[5], ctx->stream));
+        CU(cudaEventRecord(ctx->evK[5], st));
         ctx->havePackT = 1;
+    }
+    if (ctx->sPack) {
+        CU(cudaEventRecord(ctx->evPack[id], st));
+        ctx->havePack[id] = 1;
     }
     ctx->launches++;
     return 0;
@@ -407,12 +466,74 @@ static void rotate_slots(HrContext *ctx, int *freeSlot) {
     uint32_t *t = ctx->packed[0];
     ctx->packed[0] = ctx->packed[1];
     ctx->packed[1] = t;
+    const int id = ctx->packedId[0];
+    ctx->packedId[0] = ctx->packedId[1];
+    ctx->packedId[1] = id;
+}
+
+/* ---- pipelined mode ----------------------------------------------------------------------------------- */
+static int pipe_on(const HrContext *ctx) { return ctx->pipeline && ctx->bandWorld <= 1; }
+
+/* make `st` wait for every warp that reads flow buffer b */
+static int wait_warps(HrContext *ctx, cudaStream_t st, int b) {
+    for (int i = 0; i < ctx->nWarpEv[b]; ++i) CU(cudaStreamWaitEvent(st, ctx->evWarp[b][i], 0));
+    return 0;
+}
+/* order the main stream after everything in flight on the internal streams (no host wait) */
+static int pipe_join(HrContext *ctx) {
+    if (!ctx->sPack) return 0;
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->havePack[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evPack[b], 0));
+        if (ctx->haveSearch[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evSearch[b], 0));
+        if (wait_warps(ctx, ctx->stream, b)) return 1;
+    }
+    return 0;
+}
+static int sync_all(HrContext *ctx) {
+    if (pipe_join(ctx)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hr_set_pipeline(HrContext *ctx, int enable) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    if (sync_all(ctx)) return 1;
+    if (enable && !ctx->sPack) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        /* the search is the critical path of a pair: its CTAs are placed first */
+        CU(cudaStreamCreateWithPriority(&ctx->sSearch, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
+        CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
+            for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) CU(cudaEventCreateWithFlags(&ctx->evWarp[b][i], cudaEventDisableTiming));
+        }
+        const size_t ln = (size_t)ctx->lw * ctx->lh;
+        CU(cudaMalloc(&ctx->blurB[1], 2 * ln * sizeof(int16_t)));
+        CU(cudaMalloc(&ctx->blurXYB[1], ln * sizeof(uint32_t)));
+        CU(cudaMemset(ctx->blurB[1], 0, 2 * ln * sizeof(int16_t)));
+        CU(cudaMemset(ctx->blurXYB[1], 0, ln * sizeof(uint32_t)));
+        ctx->deviceBytes += 2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t);
+    }
+    ctx->pipeline = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int hr_pipeline_join(HrContext *ctx) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    return pipe_join(ctx);
 }
 
 extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *uvPlane) {
     if (!ctx) return 1;
     if (!yPlane || !uvPlane) return fail(ctx, "hr_update_frame: NULL plane");
     if (bind_device(ctx)) return 1;
+    if (pipe_join(ctx)) return 1; /* the slot being overwritten may still be read by warps in flight */
     CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
     int slot;
     rotate_slots(ctx, &slot);
@@ -433,7 +554,8 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
     if (!ctx) return 1;
     if (!dY || !dUV) return fail(ctx, "hr_update_frame_device: NULL plane");
     if (bind_device(ctx)) return 1;
-    CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
+    if (!borrow && pipe_join(ctx)) return 1; /* the slot being overwritten may still be read by warps in flight */
+    if (!pipe_on(ctx)) CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
     int slot;
     rotate_slots(ctx, &slot);
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
@@ -479,7 +601,9 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     FlowParams P;
     memset(&P, 0, sizeof(P));
     P.p1 = ctx->packed[0];
-    P.p2 = ctx->packed[1];
+    P.f2y = ctx->fy[1];
+    P.f2uv = ctx->fuv[1];
+    P.bps = ctx->bps;
     P.planePitch = ctx->planePitch;
     P.planeSize = ctx->planeSize;
     P.W = ctx->W;
@@ -505,26 +629,68 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     memcpy(P.bigOff, ctx->bigOff, sizeof(P.bigOff));
     if (++ctx->epoch == 0) ctx->epoch = 1; /* 0 is the tag of never-written words */
     P.epoch = ctx->epoch;
+    /* pipelined: into the flow buffer the warps of the previous pair are not reading */
+    const int pl = pipe_on(ctx);
+    const int fb = pl ? (ctx->flowCur ^ 1) : ctx->flowCur;
+    cudaStream_t st = pl ? ctx->sSearch : ctx->stream;
     P.off = ctx->off;
-    P.blur = ctx->blur;
+    P.blur = ctx->blurB[fb];
+    P.blurXY = ctx->blurXYB[fb];
     P.trace = ctx->traceOn ? ctx->trace : NULL;
     P.timeline = ctx->timelineOn ? ctx->timeline : NULL;
     void *args[] = {&P};
-    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], ctx->stream));
+    if (pl) {
+        /* after: the newest frame (evIn, recorded by the update), the packed copy of the previous frame, the warps
+         * that read the flow buffer about to be overwritten (those of the pair before the previous one) */
+        CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
+        if (ctx->havePack[ctx->packedId[0]]) CU(cudaStreamWaitEvent(st, ctx->evPack[ctx->packedId[0]], 0));
+        if (wait_warps(ctx, st, fb)) return 1;
+        ctx->nWarpEv[fb] = 0;
+    } else if (ctx->sPack) {
+        /* the pipeline was used earlier: order this launch after what is left of it */
+        if (pipe_join(ctx)) return 1;
+    }
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], st));
     const void *kfn = search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn);
-    CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, ctx->stream));
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, st));
     if (ctx->profiling) {
-        CU(cudaEventRecord(ctx->evK[1], ctx->stream));
+        CU(cudaEventRecord(ctx->evK[1], st));
         ctx->haveSearchT = 1;
     }
     ctx->launches++;
-    CU(cudaEventRecord(ctx->evFlowEnd, ctx->stream));
+    ctx->flowCur = fb;
+    ctx->blur = ctx->blurB[fb];
+    ctx->blurXY = ctx->blurXYB[fb];
+    if (ctx->sPack) {
+        CU(cudaEventRecord(ctx->evSearch[fb], st));
+        ctx->haveSearch[fb] = 1;
+    }
+    if (!pl || seconds) CU(cudaEventRecord(ctx->evFlowEnd, st));
     if (seconds) {
         CU(cudaEventSynchronize(ctx->evFlowEnd));
         float ms = 0.f;
-        if (ctx->framesSeen > 0) CU(cudaEventElapsedTime(&ms, ctx->evUpdate, ctx->evFlowEnd));
+        if (ctx->framesSeen > 0 && cudaEventElapsedTime(&ms, ctx->evUpdate, ctx->evFlowEnd) != cudaSuccess) {
+            cudaGetLastError(); /* pipelined device updates do not stamp their start */
+            ms = 0.f;
+        }
         *seconds = (double)ms * 1e-3;
     }
+    return 0;
+}
+
+__global__ void rcp_pair_kernel(float a, float b, float *out) {
+    out[0] = rcp_approx(a);
+    out[1] = rcp_approx(b);
+}
+static int device_rcp(HrContext *ctx, const float *den, float *out) {
+    float *d = NULL;
+    CU(cudaMalloc(&d, 2 * sizeof(float)));
+    rcp_pair_kernel<<<1, 1, 0, ctx->stream>>>(den[0], den[1], d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, "CUDA error in device_rcp: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -538,6 +704,7 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.outY = (T *)ctx->outY;
     P.outUV = (T *)ctx->outUV;
     P.flow = ctx->blur;
+    P.flowXY = ctx->blurXY;
     P.lw = ctx->lw;
     P.lh = ctx->lh;
     P.H = ctx->H;
@@ -558,24 +725,89 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
         r1 = ctx->bandRow1[ctx->bandRank];
     }
     /* band boundaries are multiples of 2^(s+1) rows, so luma and chroma row groups do not straddle them */
-    const int lumaG0 = r0 / ROWS, lumaGroups = (r1 + ROWS - 1) / ROWS - lumaG0;
-    const int chromaG0 = (r0 >> 1) / ROWS, chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - chromaG0;
-    const int groups = lumaGroups + chromaGN;
-    dim3 block(32, 8);
-    dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
-    /* the block path: 4x4 blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in
-     * [0,1], level denominators for which div.full.f32 is MUFU.RCP * x (hr_warp.cuh) */
-    const float den1 = white - black, den2 = white;
-    const int denOk = fabsf(den1) >= 1.17549435e-38f && fabsf(den1) <= 8.50705917e37f && fabsf(den2) >= 1.17549435e-38f && fabsf(den2) <= 8.50705917e37f;
-    int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
-               (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
-    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], ctx->stream));
-    if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups, lumaG0, chromaG0, chromaGN);
-    else warp_blend_kernel<T, 4><<<grid, block, 0, ctx->stream>>>(P, fast, lumaGroups, lumaG0, chromaG0, chromaGN);
+    WarpFastArgs A;
+    memset(&A, 0, sizeof(A));
+    A.lumaG0 = r0 / ROWS;
+    A.lumaGroups = (r1 + ROWS - 1) / ROWS - A.lumaG0;
+    A.chromaG0 = (r0 >> 1) / ROWS;
+    A.chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - A.chromaG0;
+    const int groups = A.lumaGroups + A.chromaGN;
+    /* level constants (hr_warp.cuh: 8-bit = the reference's expressions as NVIDIA OpenCL compiles them; 16-bit =
+     * DESIGN.md §P010, correctly rounded reciprocals) */
+    const bool is16 = sizeof(T) == 2;
+    volatile float b16 = black / 255.0f, w16 = white / 255.0f;
+    b16 = b16 * 65472.0f;
+    w16 = w16 * 65472.0f;
+    const float outMax = is16 ? 65472.0f : 255.0f, inMax = is16 ? 65535.0f : 255.0f, mid = is16 ? 32768.0f : 128.0f;
+    A.sub[0] = is16 ? (float)b16 : black;
+    A.sub[1] = mid;
+    A.den[0] = is16 ? (float)w16 - (float)b16 : white - black;
+    A.den[1] = is16 ? (float)w16 : white;
+    int denOk = 1;
+    for (int c = 0; c < 2; ++c) denOk = denOk && fabsf(A.den[c]) >= 1.17549435e-38f && fabsf(A.den[c]) <= 8.50705917e37f;
+    if (denOk) {
+        if (!is16 && (!ctx->haveRcp8 || ctx->rcp8Den[0] != A.den[0] || ctx->rcp8Den[1] != A.den[1])) {
+            /* MUFU.RCP of the two denominators, read back once per change of the level knobs */
+            if (device_rcp(ctx, A.den, ctx->rcp8)) return 1;
+            ctx->rcp8Den[0] = A.den[0];
+            ctx->rcp8Den[1] = A.den[1];
+            ctx->haveRcp8 = 1;
+        }
+        for (int c = 0; c < 2; ++c) {
+            volatile float rc = is16 ? 1.0f / A.den[c] : ctx->rcp8[c];
+            A.rcp[c] = rc;
+            A.subIsInt[c] = A.sub[c] >= 0.0f && A.sub[c] < 4194304.0f && floorf(A.sub[c]) == A.sub[c];
+            /* the map is monotonic: it stays inside the output range iff its two ends do */
+            volatile float lo = (0.0f - A.sub[c]) * rc, hi = (inMax - A.sub[c]) * rc;
+            if (c == 0) {
+                lo = lo * outMax;
+                hi = hi * outMax;
+            } else {
+                lo = fmaf(lo, outMax, mid);
+                hi = fmaf(hi, outMax, mid);
+            }
+            const float mn = fminf(lo, hi), mx = fmaxf(lo, hi);
+            A.clampNeeded[c] = !(mn >= 0.0f && mx < (is16 ? 65536.0f : 256.0f));
+        }
+    }
+    /* the block path: blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in [0,1], level
+     * denominators for which div.full.f32 is MUFU.RCP * x (hr_warp.cuh) */
+    const int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
+                     ctx->H >= 2 * (ROWS + 2) && ctx->aW >= 8 &&
+                     (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
+    /* pipelined: warps into caller-owned planes are independent of one another -> round-robin over the warp
+     * streams, each after the search that produced the flow; warps into the internal output frame stay on the
+     * main stream (the download that follows is ordered there) */
+    const int pl = pipe_on(ctx), fb = ctx->flowCur;
+    cudaStream_t st = ctx->stream;
+    if (pl) {
+        if (ctx->outY != ctx->outBuf) st = ctx->sWarp[ctx->warpRR++ % HR_WARP_STREAMS];
+        if (ctx->haveSearch[fb]) CU(cudaStreamWaitEvent(st, ctx->evSearch[fb], 0));
+        else CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
+    }
+    if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], st));
+    if (fast) {
+        dim3 block(32, 4);
+        dim3 grid((ctx->aW + 127) / 128, (groups + 3) / 4);
+        if (ROWS == 8) warp_fast_kernel<T, 8><<<grid, block, 0, st>>>(P, A);
+        else warp_fast_kernel<T, 4><<<grid, block, 0, st>>>(P, A);
+    } else {
+        dim3 block(32, 8);
+        dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
+        if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, st>>>(P, 0, A.lumaGroups, A.lumaG0, A.chromaG0, A.chromaGN);
+        else warp_blend_kernel<T, 4><<<grid, block, 0, st>>>(P, 0, A.lumaGroups, A.lumaG0, A.chromaG0, A.chromaGN);
+    }
     CU(cudaGetLastError());
     if (ctx->profiling) {
-        CU(cudaEventRecord(ctx->evK[3], ctx->stream));
+        CU(cudaEventRecord(ctx->evK[3], st));
         ctx->haveWarpT = 1;
+    }
+    if (pl) {
+        if (ctx->nWarpEv[fb] == HR_MAX_WARP_EVENTS) { /* fold the recorded readers into one event */
+            if (wait_warps(ctx, st, fb)) return 1;
+            ctx->nWarpEv[fb] = 0;
+        }
+        CU(cudaEventRecord(ctx->evWarp[fb][ctx->nWarpEv[fb]++], st));
     }
     ctx->launches++;
     return 0;
@@ -589,8 +821,34 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
     }
     if (mode < 0 || mode > 6) return fail(ctx, "hr_warp: unknown output mode %d", mode);
     if (bind_device(ctx)) return 1;
-    CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
+    if (!ctx->pipeline && ctx->sPack && pipe_join(ctx)) return 1; /* leftovers of an earlier pipelined phase */
+    if (!pipe_on(ctx) || ctx->outY == ctx->outBuf) CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
     return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, t, mode, black, white) : launch_warp<uint16_t>(ctx, t, mode, black, white);
+}
+
+/* One source frame of a device-resident stream in ONE call: update + flow + nWarps warps, each into its own
+ * caller-owned planes. Enqueue-only. */
+extern "C" int hr_step_device(HrContext *ctx, const void *dY, const void *dUV, int borrow, int searchRadius, int deltaScalar, int neighborBiasScalar,
+                              int nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel, float whiteLevel, void *const *outY,
+                              void *const *outUV) {
+    if (!ctx) return 1;
+    if (nWarps < 0 || (nWarps > 0 && (!blendingScalars || !outY || !outUV))) return fail(ctx, "hr_step_device: bad warp list");
+    if (hr_update_frame_device(ctx, dY, dUV, borrow)) return 1;
+    if (ctx->framesSeen < 2) return 0; /* the first frame of a stream has no partner yet (vf_HopperRender.c:490-495) */
+    if (hr_calc_flow(ctx, searchRadius, deltaScalar, neighborBiasScalar, NULL)) return 1;
+    void *keepY = ctx->outY, *keepUV = ctx->outUV;
+    int rc = 0;
+    for (int i = 0; i < nWarps && !rc; ++i) {
+        if (!outY[i] || !outUV[i]) rc = fail(ctx, "hr_step_device: NULL output plane");
+        else {
+            ctx->outY = outY[i];
+            ctx->outUV = outUV[i];
+            rc = hr_warp(ctx, blendingScalars[i], frameOutputMode, blackLevel, whiteLevel);
+        }
+    }
+    ctx->outY = keepY;
+    ctx->outUV = keepUV;
+    return rc;
 }
 
 extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds) {
@@ -839,7 +1097,7 @@ extern "C" int hr_get_offsets(HrContext *ctx, int16_t *raw, int16_t *blurred) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
     const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (sync_all(ctx)) return 1;
     if (raw) CU(cudaMemcpy(raw, ctx->off, n, cudaMemcpyDeviceToHost));
     if (blurred) CU(cudaMemcpy(blurred, ctx->blur, n, cudaMemcpyDeviceToHost));
     return 0;
@@ -849,8 +1107,12 @@ extern "C" int hr_set_blurred_offsets(HrContext *ctx, const int16_t *blurred) {
     if (!ctx || !blurred) return 1;
     if (bind_device(ctx)) return 1;
     const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (sync_all(ctx)) return 1;
     CU(cudaMemcpy(ctx->blur, blurred, n, cudaMemcpyHostToDevice));
+    const int ln = ctx->lw * ctx->lh;
+    pack_flow_kernel<<<(ln + 255) / 256, 256, 0, ctx->stream>>>(ctx->blur, ctx->blurXY, ln);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -880,7 +1142,7 @@ extern "C" int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers) {
     if (step < 0 || step >= 2 * ctx->iters) return fail(ctx, "hr_get_step_layers: step %d out of range", step);
     if (bind_device(ctx)) return 1;
     const size_t ln = (size_t)ctx->lw * ctx->lh;
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (sync_all(ctx)) return 1;
     CU(cudaMemcpy(layers, ctx->trace + (size_t)step * ln, ln, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -888,7 +1150,7 @@ extern "C" int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers) {
 extern "C" int hr_get_kernel_times(HrContext *ctx, double *searchSeconds, double *warpSeconds, double *packSeconds) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (sync_all(ctx)) return 1;
     double *outs[3] = {searchSeconds, warpSeconds, packSeconds};
     const int have[3] = {ctx->haveSearchT, ctx->haveWarpT, ctx->havePackT};
     for (int i = 0; i < 3; ++i) {

@@ -377,8 +377,15 @@ __device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh
         put_tagged(P.T + P.tOff[it] + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
 }
 
+/* HR_SEARCH_MAXNREG: registers per thread the search may use. One CTA of 512 threads per SM either way; a lower
+ * cap leaves room for the pack and warp CTAs of the neighbouring pairs on the same SM (pipelined mode). */
+#ifdef HR_SEARCH_MAXNREG
+#define HR_SEARCH_BOUNDS __maxnreg__(HR_SEARCH_MAXNREG)
+#else
+#define HR_SEARCH_BOUNDS __launch_bounds__(HR_THREADS, 1)
+#endif
 template <int RT, bool MULTI, bool DBG>
-__global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowParams P) {
+__global__ void HR_SEARCH_BOUNDS flow_search_kernel(const FlowParams P) {
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nCtas = gridDim.x;
@@ -396,9 +403,20 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
     Thr t;
     t.ox = t.oy = 0;
     t.nw[0] = t.nw[1] = t.nw[2] = t.nw[3] = 0u;
+    /* frame2 sample of a lattice point as the packed word Y | U << 8 | V << 16 (calcDeltaSumsKernel.cl:96-98:
+     * chroma at row y >> 1, byte column x & ~1 (+1)); P010: the top 8 bits of every sample */
+    auto frame2_word = [&](int x, int y) -> uint32_t {
+        const size_t iy = (size_t)y * P.W + x, iuv = (size_t)(y >> 1) * P.W + (x & ~1);
+        if (P.bps == 1) {
+            const uint8_t *fy = (const uint8_t *)P.f2y, *fuv = (const uint8_t *)P.f2uv;
+            return (uint32_t)__ldg(fy + iy) | ((uint32_t)__ldg(fuv + iuv) << 8) | ((uint32_t)__ldg(fuv + iuv + 1) << 16);
+        }
+        const uint16_t *fy = (const uint16_t *)P.f2y, *fuv = (const uint16_t *)P.f2uv;
+        return ((uint32_t)__ldg(fy + iy) >> 8) | ((uint32_t)__ldg(fuv + iuv) & 0xff00u) | (((uint32_t)__ldg(fuv + iuv + 1) & 0xff00u) << 8);
+    };
     auto load_frame2 = [&]() {
-        t.v2a = __ldg(P.p2 + (t.cy0s >> P.s) * P.planePitch + (t.cxs >> P.s)) & t.m0;
-        t.v2b = __ldg(P.p2 + (t.cy1s >> P.s) * P.planePitch + (t.cxs >> P.s)) & t.m1;
+        t.v2a = frame2_word(t.cxs, t.cy0s) & t.m0;
+        t.v2b = frame2_word(t.cxs, t.cy1s) & t.m1;
     };
     if (!MULTI) {
         thr_place(P, t, blockIdx.x, warp, lane);
@@ -542,8 +560,10 @@ __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_kernel(const FlowPa
                         sy += hY[(r + k) * 32 + c];
                     }
                     const size_t idx = (size_t)y * P.lw + x;
-                    P.blur[idx] = (int16_t)(sx / 64); /* C division truncates toward zero */
-                    P.blur[ln + idx] = (int16_t)(sy / 64);
+                    const int bx = sx / 64, by = sy / 64; /* C division truncates toward zero */
+                    P.blur[idx] = (int16_t)bx;
+                    P.blur[ln + idx] = (int16_t)by;
+                    P.blurXY[idx] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
                 }
             }
             __syncthreads();
