@@ -40,6 +40,11 @@ WORKLOADS = {
     "8k-p010-24to60": (7680, 4320, 1, 24.0, 60.0, 2),
 }
 L2_BYTES = 126 * 1024 * 1024
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {
+    ("1080p-nv12-24to60", "search"): 5198080, ("1080p-nv12-24to60", "warp"): 6786560, ("1080p-nv12-24to60", "pack"): 3116288,
+    ("4k-p010-24to144", "warp"): 52152832, ("4k-p010-24to144", "pack"): 25096448,
+}
 
 
 def parse_args():
@@ -53,6 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="device-resident loop without the pipelined mode (one kernel after the other)")
     ap.add_argument("--bands", action="store_true",
                     help="split every frame into spatial bands over the N ranks (8K config, SURVEY.md §8e): strong scaling, "
                          "bands uploaded/warped/downloaded per GPU, the other bands pulled by NVLink P2P")
@@ -190,6 +196,24 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPU cores next to GPU `index` (NVML's CPU affinity), so that the pinned host
+    frames of the end-to-end leg are allocated on the GPU's own NUMA node. Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_ours(args):
     import torch
     import hr_pkg
@@ -202,6 +226,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    numa_cpus = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -257,14 +282,23 @@ def run_ours(args):
             g.update_frame_device(y, uv, borrow=True)
 
     def step_device(i):
-        feed(i)
-        g.calc_flow(radius, 8, 6, blocking=False)
-        for t in ts[i]:
-            oy, ouv = out_ring[oi[0] % len(out_ring)]
-            oi[0] += 1
-            g.set_output_device(oy, ouv)
-            g.warp(t, mode)
-        return len(ts[i])
+        n = len(ts[i])
+        if banded:
+            feed(i)
+            g.calc_flow(radius, 8, 6, blocking=False)
+            for t in ts[i]:
+                oy, ouv = out_ring[oi[0] % len(out_ring)]
+                oi[0] += 1
+                g.set_output_device(oy, ouv)
+                g.warp(t, mode)
+            return n
+        # one C call per source frame: update (borrowed device planes) + flow + the pacing rule's warps, each into
+        # its own output frame; pipelined mode overlaps the independent work of consecutive pairs
+        outs = [out_ring[(oi[0] + j) % len(out_ring)] for j in range(n)]
+        oi[0] += n
+        y, uv = ring[i % nring]
+        g.step_device(y, uv, ts[i], outs, radius=radius, mode=mode)
+        return n
 
     def barrier():
         stream.synchronize()
@@ -273,10 +307,13 @@ def run_ours(args):
             dist.barrier()
 
     # ---- device-resident timed region ---------------------------------------------------------
+    pipelined = (not banded) and (not args.serial)
     with torch.cuda.stream(stream):
         feed(nring - 1)
+        g.set_pipeline(pipelined)
         for i in range(W_):
             step_device(i)
+        g.synchronize()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
@@ -287,11 +324,26 @@ def run_ours(args):
         outs = 0
         for i in range(K):
             outs += step_device(W_ + i)
+        g.pipeline_join()              # the main stream now follows every internal stream: e1 closes the whole region
         e1.record(stream)
+        g.synchronize()
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         launches = g.launch_count() - l0
         ms = e0.elapsed_time(e1)
+        g.set_pipeline(False)
+        serial_ms = None
+        if pipelined:                  # the same steps, one kernel after the other (what the blocking interface sees)
+            for i in range(W_):
+                step_device(i)
+            g.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            ks = min(K, 100)
+            so = sum(step_device(W_ + i) for i in range(ks))
+            s1.record(stream)
+            g.synchronize()
+            serial_ms = s0.elapsed_time(s1) / max(1, so)
 
     # ---- per-kernel device time, by difference -------------------------------------------------------
     # One CUDA event pair around a single ~5-40 us launch adds several us of front-end latency to it, so
@@ -337,13 +389,20 @@ def run_ours(args):
             raise SystemExit("initOpticalFlowCalc failed")
         ofc.opticalFlowSearchRadius = radius
         npdt = np.uint16 if pixfmt else np.uint8
+        # host frames as mpv's image pool lays them out: one pinned allocation, the UV plane right behind the Y plane
+        def host_frame():
+            ny, nuv = (r1 - r0) * w, ((r1 >> 1) - (r0 >> 1)) * w
+            buf = torch.empty(ny + nuv, dtype=tdtype).pin_memory()
+            return buf[:ny].view(r1 - r0, w), buf[ny:].view((r1 >> 1) - (r0 >> 1), w)
+
         hring = []
         for k in range(nbase):
             y, uv = base[k]
-            ty = torch.from_numpy(np.ascontiguousarray(y[r0:r1])).pin_memory()
-            tuv = torch.from_numpy(np.ascontiguousarray(uv[r0 >> 1:r1 >> 1])).pin_memory()
+            ty, tuv = host_frame()
+            ty.copy_(torch.from_numpy(np.ascontiguousarray(y[r0:r1])).view(tdtype))
+            tuv.copy_(torch.from_numpy(np.ascontiguousarray(uv[r0 >> 1:r1 >> 1])).view(tdtype))
             hring.append((ty, tuv))
-        hout = (torch.empty((r1 - r0, w), dtype=tdtype).pin_memory(), torch.empty(((r1 >> 1) - (r0 >> 1), w), dtype=tdtype).pin_memory())
+        hout = host_frame()
         Ke = min(K, 100)
         We = min(W_, 5)
         if banded:
@@ -410,12 +469,13 @@ def run_ours(args):
             if avg[k] > 0:
                 ach = alg[k] / (avg[k] * 1e-3) / 1e9
                 roof[k] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                           "traffic": None, "avg_us": avg[k] * 1e3, "share_of_step": per_step[k] / max(1e-12, sum(per_step.values())),
+                           "traffic": NCU_TRAFFIC.get((args.workload, k)), "avg_us": avg[k] * 1e3, "share_of_step": per_step[k] / max(1e-12, sum(per_step.values())),
                            "algorithmic_bytes": alg[k], "peak_source": pk_src}
         evals = 2 * g.info.iterations * radius * lw * lh
         if avg["search"] > 0:
             roof["search"]["candidate_evals_per_s"] = evals / (avg["search"] * 1e-3)
-            roof["search"]["note"] = "latency/ALU bound (16 dependent steps, grid barriers): HBM fraction is not the limiter, see DESIGN.md"
+            roof["search"]["note"] = ("latency/issue bound, not HBM: 16 dependent steps with tile-to-tile hand-offs; ncu (profiles/): issue slots 39 % busy, "
+                                      "ALU pipe 39 %, 41 instructions per packed SAD; the HBM-bound kernel of the step is the warp, see roofline_hbm_kernel")
         line = {
             "metric": "interpolated frames/s", "value": tot_outs / (max_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W_, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "strong" if banded else "weak", "vs_baseline": None,
@@ -423,18 +483,22 @@ def run_ours(args):
             "config": {"workload": args.workload, "frame": "%dx%d" % (w, h), "search_radius": radius, "mode": mode,
                        "streams_per_gpu": 1, "partition": ("%d spatial bands, NVLink P2P gather" % world) if banded else ("independent streams" if world > 1 else "none"),
                        "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (nring, nring * frame_bytes >> 20),
-                       "flow_ms_per_pair": avg["search"], "interp_only_frames_per_s": None},
+                       "flow_ms_per_pair": avg["search"], "interp_only_frames_per_s": None,
+                       "device_loop": ("pipelined: pack || search, warps on parallel streams, search(k+1) || warps(k)" if pipelined else "serial"),
+                       "serial_frames_per_s": (1e3 / serial_ms if serial_ms else None)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof.get(dom),
             "kernels": roof,
             "dominant_kernel": dom,
+            "roofline_hbm_kernel": dict(roof.get("warp", {}), kernel="warp_fast_kernel"),
         }
         if e2e:
             band_frac = (r1 - r0) / h
             line["e2e"] = {"value": e_outs / e_dt, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes * band_frac),
                            "d2h_bytes_per_step": int(frame_bytes * band_frac * (e2e[0] / e2e[2])), "steps": e2e[2],
-                           "api": "initOpticalFlowCalc/updateFrame/calculateOpticalFlow/warpFrames/downloadFrame, pinned host planes, blocking like the reference"}
+                           "api": "initOpticalFlowCalc/updateFrame/calculateOpticalFlow/warpFrames/downloadFrame, pinned host planes, blocking like the reference",
+                           "host_cpus_near_gpu": numa_cpus}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))

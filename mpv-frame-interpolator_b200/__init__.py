@@ -413,6 +413,12 @@ def initOpticalFlowCalc(ofc: OpticalFlowCalc, frameHeight: int, frameWidth: int,
     except (HrError, OSError, RuntimeError) as e:
         print("[HopperRender] init failed: %s" % e)
         return True
+    try:
+        impl.set_pipeline(True)      # as the C host does (opticalFlowCalc.c): pack beside the search, same results
+    except HrError as e:
+        print("[HopperRender] init failed: %s" % e)
+        impl.close()
+        return True
     ofc.impl = impl
     ofc.frameWidth, ofc.frameHeight, ofc.actualWidth = frameWidth, frameHeight, actualWidth
     ofc.outputBlackLevel, ofc.outputWhiteLevel = 0.0, 255.0      # opticalFlowCalc.c:328-329

@@ -155,8 +155,10 @@ extern "C" int hr_destroy(HrContext *ctx) {
         for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i)
             if (ctx->evWarp[b][i]) cudaEventDestroy(ctx->evWarp[b][i]);
     }
-    cudaFree(ctx->blurB[1]);
+    cudaFree(ctx->blurB[1]); /* ctx->blur / blurXY alias one of the two flow buffers: [0] is freed below through them */
     cudaFree(ctx->blurXYB[1]);
+    ctx->blur = ctx->blurB[0];
+    ctx->blurXY = ctx->blurXYB[0];
     cudaFree(ctx->frameBuf[0]);
     cudaFree(ctx->frameBuf[1]);
     cudaFree(ctx->packed[0]);
@@ -539,8 +541,13 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     rotate_slots(ctx, &slot);
     uint8_t *dst = ctx->frameBuf[slot];
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
-    CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
+    if ((const uint8_t *)uvPlane == (const uint8_t *)yPlane + ylen) {
+        /* planes of one allocation, back to back (mpv's image pool lays NV12 out like this): one transfer */
+        CU(cudaMemcpyAsync(dst, yPlane, ylen + uvlen, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->fy[1] = dst;
     ctx->fuv[1] = dst + ylen;
     ctx->fslot[1] = slot;
@@ -792,10 +799,11 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
         if (ROWS == 8) warp_fast_kernel<T, 8><<<grid, block, 0, st>>>(P, A);
         else warp_fast_kernel<T, 4><<<grid, block, 0, st>>>(P, A);
     } else {
+        /* per-sample kernel, row groups of 4 */
+        const int lg0 = r0 / 4, lgn = (r1 + 3) / 4 - lg0, cg0 = (r0 >> 1) / 4, cgn = ((r1 >> 1) + 3) / 4 - cg0;
         dim3 block(32, 8);
-        dim3 grid((ctx->aW + 127) / 128, (groups + 7) / 8);
-        if (ROWS == 8) warp_blend_kernel<T, 8><<<grid, block, 0, st>>>(P, 0, A.lumaGroups, A.lumaG0, A.chromaG0, A.chromaGN);
-        else warp_blend_kernel<T, 4><<<grid, block, 0, st>>>(P, 0, A.lumaGroups, A.lumaG0, A.chromaG0, A.chromaGN);
+        dim3 grid((ctx->aW + 127) / 128, (lgn + cgn + 7) / 8);
+        warp_generic_kernel<T><<<grid, block, 0, st>>>(P, lgn, lg0, cg0, cgn);
     }
     CU(cudaGetLastError());
     if (ctx->profiling) {
@@ -856,8 +864,12 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
     if (!yPlane || !uvPlane) return fail(ctx, "hr_download: NULL plane");
     if (bind_device(ctx)) return 1;
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
-    CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(uvPlane, ctx->outUV, uvlen, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((uint8_t *)uvPlane == (uint8_t *)yPlane + ylen && (uint8_t *)ctx->outUV == (uint8_t *)ctx->outY + ylen) {
+        CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen + uvlen, cudaMemcpyDeviceToHost, ctx->stream)); /* back-to-back planes: one transfer */
+    } else {
+        CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(uvPlane, ctx->outUV, uvlen, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
     CU(cudaEventSynchronize(ctx->evDlEnd));
     if (seconds) {

@@ -379,11 +379,10 @@ __device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh
 
 /* HR_SEARCH_MAXNREG: registers per thread the search may use. One CTA of 512 threads per SM either way; a lower
  * cap leaves room for the pack and warp CTAs of the neighbouring pairs on the same SM (pipelined mode). */
-#ifdef HR_SEARCH_MAXNREG
-#define HR_SEARCH_BOUNDS __maxnreg__(HR_SEARCH_MAXNREG)
-#else
-#define HR_SEARCH_BOUNDS __launch_bounds__(HR_THREADS, 1)
+#ifndef HR_SEARCH_MAXNREG
+#define HR_SEARCH_MAXNREG 88 /* measured (tools/diag_pipeline.py): no spills at R = 5, 24 bytes at R = 16, same serial time as 117 */
 #endif
+#define HR_SEARCH_BOUNDS __maxnreg__(HR_SEARCH_MAXNREG)
 template <int RT, bool MULTI, bool DBG>
 __global__ void HR_SEARCH_BOUNDS flow_search_kernel(const FlowParams P) {
     __shared__ SearchShared sh;

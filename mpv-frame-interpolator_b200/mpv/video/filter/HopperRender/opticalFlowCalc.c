@@ -76,6 +76,13 @@ bool initOpticalFlowCalc(struct OpticalFlowCalc *ofc, const int frameHeight, con
         fprintf(stderr, "HopperRender CUDA error occurred in function: %s (%s)\n", __func__, hr_last_error(NULL));
         return 1;
     }
+    /* the packed copy of a new frame is only needed by the NEXT pair's search: let it be built beside this pair's
+     * search instead of in front of it (results are identical, include/hopperrender_cuda.h) */
+    if (hr_set_pipeline(ctx, 1)) {
+        fprintf(stderr, "HopperRender CUDA error occurred in function: %s (%s)\n", __func__, hr_last_error(ctx));
+        hr_destroy(ctx);
+        return 1;
+    }
     HrInfo info;
     hr_get_info(ctx, &info);
     ofc->opticalFlowResScalar = info.resScalar;

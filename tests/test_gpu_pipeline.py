@@ -52,3 +52,38 @@ def test_pipelined_steps_equal_serial(hr, synth, w, h, pixfmt):
     b.calc_flow(8, 8, 6)
     assert np.array_equal(b.get_offsets()[1], flows[0])
     b.close()
+
+
+@pytest.mark.parametrize("pixfmt", [0, 1])
+def test_download_into_pinned_planes_equals_staged_copy(hr, synth, pixfmt):
+    """downloadFrame into pinned and into pageable host planes, repeated downloads of one warp, mode changes in
+    between, through the reference-named interface (which runs the context in pipelined mode): same bits."""
+    import torch
+
+    w, h = 1920, 1080
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    npdt = np.uint16 if pixfmt else np.uint8
+    tdt = torch.uint16 if pixfmt else torch.uint8
+    ofc = hr.OpticalFlowCalc()
+    assert not hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt)
+    f = [clip.frame(k) for k in range(3)]
+    py, puv = torch.zeros((h, w), dtype=tdt).pin_memory(), torch.zeros((h // 2, w), dtype=tdt).pin_memory()
+    assert not hr.updateFrame(ofc, list(f[0]))
+    for k in (1, 2):
+        assert not hr.updateFrame(ofc, list(f[k]))
+        assert not hr.calculateOpticalFlow(ofc)
+        for t, mode in ((0.0, 2), (0.4, 2), (0.8, 5), (0.6, 0), (0.3, 3)):
+            ny, nuv = np.zeros((h, w), npdt), np.zeros((h // 2, w), npdt)
+            assert not hr.warpFrames(ofc, t, mode)
+            assert not hr.downloadFrame(ofc, [ny, nuv])
+            assert not hr.warpFrames(ofc, t, mode)
+            assert not hr.downloadFrame(ofc, [py, puv])
+            assert ofc.warpCalcTime > 0.0
+            assert np.array_equal(py.numpy().view(npdt), ny) and np.array_equal(puv.numpy().view(npdt), nuv), (k, t, mode)
+            py.zero_()
+            assert not hr.downloadFrame(ofc, [py, puv])            # again, without a new warp
+            assert np.array_equal(py.numpy().view(npdt), ny)
+            ny2, nuv2 = np.zeros_like(ny), np.zeros_like(nuv)
+            assert not hr.downloadFrame(ofc, [ny2, nuv2])
+            assert np.array_equal(ny2, ny) and np.array_equal(nuv2, nuv)
+    hr.freeOFC(ofc)
