@@ -148,6 +148,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads it can use: torchrun exports OMP_NUM_THREADS=1 to its workers
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     from oracle import hr_oracle_py as O
     import hr_pkg
 
