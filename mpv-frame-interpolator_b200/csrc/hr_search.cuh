@@ -192,13 +192,18 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
 
     uint32_t bestS = 0xffffffffu, mine = 0u;
     int winner = 0;
-    auto issue = [&](int z0, uint32_t (&va)[HR_ZCHUNK], uint32_t (&vb)[HR_ZCHUNK]) {
+    /* the two branches are separate code (a warp-uniform branch, not predication): the common, interior one
+     * carries no mirror arithmetic, and for AXIS 1 the lower point's word sits exactly one packed row below
+     * the upper point's (same phase plane) */
+    const bool lowerIsNextRow = AXIS == 1 && mb == ma + (1 << s);
+    auto issue_one = [&](auto interiorTag, int z0, uint32_t (&va)[HR_ZCHUNK], uint32_t (&vb)[HR_ZCHUNK]) {
+        constexpr bool INTERIOR = decltype(interiorTag)::value;
 #pragma unroll
         for (int j = 0; j < HR_ZCHUNK; ++j) {
             if (z0 + j < R) {
                 const int c = layer_shift<RT>(P, z0 + j);
                 int pa = ma + c, pb = mb + c;
-                if (!interior) {
+                if (!INTERIOR) {
                     pa = search_mirror(pa, D);
                     if (AXIS) pb = search_mirror(pb, D);
                 }
@@ -206,12 +211,20 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
                     const int xi = (pa & m) * mulA + (pa >> s);
                     va[j] = __ldg(P.p1 + (fa + xi));
                     vb[j] = __ldg(P.p1 + (fb + xi));
+                } else if (INTERIOR) {
+                    const uint32_t *q = P.p1 + (fa + (pa & m) * mulA + (pa >> s) * P.planePitch);
+                    va[j] = __ldg(q);
+                    vb[j] = __ldg(lowerIsNextRow ? q + P.planePitch : q);
                 } else {
                     va[j] = __ldg(P.p1 + (fa + (pa & m) * mulA + (pa >> s) * P.planePitch));
                     vb[j] = __ldg(P.p1 + (fb + (pb & m) * mulA + (pb >> s) * P.planePitch));
                 }
             }
         }
+    };
+    auto issue = [&](int z0, uint32_t (&va)[HR_ZCHUNK], uint32_t (&vb)[HR_ZCHUNK]) {
+        if (interior) issue_one(std::true_type(), z0, va, vb);
+        else issue_one(std::false_type(), z0, va, vb);
     };
     auto consume = [&](int z0, const uint32_t (&va)[HR_ZCHUNK], const uint32_t (&vb)[HR_ZCHUNK]) {
 #pragma unroll

@@ -137,14 +137,15 @@ def _warp_both(g, o, t, mode, black=0.0, white=255.0):
     return gy, guv, oy, ouv
 
 
-@pytest.mark.parametrize("w,h,stride", [(1920, 1080, 1920), (854, 480, 896), (480, 270, 480)])
+# (1918, 1080, 1920): encoded width not a multiple of 4 -> partial columns of the block kernel; 4K: 8-row blocks
+@pytest.mark.parametrize("w,h,stride", [(1920, 1080, 1920), (854, 480, 896), (480, 270, 480), (1918, 1080, 1920), (3840, 2160, 3840)])
 def test_warp_all_modes(hr, oracle, synth, w, h, stride):
     c = synth.MovingTextureClip(w, h, stride=stride)
     g, o = _run_pair(hr, oracle, c.frame(2), c.frame(3), h, stride, w, 8)
     _assert_flow_equal(g, o)
     msgs = []
     for mode in range(7):
-        for t in (0.0, 0.4, np.float32(0.8), 1.0):
+        for t in ((0.0, 0.4, np.float32(0.8), 1.0) if h <= 1080 else (0.4,)):
             gy, guv, oy, ouv = _warp_both(g, o, t, mode)
             tol = 1 if mode == 3 else 0
             for nm, a, b in (("Y", gy, oy), ("UV", guv, ouv)):
@@ -267,3 +268,45 @@ def test_device_resident_update_matches_host_update(hr, synth):
         by, buv, _ = b.download()
         assert np.array_equal(a.get_offsets()[1], b.get_offsets()[1])
         assert np.array_equal(ay, by) and np.array_equal(auv, buv)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160)])
+def test_p010_levels_and_large_flow(hr, oracle, synth, w, h):
+    """P010 with the level presets (the 16-bit black level is then not an integer: the unfolded subtraction and the
+    float clamp of the block kernel), with out-of-range samples (low 6 bits set, values above 1023 << 6: the 16-bit
+    clamp) and with a flow that reaches across the frame."""
+    c = synth.MovingTextureClip(w, h, pixfmt=1)
+    f2, f3 = c.frame(2), c.frame(3)
+    rng = np.random.default_rng(11)
+    noisy = []
+    for y, uv in (f2, f3):
+        y, uv = y.copy(), uv.copy()
+        y[::3, ::5] |= rng.integers(0, 64, size=y[::3, ::5].shape).astype(np.uint16)
+        y[5::97, 7::89] = 65535
+        uv[::5, ::3] |= rng.integers(0, 64, size=uv[::5, ::3].shape).astype(np.uint16)
+        uv[3::53, 2::61] = 65535
+        uv[9::53, 5::61] = 0
+        noisy.append((y, uv))
+    g, o = _run_pair(hr, oracle, noisy[0], noisy[1], h, w, w, 5, pixfmt=1)
+    _assert_flow_equal(g, o)
+    msgs = []
+    tol = 4 * 64
+    for black, white in ((0.0, 255.0), (16.0, 219.0), (10.0, 219.0), (30.0, 255.0)):
+        for mode in (2, 5):
+            gy, guv, oy, ouv = _warp_both(g, o, 0.6, mode, black, white)
+            for nm, a, b in (("Y", gy, oy), ("UV", guv, ouv)):
+                r = _diff_report("P010 levels %g/%g mode %d %s" % (black, white, mode, nm), a, b, tol)
+                if r:
+                    msgs.append(r)
+    lw, lh = g.info.lowWidth, g.info.lowHeight
+    coarse = rng.integers(-512, 393, size=(2, (lh + 14) // 15, (lw + 15) // 16))
+    flow = np.repeat(np.repeat(coarse, 15, axis=1), 16, axis=2)[:, :lh, :lw].astype(np.int16)
+    g.set_blurred_offsets(flow)
+    o.set_blurred_offsets(flow)
+    for mode in (0, 1, 2):
+        gy, guv, oy, ouv = _warp_both(g, o, 0.3, mode, 16.0, 219.0)
+        for nm, a, b in (("Y", gy, oy), ("UV", guv, ouv)):
+            r = _diff_report("P010 large flow mode %d %s" % (mode, nm), a, b, tol)
+            if r:
+                msgs.append(r)
+    assert not msgs, "\n".join(msgs)
