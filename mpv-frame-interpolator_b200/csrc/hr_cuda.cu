@@ -202,7 +202,7 @@ static int create_impl(HrContext *ctx) {
     ctx->tilesY = (ctx->lh + HR_TILE - 1) / HR_TILE;
     ctx->numTiles = ctx->tilesX * ctx->tilesY;
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_kernel<0, true, false>, HR_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flow_search_generic_kernel<true, false>, HR_THREADS, 0));
     if (perSm > 1) perSm = 1; /* one tile per SM: the search is latency-bound, spread it out */
     if (perSm < 1) return fail(ctx, "search kernel does not fit on an SM");
     const int maxResident = perSm * ctx->smCount;
@@ -587,14 +587,14 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
  * (config.h:6-7, vf_HopperRender.c:326-345): those radii get a kernel with the layer loop fully
  * unrolled and the layer shifts as immediates; any other radius runs the generic kernel. */
 static const void *search_kernel_for(int R, int multi, int timeline) {
-    if (multi) return (const void *)flow_search_kernel<0, true, false>;
-    if (timeline) return R == 5 ? (const void *)flow_search_kernel<5, false, true> : (const void *)flow_search_kernel<0, false, true>;
+    if (multi) return (const void *)flow_search_generic_kernel<true, false>;
+    if (timeline) return R == 5 ? (const void *)flow_search_kernel<5, false, true> : (const void *)flow_search_generic_kernel<false, true>;
     switch (R) {
 #define HR_RCASE(r) case r: return (const void *)flow_search_kernel<r, false, false>;
         HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
         HR_RCASE(13) HR_RCASE(14) HR_RCASE(15) HR_RCASE(16)
 #undef HR_RCASE
-        default: return (const void *)flow_search_kernel<0, false, false>;
+        default: return (const void *)flow_search_generic_kernel<false, false>;
     }
 }
 

@@ -38,6 +38,7 @@ struct SearchShared {
     int winner[4];                               /* winning layer of the tile's window(s)           */
     union {
         int4 parked[HR_MAX_TILES_PER_CTA][HR_THREADS]; /* MULTI only: per-thread state of each owned tile */
+        int4 pairState[2][2][HR_THREADS];         /* NP == 2: per-thread state of each of the two frame pairs */
         struct {                                  /* blur phase                                      */
             int16_t tX[40 * 40], tY[40 * 40];     /* tile + 4-point halo of the raw offsets           */
             int hX[40 * 32], hY[40 * 32];         /* horizontal 8-tap sums                            */
@@ -67,11 +68,11 @@ __device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int cur, u
  * is (x0,y0): positions +-2*ws clamped to the lattice, read from the previous level's table (words
  * hold x | y << 16). All points of a window resolve to the same four windows, so one lookup serves
  * the whole window and both axis steps of the level. */
-__device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int ws, int x0, int y0, uint32_t (&nw)[4]) {
+__device__ __forceinline__ void load_neighbours(const FlowParams &P, const PairIO &io, int it, int ws, int x0, int y0, uint32_t (&nw)[4]) {
     const int pws = ws << 1;
     const int lgp = 31 - __clz(pws);
     const int pnwx = (P.lw + pws - 1) >> lgp;
-    const unsigned long long *Tp = P.T + P.tOff[it - 1];
+    const unsigned long long *Tp = io.T + P.tOff[it - 1];
     const int yd = hr_min(y0 + pws, P.lh - 1) >> lgp, yu = hr_max(y0 - pws, 0) >> lgp;
     const int xr = hr_min(x0 + pws, P.lw - 1) >> lgp, xl = hr_max(x0 - pws, 0) >> lgp;
     const int xc = x0 >> lgp, yc = y0 >> lgp;
@@ -105,13 +106,13 @@ __device__ __forceinline__ int layer_shift(const FlowParams &P, int z) {
 /* Executed by one full warp: lane z holds the window's SAD for layer z; returns the winner.
  * nw: the window's four neighbour words (loaded on the first axis step of a level, reused on the second). */
 template <int AXIS>
-__device__ __forceinline__ int finalize_warp(const FlowParams &P, int R, int it, int ws, int lane, uint32_t sad, int x0, int y0, int cur, bool loadNb,
+__device__ __forceinline__ int finalize_warp(const FlowParams &P, const PairIO &io, int R, int it, int ws, int lane, uint32_t sad, int x0, int y0, int cur, bool loadNb,
                                              uint32_t (&nw)[4]) {
     const bool useNb = it >= HR_FIRST_NEIGHBOR_ITERATION;
     const uint32_t count = (uint32_t)(hr_min(x0 + ws, P.lw) - x0) * (uint32_t)(hr_min(y0 + ws, P.lh) - y0);
     int n[4] = {0, 0, 0, 0};
     if (useNb) {
-        if (loadNb) load_neighbours(P, it, ws, x0, y0, nw);
+        if (loadNb) load_neighbours(P, io, it, ws, x0, y0, nw);
         neighbour_axis(nw, AXIS, n);
     }
     const uint32_t S = (lane < R) ? window_total(sad, P.cand[lane < R ? lane : 0], cur, count, useNb, n, P.dS, P.nS) : 0xffffffffu;
@@ -143,10 +144,10 @@ __device__ __forceinline__ void thr_place(const FlowParams &P, Thr &t, int tile,
     t.cy1s = hr_min(t.py + 1, P.lh - 1) << P.s;
 }
 
-__device__ __forceinline__ void trace_store(const FlowParams &P, const Thr &t, int step, int winner) {
-    if (P.trace) {
-        if (t.m0) P.trace[((size_t)step * P.lh + t.py) * P.lw + t.px] = (uint8_t)winner;
-        if (t.m1) P.trace[((size_t)step * P.lh + t.py + 1) * P.lw + t.px] = (uint8_t)winner;
+__device__ __forceinline__ void trace_store(const FlowParams &P, const PairIO &io, const Thr &t, int step, int winner) {
+    if (io.trace) {
+        if (t.m0) io.trace[((size_t)step * P.lh + t.py) * P.lw + t.px] = (uint8_t)winner;
+        if (t.m1) io.trace[((size_t)step * P.lh + t.py + 1) * P.lw + t.px] = (uint8_t)winner;
     }
 }
 
@@ -155,7 +156,7 @@ __device__ __forceinline__ void trace_store(const FlowParams &P, const Thr &t, i
  * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
  * For WS = 64 the step only publishes the tile's totals; big_finish() scores them. */
 template <int RT, int WS, int AXIS>
-__device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp) {
+__device__ __forceinline__ void search_step(const FlowParams &P, const PairIO &io, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp) {
     constexpr bool small = WS <= 8;
     const int R = RT > 0 ? RT : P.R;
     const int s = P.s, m = (1 << s) - 1;
@@ -204,11 +205,11 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
                 }
                 if (AXIS == 0) {
                     const int xi = (pa & m) * mulA + (pa >> s);
-                    va[j] = __ldg(P.p1 + (fa + xi));
-                    vb[j] = __ldg(P.p1 + (fb + xi));
+                    va[j] = __ldg(io.p1 + (fa + xi));
+                    vb[j] = __ldg(io.p1 + (fb + xi));
                 } else {
-                    va[j] = __ldg(P.p1 + (fa + (pa & m) * mulA + (pa >> s) * P.planePitch));
-                    vb[j] = __ldg(P.p1 + (fb + (pb & m) * mulA + (pb >> s) * P.planePitch));
+                    va[j] = __ldg(io.p1 + (fa + (pa & m) * mulA + (pa >> s) * P.planePitch));
+                    vb[j] = __ldg(io.p1 + (fb + (pb & m) * mulA + (pb >> s) * P.planePitch));
                 }
             }
         }
@@ -257,9 +258,9 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
     auto fetch_neighbours = [&]() {
         if (useNb && AXIS == 0) {
             if (small) {
-                if (ownWindow) load_neighbours(P, it, WS, x0, y0, t.nw);
+                if (ownWindow) load_neighbours(P, io, it, WS, x0, y0, t.nw);
             } else if (WS <= HR_TILE) {
-                if (scorer) load_neighbours(P, it, WS, sx0, sy0, t.nw);
+                if (scorer) load_neighbours(P, io, it, WS, sx0, sy0, t.nw);
             }
         }
         if (small && useNb) neighbour_axis(t.nw, AXIS, nb);
@@ -295,7 +296,7 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
                 uint32_t tt = 0;
 #pragma unroll
                 for (int w = 0; w < HR_NWARPS; ++w) tt += sh.warpTot[w][lane];
-                put_tagged(P.partial + P.bigOff[step] + t.tile * HR_RMAX + lane, P.epoch, tt);
+                put_tagged(io.partial + P.bigOff[step] + t.tile * HR_RMAX + lane, P.epoch, tt);
             }
             __syncthreads(); /* warpTot is reused by big_finish */
             return;
@@ -305,13 +306,13 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
                 uint32_t tt = 0;
 #pragma unroll
                 for (int w = 0; w < HR_NWARPS; ++w) tt += sh.warpTot[w][lane];
-                const int wz = finalize_warp<AXIS>(P, R, it, WS, lane, tt, t.tx0, t.ty0, cur, false, t.nw);
+                const int wz = finalize_warp<AXIS>(P, io, R, it, WS, lane, tt, t.tx0, t.ty0, cur, false, t.nw);
                 if (lane == 0) sh.winner[0] = wz;
             }
         } else if (((warp & 1) | ((warp >> 2) & 1)) == 0) { /* window 16: leader warp of each 2x2 warp group */
             const uint32_t tt = sh.warpTot[warp][lane] + sh.warpTot[warp + 1][lane] + sh.warpTot[warp + 4][lane] + sh.warpTot[warp + 5][lane];
             int wz = 0;
-            if (scorer) wz = finalize_warp<AXIS>(P, R, it, WS, lane, tt, sx0, sy0, cur, false, t.nw);
+            if (scorer) wz = finalize_warp<AXIS>(P, io, R, it, WS, lane, tt, sx0, sy0, cur, false, t.nw);
             if (lane == 0) sh.winner[(warp >> 3) * 2 + ((warp >> 1) & 1)] = wz;
         }
         __syncthreads();
@@ -319,25 +320,25 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
     }
     if (AXIS) t.oy += P.cand[winner];
     else t.ox += P.cand[winner];
-    trace_store(P, t, step, winner);
+    trace_store(P, io, t, step, winner);
     /* publish this level's windows (neighbours of the next level / blur) */
     if (AXIS == 1 && t.m0 && (t.px & (WS - 1)) == 0 && (t.py & (WS - 1)) == 0) {
         const int lgw = 31 - __clz(WS), nwx = (P.lw + WS - 1) >> lgw;
-        put_tagged(P.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw), P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
+        put_tagged(io.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw), P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
     }
 }
 
 /* Second half of a step whose windows span several tiles: sum the totals of the window's tiles in a
  * fixed order (warp w takes tiles w, w+16, ... — independent L2 loads, lane = layer) and score. */
 template <int RT, int AXIS>
-__device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp, bool loadNb) {
+__device__ __forceinline__ void big_finish(const FlowParams &P, const PairIO &io, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp, bool loadNb) {
     const int R = RT > 0 ? RT : P.R;
     const int step = it * 2 + AXIS;
     const int lgw = 31 - __clz(ws), nwx = (P.lw + ws - 1) >> lgw;
     const int wx = t.tx0 >> lgw, wy = t.ty0 >> lgw;
     const int lgt = lgw - 5, tpw = 1 << lgt;                     /* tiles per window side */
     const int ax0 = wx << lgt, ay0 = wy << lgt;
-    const unsigned long long *ps = P.partial + P.bigOff[step] + lane;
+    const unsigned long long *ps = io.partial + P.bigOff[step] + lane;
     uint32_t tt = 0;
     for (int i0 = warp; i0 < tpw * tpw; i0 += 4 * HR_NWARPS) {
         /* up to four tile totals per pass: issue the loads together, then re-load the ones whose tag is stale */
@@ -365,16 +366,16 @@ __device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh
         uint32_t sad = 0;
 #pragma unroll
         for (int w = 0; w < HR_NWARPS; ++w) sad += sh.warpTot[w][lane];
-        const int wz = finalize_warp<AXIS>(P, R, it, ws, lane, sad, wx << lgw, wy << lgw, cur, loadNb, t.nw);
+        const int wz = finalize_warp<AXIS>(P, io, R, it, ws, lane, sad, wx << lgw, wy << lgw, cur, loadNb, t.nw);
         if (lane == 0) sh.winner[0] = wz;
     }
     __syncthreads();
     const int winner = sh.winner[0];
     if (AXIS) t.oy += P.cand[winner];
     else t.ox += P.cand[winner];
-    trace_store(P, t, step, winner);
+    trace_store(P, io, t, step, winner);
     if (AXIS == 1 && threadIdx.x == 0 && t.tx0 == (wx << lgw) && t.ty0 == (wy << lgw))
-        put_tagged(P.T + P.tOff[it] + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
+        put_tagged(io.T + P.tOff[it] + wy * nwx + wx, P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
 }
 
 /* HR_SEARCH_MAXNREG: registers per thread the search may use. One CTA of 512 threads per SM either way; a lower
@@ -383,8 +384,15 @@ __device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh
 #define HR_SEARCH_MAXNREG 88 /* measured (tools/diag_pipeline.py): no spills at R = 5, 24 bytes at R = 16, same serial time as 117 */
 #endif
 #define HR_SEARCH_BOUNDS __maxnreg__(HR_SEARCH_MAXNREG)
-template <int RT, bool MULTI, bool DBG>
-__device__ __forceinline__ void flow_search_body(const FlowParams &P) {
+/* NP = 2: the launch searches two independent frame pairs (P.io[0], P.io[1]) on the same tiles, one step of the
+ * one, then the same step of the other. The words a tile waits for — the other tiles' totals of a cross-tile
+ * window, the neighbour windows of the previous level, the blur halo — were published one sub-step earlier by
+ * CTAs that run the same sequence, so the hand-off latency of one pair is covered by the evaluations of the other;
+ * the code of a step runs twice in a row (second time from a warm instruction cache). Per-thread state of the
+ * pair that is not being worked on sits in shared memory. */
+template <int RT, bool MULTI, bool DBG, int NP = 1>
+__global__ void HR_SEARCH_BOUNDS flow_search_kernel(const __grid_constant__ FlowParams P) {
+    static_assert(NP == 1 || (!MULTI && !DBG), "two pairs: single-tile CTAs, no timeline");
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nCtas = gridDim.x;
@@ -404,65 +412,101 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
     t.nw[0] = t.nw[1] = t.nw[2] = t.nw[3] = 0u;
     /* frame2 sample of a lattice point as the packed word Y | U << 8 | V << 16 (calcDeltaSumsKernel.cl:96-98:
      * chroma at row y >> 1, byte column x & ~1 (+1)); P010: the top 8 bits of every sample */
-    auto frame2_word = [&](int x, int y) -> uint32_t {
+    auto frame2_word = [&](const PairIO &io, int x, int y) -> uint32_t {
         const size_t iy = (size_t)y * P.W + x, iuv = (size_t)(y >> 1) * P.W + (x & ~1);
         if (P.bps == 1) {
-            const uint8_t *fy = (const uint8_t *)P.f2y, *fuv = (const uint8_t *)P.f2uv;
+            const uint8_t *fy = (const uint8_t *)io.f2y, *fuv = (const uint8_t *)io.f2uv;
             return (uint32_t)__ldg(fy + iy) | ((uint32_t)__ldg(fuv + iuv) << 8) | ((uint32_t)__ldg(fuv + iuv + 1) << 16);
         }
-        const uint16_t *fy = (const uint16_t *)P.f2y, *fuv = (const uint16_t *)P.f2uv;
+        const uint16_t *fy = (const uint16_t *)io.f2y, *fuv = (const uint16_t *)io.f2uv;
         return ((uint32_t)__ldg(fy + iy) >> 8) | ((uint32_t)__ldg(fuv + iuv) & 0xff00u) | (((uint32_t)__ldg(fuv + iuv + 1) & 0xff00u) << 8);
     };
-    auto load_frame2 = [&]() {
-        t.v2a = frame2_word(t.cxs, t.cy0s) & t.m0;
-        t.v2b = frame2_word(t.cxs, t.cy1s) & t.m1;
+    auto load_frame2 = [&](const PairIO &io) {
+        t.v2a = frame2_word(io, t.cxs, t.cy0s) & t.m0;
+        t.v2b = frame2_word(io, t.cxs, t.cy1s) & t.m1;
     };
-    if (!MULTI) {
+    auto park_pair = [&](int pair) {
+        sh.pairState[pair][0][tid] = make_int4(t.ox, t.oy, (int)t.v2a, (int)t.v2b);
+        sh.pairState[pair][1][tid] = make_int4((int)t.nw[0], (int)t.nw[1], (int)t.nw[2], (int)t.nw[3]);
+    };
+    auto unpark_pair = [&](int pair) {
+        const int4 a = sh.pairState[pair][0][tid], b = sh.pairState[pair][1][tid];
+        t.ox = a.x;
+        t.oy = a.y;
+        t.v2a = (uint32_t)a.z;
+        t.v2b = (uint32_t)a.w;
+        t.nw[0] = (uint32_t)b.x;
+        t.nw[1] = (uint32_t)b.y;
+        t.nw[2] = (uint32_t)b.z;
+        t.nw[3] = (uint32_t)b.w;
+    };
+    if (NP == 2) {
         thr_place(P, t, blockIdx.x, warp, lane);
-        load_frame2();
+#pragma unroll 1
+        for (int pair = 0; pair < 2; ++pair) {
+            load_frame2(P.io[pair]);
+            park_pair(pair);
+        }
+    } else if (!MULTI) {
+        thr_place(P, t, blockIdx.x, warp, lane);
+        load_frame2(P.io[0]);
     } else {
         int slot = 0;
         for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
             thr_place(P, t, tile, warp, lane);
-            load_frame2();
+            load_frame2(P.io[0]);
             sh.parked[slot][tid] = make_int4(0, 0, (int)t.v2a, (int)t.v2b);
         }
     }
-    /* a CTA that owns several tiles (MULTI) parks the per-thread state of each in shared memory */
-    auto for_tiles = [&](auto body) {
-        int slot = 0;
-        for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
-            if (MULTI) {
-                thr_place(P, t, tile, warp, lane);
-                const int4 st = sh.parked[slot][tid];
-                t.ox = st.x;
-                t.oy = st.y;
-                t.v2a = (uint32_t)st.z;
-                t.v2b = (uint32_t)st.w;
-            }
-            body();
-            if (MULTI) {
-                sh.parked[slot][tid] = make_int4(t.ox, t.oy, (int)t.v2a, (int)t.v2b);
+    /* the units of a CTA: its tile (one pair), its tiles (MULTI: several per CTA, state parked in shared memory),
+     * or its tile for each of the two pairs (NP == 2, state parked likewise) */
+    auto for_units = [&](auto body) {
+        if constexpr (NP == 2) {
+#pragma unroll 1
+            for (int pair = 0; pair < 2; ++pair) {
+                unpark_pair(pair);
+                body(P.io[pair]);
+                park_pair(pair);
                 __syncthreads();
+            }
+        } else {
+            int slot = 0;
+            for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
+                if (MULTI) {
+                    thr_place(P, t, tile, warp, lane);
+                    const int4 st = sh.parked[slot][tid];
+                    t.ox = st.x;
+                    t.oy = st.y;
+                    t.v2a = (uint32_t)st.z;
+                    t.v2b = (uint32_t)st.w;
+                }
+                body(P.io[0]);
+                if (MULTI) {
+                    sh.parked[slot][tid] = make_int4(t.ox, t.oy, (int)t.v2a, (int)t.v2b);
+                    __syncthreads();
+                }
             }
         }
     };
     auto level = [&](auto wsTag, int it, int ws) {
         constexpr int WS = decltype(wsTag)::value;
         if constexpr (WS > HR_TILE) {
-            for_tiles([&] { search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp); });
+            for_units([&](const PairIO &io) { search_step<RT, WS, 0>(P, io, sh, t, it, ws, lane, warp); });
             HR_STAMP();
-            for_tiles([&] { big_finish<RT, 0>(P, sh, t, it, ws, lane, warp, true); });
+            for_units([&](const PairIO &io) { big_finish<RT, 0>(P, io, sh, t, it, ws, lane, warp, true); });
             HR_STAMP();
-            for_tiles([&] { search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp); });
+            for_units([&](const PairIO &io) { search_step<RT, WS, 1>(P, io, sh, t, it, ws, lane, warp); });
             HR_STAMP();
-            for_tiles([&] { big_finish<RT, 1>(P, sh, t, it, ws, lane, warp, MULTI); });
+            for_units([&](const PairIO &io) { big_finish<RT, 1>(P, io, sh, t, it, ws, lane, warp, MULTI); });
             HR_STAMP();
+        } else if constexpr (NP == 2) {
+            for_units([&](const PairIO &io) { search_step<RT, WS, 0>(P, io, sh, t, it, ws, lane, warp); });
+            for_units([&](const PairIO &io) { search_step<RT, WS, 1>(P, io, sh, t, it, ws, lane, warp); });
         } else {
-            for_tiles([&] {
-                search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp);
+            for_units([&](const PairIO &io) {
+                search_step<RT, WS, 0>(P, io, sh, t, it, ws, lane, warp);
                 HR_STAMP();
-                search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp);
+                search_step<RT, WS, 1>(P, io, sh, t, it, ws, lane, warp);
                 HR_STAMP();
             });
         }
@@ -479,25 +523,27 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
     HR_STAMP(); /* search done */
 
     /* raw offsets (offsetArray) */
-    for_tiles([&] {
+    for_units([&](const PairIO &io) {
         if (t.m0) {
             const size_t idx = (size_t)t.py * P.lw + t.px;
-            P.off[idx] = (int16_t)t.ox;
-            P.off[ln + idx] = (int16_t)t.oy;
+            io.off[idx] = (int16_t)t.ox;
+            io.off[ln + idx] = (int16_t)t.oy;
         }
         if (t.m1) {
             const size_t idx = (size_t)(t.py + 1) * P.lw + t.px;
-            P.off[idx] = (int16_t)t.ox;
-            P.off[ln + idx] = (int16_t)t.oy;
+            io.off[idx] = (int16_t)t.ox;
+            io.off[ln + idx] = (int16_t)t.oy;
         }
     });
 
     /* ------------- blur the raw offsets (K4), reading the last level's window table --------------- */
-    {
+#pragma unroll 1
+    for (int pair = 0; pair < NP; ++pair) {
+        const PairIO &io = P.io[pair];
         const int lws = P.first >> (P.iters - 1); /* = 2 */
         const int lgl = 31 - __clz(lws);
         const int lnwx = (P.lw + lws - 1) >> lgl;
-        const unsigned long long *Tl = P.T + P.tOff[P.iters - 1];
+        const unsigned long long *Tl = io.T + P.tOff[P.iters - 1];
         int16_t *tX = sh.blur.tX, *tY = sh.blur.tY;
         int *hX = sh.blur.hX, *hY = sh.blur.hY;
         constexpr int NT = HR_THREADS;
@@ -560,9 +606,9 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
                     }
                     const size_t idx = (size_t)y * P.lw + x;
                     const int bx = sx / 64, by = sy / 64; /* C division truncates toward zero */
-                    P.blur[idx] = (int16_t)bx;
-                    P.blur[ln + idx] = (int16_t)by;
-                    P.blurXY[idx] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
+                    io.blur[idx] = (int16_t)bx;
+                    io.blur[ln + idx] = (int16_t)by;
+                    io.blurXY[idx] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
                 }
             }
             __syncthreads();
@@ -575,17 +621,6 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
         P.timeline[blockIdx.x * HR_TIMELINE_SLOTS + HR_TIMELINE_SLOTS - 1] = (long long)gt;
     }
 #undef HR_STAMP
-}
-/* radius known at compile time (5..16, what the filter uses): register cap; the generic instantiations (any
- * radius 2..32, several tiles per CTA) keep all the registers one CTA per SM can have */
-template <int RT, bool MULTI, bool DBG>
-__global__ void HR_SEARCH_BOUNDS flow_search_kernel(const FlowParams P) {
-    static_assert(RT > 0 && !MULTI, "capped instantiation");
-    flow_search_body<RT, MULTI, DBG>(P);
-}
-template <bool MULTI, bool DBG>
-__global__ void __launch_bounds__(HR_THREADS, 1) flow_search_generic_kernel(const FlowParams P) {
-    flow_search_body<0, MULTI, DBG>(P);
 }
 
 /* Stand-alone K4 (parity tap hr_blur_flow): direct 64-tap form of blurFlowKernel.cl:80-88. */
