@@ -384,13 +384,11 @@ def run_ours(args):
     g.set_output_device(None, None)
 
     # ---- end-to-end through the reference-facing interface, host buffers -------------------------
+    # The compiled C host layer (opticalFlowCalc.c, the drop-in for the reference's file of that name) driven by
+    # hrReplay.c, the filter's per-frame call sequence as a C loop: updateFrame (H2D) / calculateOpticalFlow /
+    # warpFrames / downloadFrame (D2H) per output, every call blocking like the reference's.
     e2e = None
     if not args.no_e2e:
-        ofc = hr.OpticalFlowCalc()
-        if hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt, device=local):
-            raise SystemExit("initOpticalFlowCalc failed")
-        ofc.opticalFlowSearchRadius = radius
-        npdt = np.uint16 if pixfmt else np.uint8
         # host frames as mpv's image pool lays them out: one pinned allocation, the UV plane right behind the Y plane
         def host_frame():
             ny, nuv = (r1 - r0) * w, ((r1 >> 1) - (r0 >> 1)) * w
@@ -408,37 +406,51 @@ def run_ours(args):
         Ke = min(K, 100)
         We = min(W_, 5)
         if banded:
+            ofc = hr.OpticalFlowCalc()
+            if hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt, device=local):
+                raise SystemExit("initOpticalFlowCalc failed")
+            ofc.opticalFlowSearchRadius = radius
             hr.connect_bands_distributed(ofc.impl, dist, rows)
 
-        def update_host(ty, tuv):
-            if banded:                                      # a rank moves only its band over PCIe
-                ofc.impl.band_upload(ty, tuv)
+            def step_host(i):                               # a rank moves only its band over PCIe
+                ofc.impl.band_upload(*hring[i % nbase])
                 ofc.impl.band_gather(blocking=True)
-            else:
-                assert not hr.updateFrame(ofc, [ty, tuv])
-
-        def step_host(i):
-            update_host(*hring[i % nbase])
-            assert not hr.calculateOpticalFlow(ofc)
-            for t in ts[i]:
-                assert not hr.warpFrames(ofc, t, mode)
-                if banded:
+                assert not hr.calculateOpticalFlow(ofc)
+                for t in ts[i]:
+                    assert not hr.warpFrames(ofc, t, mode)
                     ofc.impl.band_download(hout[0], hout[1])
-                else:
-                    assert not hr.downloadFrame(ofc, [hout[0], hout[1]])
-            return len(ts[i])
+                return len(ts[i])
 
-        update_host(*hring[nbase - 1])
-        for i in range(We):
-            step_host(i)
-        barrier()
-        t0 = time.perf_counter()
-        eouts = sum(step_host(We + i) for i in range(Ke))
-        torch.cuda.synchronize()
-        edt = time.perf_counter() - t0
+            step_host(nbase - 1)
+            for i in range(We):
+                step_host(i)
+            barrier()
+            t0 = time.perf_counter()
+            eouts = sum(step_host(We + i) for i in range(Ke))
+            torch.cuda.synchronize()
+            edt = time.perf_counter() - t0
+            hr.freeOFC(ofc)
+            e2e_api = "band_upload/band_gather/calculateOpticalFlow/warpFrames/band_download per rank, pinned host planes"
+        else:
+            import ctypes
+
+            lib = hr.load_ofc_library()
+            cofc = hr.COpticalFlowCalc()
+            cofc.pixelFormat = pixfmt
+            cofc.cudaDevice = local + 1
+            if lib.initOpticalFlowCalc(ctypes.byref(cofc), h, w, w):
+                raise SystemExit("initOpticalFlowCalc (C host layer) failed")
+            cofc.opticalFlowSearchRadius = radius
+            hr.replay_stream_c(cofc, hring, nbase - 1, [[]], mode, hout)           # the first frame of the stream
+            hr.replay_stream_c(cofc, hring, 0, ts[:We], mode, hout)
+            barrier()
+            t0 = time.perf_counter()
+            eouts = hr.replay_stream_c(cofc, hring, We, ts[We:We + Ke], mode, hout)
+            edt = time.perf_counter() - t0
+            lib.freeOFC(ctypes.byref(cofc))
+            e2e_api = ("libhopperrender_ofc.so: initOpticalFlowCalc, then hrReplayStream = updateFrame/calculateOpticalFlow/warpFrames/downloadFrame "
+                       "in the filter's order, pinned host planes, every call blocking like the reference's")
         e2e = (eouts, edt, Ke)
-        hr.freeOFC(ofc)
-        del npdt
 
     # ---- reduce over ranks (sharding.py: the N > 1 host logic, covered on CPU by tests/test_sharding_cpu.py) ----
     from hopperrender_b200 import sharding
@@ -499,7 +511,7 @@ def run_ours(args):
             band_frac = (r1 - r0) / h
             line["e2e"] = {"value": e_outs / e_dt, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes * band_frac),
                            "d2h_bytes_per_step": int(frame_bytes * band_frac * (e2e[0] / e2e[2])), "steps": e2e[2],
-                           "api": "initOpticalFlowCalc/updateFrame/calculateOpticalFlow/warpFrames/downloadFrame, pinned host planes, blocking like the reference",
+                           "api": e2e_api,
                            "host_cpus_near_gpu": numa_cpus}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -470,3 +470,68 @@ def warpFrames(ofc: OpticalFlowCalc, blendingScalar: float, frameOutputMode: int
     if not ofc.isInitialized:
         return True
     return bool(ofc.impl.lib.hr_warp(ofc.impl.h, float(blendingScalar), int(frameOutputMode), float(ofc.outputBlackLevel), float(ofc.outputWhiteLevel)))
+
+
+# ---- the C host layer itself (mpv/video/filter/HopperRender/opticalFlowCalc.{h,c} + hrReplay.c), for callers that
+# ---- want the compiled drop-in rather than this module's mirror of it (bench.py's end-to-end leg)
+class COpticalFlowCalc(C.Structure):
+    """`struct OpticalFlowCalc` as laid out by mpv/video/filter/HopperRender/opticalFlowCalc.h."""
+    _fields_ = [
+        ("isInitialized", C.c_bool), ("frameWidth", C.c_int), ("frameHeight", C.c_int), ("actualWidth", C.c_int),
+        ("outputBlackLevel", C.c_float), ("outputWhiteLevel", C.c_float),
+        ("opticalFlowResScalar", C.c_int), ("opticalFlowFrameWidth", C.c_int), ("opticalFlowFrameHeight", C.c_int),
+        ("opticalFlowSearchRadius", C.c_int), ("ofcCalcTime", C.c_double), ("warpCalcTime", C.c_double),
+        ("deltaScalar", C.c_int), ("neighborBiasScalar", C.c_int),
+        ("pixelFormat", C.c_int), ("cudaDevice", C.c_int), ("impl", C.c_void_p),
+    ]
+
+
+_ofc_lib = None
+
+
+def load_ofc_library():
+    """dlopen libhopperrender_ofc.so (the C host layer, linked against the CUDA library)."""
+    global _ofc_lib
+    if _ofc_lib is not None:
+        return _ofc_lib
+    load_library()
+    path = _build.OFC_LIB
+    if not path.exists():
+        _build.build_host()
+    lib = C.CDLL(str(path))
+    P = C.POINTER(COpticalFlowCalc)
+    PP = C.POINTER(C.c_void_p)
+    for name, res, args in (
+        ("initOpticalFlowCalc", C.c_bool, [P, C.c_int, C.c_int, C.c_int]),
+        ("freeOFC", None, [P]),
+        ("updateFrame", C.c_bool, [P, PP]),
+        ("downloadFrame", C.c_bool, [P, PP]),
+        ("calculateOpticalFlow", C.c_bool, [P]),
+        ("warpFrames", C.c_bool, [P, C.c_float, C.c_int]),
+        ("hrReplayStream", C.c_longlong, [P, PP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, PP]),
+    ):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _ofc_lib = lib
+    return lib
+
+
+def replay_stream_c(ofc, frames, first_frame, ts_per_step, mode, out_planes):
+    """hrReplayStream: the filter's call sequence for len(ts_per_step) source frames as one C loop.
+    frames: list of (y, uv) host planes used round-robin; out_planes: (y, uv). Returns outputs delivered."""
+    lib = load_ofc_library()
+    n = len(frames)
+    planes = (C.c_void_p * (2 * n))(*[_ptr(p).value for f in frames for p in f])
+    flat = [float(t) for step in ts_per_step for t in step]
+    ts = (C.c_float * max(1, len(flat)))(*flat)
+    starts, acc = [0], 0
+    for step in ts_per_step:
+        acc += len(step)
+        starts.append(acc)
+    st = (C.c_int * len(starts))(*starts)
+    outs = (C.c_void_p * 2)(_ptr(out_planes[0]).value, _ptr(out_planes[1]).value)
+    got = lib.hrReplayStream(C.byref(ofc), planes, n, first_frame, len(ts_per_step), ts, st, int(mode), outs)
+    if got < 0:
+        raise HrError("hrReplayStream: a call of the optical-flow-calc interface failed")
+    return int(got)

@@ -87,3 +87,40 @@ def test_download_into_pinned_planes_equals_staged_copy(hr, synth, pixfmt):
             assert not hr.downloadFrame(ofc, [ny2, nuv2])
             assert np.array_equal(ny2, ny) and np.array_equal(nuv2, nuv)
     hr.freeOFC(ofc)
+
+
+def test_c_host_layer_replay_equals_call_by_call(hr, synth):
+    """libhopperrender_ofc.so (the compiled drop-in for the reference's opticalFlowCalc.c) driven by hrReplay.c
+    delivers the same frames as the six calls made one by one."""
+    import ctypes
+    import torch
+
+    w, h = 1920, 1080
+    clip = synth.MovingTextureClip(w, h)
+    frames = [clip.frame(k) for k in range(4)]
+    ts = [[0.0, 0.4, 0.8], [0.2, 0.6], [0.0, 0.4, 0.8]]
+    ofc = hr.OpticalFlowCalc()
+    assert not hr.initOpticalFlowCalc(ofc, h, w, w)
+    assert not hr.updateFrame(ofc, list(frames[0]))
+    want = None
+    for k in range(3):
+        assert not hr.updateFrame(ofc, list(frames[k + 1]))
+        assert not hr.calculateOpticalFlow(ofc)
+        for t in ts[k]:
+            y, uv = np.zeros((h, w), np.uint8), np.zeros((h // 2, w), np.uint8)
+            assert not hr.warpFrames(ofc, t, 2)
+            assert not hr.downloadFrame(ofc, [y, uv])
+            want = (y, uv)
+    hr.freeOFC(ofc)
+
+    lib = hr.load_ofc_library()
+    c = hr.COpticalFlowCalc()
+    assert not lib.initOpticalFlowCalc(ctypes.byref(c), h, w, w)
+    assert c.isInitialized and c.opticalFlowResScalar == 2 and c.opticalFlowFrameWidth == 480
+    oy, ouv = torch.zeros((h, w), dtype=torch.uint8).pin_memory(), torch.zeros((h // 2, w), dtype=torch.uint8).pin_memory()
+    assert hr.replay_stream_c(c, frames, 0, [[]], 2, (oy, ouv)) == 0
+    assert hr.replay_stream_c(c, frames, 1, ts, 2, (oy, ouv)) == 8
+    assert c.ofcCalcTime > 0.0 and c.warpCalcTime > 0.0
+    assert np.array_equal(oy.numpy(), want[0]) and np.array_equal(ouv.numpy(), want[1])
+    lib.freeOFC(ctypes.byref(c))
+    assert not c.isInitialized
