@@ -50,12 +50,12 @@ NCU_TRAFFIC = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-nv12-24to60", choices=sorted(WORKLOADS))
     ap.add_argument("--radius", type=int, default=5, help="search radius (config.h MIN_SEARCH_RADIUS = 5 is the default)")
-    ap.add_argument("--cpu-sample-steps", type=int, default=60)
+    ap.add_argument("--cpu-sample-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="device-resident loop without the pipelined mode (one kernel after the other)")
@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -271,6 +271,7 @@ def run_ours(args):
     stream.synchronize()
     K, W_ = args.steps, max(3, args.warmup)
     ts = pacing_ts(W_ + K, sfps, dfps)
+    interp_share = sum(1 for i in range(W_, W_ + K) for t in ts[i] if t > 1e-6) / max(1, sum(len(ts[i]) for i in range(W_, W_ + K)))
     radius = args.radius
 
     oi = [0]
@@ -497,7 +498,9 @@ def run_ours(args):
             "config": {"workload": args.workload, "frame": "%dx%d" % (w, h), "search_radius": radius, "mode": mode,
                        "streams_per_gpu": 1, "partition": ("%d spatial bands, NVLink P2P gather" % world) if banded else ("independent streams" if world > 1 else "none"),
                        "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (nring, nring * frame_bytes >> 20),
-                       "flow_ms_per_pair": avg["search"], "interp_only_frames_per_s": None,
+                       "flow_ms_per_pair": avg["search"],
+                       # every delivered frame is a warp output (vf_HopperRender.c:357-375); the ones with t != 0 alone:
+                       "interp_only_frames_per_s": tot_outs / (max_ms * 1e-3) * interp_share,
                        "device_loop": ("pipelined: pack || search, warps on parallel streams, search(k+1) || warps(k)" if pipelined else "serial"),
                        "serial_frames_per_s": (1e3 / serial_ms if serial_ms else None)},
             "gpu_launches": int(launches),
