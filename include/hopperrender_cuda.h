@@ -84,7 +84,8 @@ int hr_synchronize(HrContext *ctx);
  * internal streams: the packed copy of frame k is built while the search of pair k runs, the warps of one pair
  * run side by side, the search of pair k+1 runs beside the warps of pair k (two flow buffers). Results are
  * bit-identical to the serial mode. Outputs in caller-owned planes are complete after hr_synchronize, or — for
- * work that the caller enqueues on the context's stream — after hr_pipeline_join. Calls that block or touch
+ * work that the caller enqueues on the context's stream — after hr_pipeline_join; the same two calls are what
+ * orders a caller's re-use of borrowed input planes after the warps that still read them. Calls that block or touch
  * host memory (hr_update_frame, hr_download, the taps) behave as before. Ignored while bands are configured. */
 int hr_set_pipeline(HrContext *ctx, int enable);
 int hr_pipeline_join(HrContext *ctx);
