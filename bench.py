@@ -303,6 +303,23 @@ def run_ours(args):
         g.step_device(y, uv, ts[i], outs, radius=radius, mode=mode)
         return n
 
+    CHUNK = 25
+
+    def steps_device(i0, count):
+        """`count` source frames from step i0, enqueued CHUNK frames per C call (hr_steps_device)."""
+        if banded:
+            return sum(step_device(i0 + j) for j in range(count))
+        total = 0
+        for c0 in range(i0, i0 + count, CHUNK):
+            c1 = min(c0 + CHUNK, i0 + count)
+            tl = ts[c0:c1]
+            n = sum(len(t) for t in tl)
+            outs = [out_ring[(oi[0] + j) % len(out_ring)] for j in range(n)]
+            oi[0] += n
+            g.steps_device([ring[j % nring] for j in range(c0, c1)], tl, outs, radius=radius, mode=mode)
+            total += n
+        return total
+
     def barrier():
         stream.synchronize()
         torch.cuda.synchronize()
@@ -314,8 +331,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         feed(nring - 1)
         g.set_pipeline(pipelined)
-        for i in range(W_):
-            step_device(i)
+        steps_device(0, W_)
         g.synchronize()
         barrier()
         sampler = ClockSampler(local)
@@ -324,9 +340,7 @@ def run_ours(args):
         l0 = g.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        outs = 0
-        for i in range(K):
-            outs += step_device(W_ + i)
+        outs = steps_device(W_, K)
         g.pipeline_join()              # the main stream now follows every internal stream: e1 closes the whole region
         e1.record(stream)
         g.synchronize()
@@ -337,13 +351,12 @@ def run_ours(args):
         g.set_pipeline(False)
         serial_ms = None
         if pipelined:                  # the same steps, one kernel after the other (what the blocking interface sees)
-            for i in range(W_):
-                step_device(i)
+            steps_device(0, W_)
             g.synchronize()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record(stream)
             ks = min(K, 100)
-            so = sum(step_device(W_ + i) for i in range(ks))
+            so = steps_device(W_, ks)
             s1.record(stream)
             g.synchronize()
             serial_ms = s0.elapsed_time(s1) / max(1, so)
@@ -501,7 +514,7 @@ def run_ours(args):
                        "flow_ms_per_pair": avg["search"],
                        # every delivered frame is a warp output (vf_HopperRender.c:357-375); the ones with t != 0 alone:
                        "interp_only_frames_per_s": tot_outs / (max_ms * 1e-3) * interp_share,
-                       "device_loop": ("pipelined: pack || search, warps on parallel streams, search(k+1) || warps(k)" if pipelined else "serial"),
+                       "device_loop": ("pipelined: pack || search, two search lanes, warps on parallel streams, search(k+1) || warps(k); %d source frames per C call" % CHUNK if pipelined else "serial"),
                        "serial_frames_per_s": (1e3 / serial_ms if serial_ms else None)},
             "gpu_launches": int(launches),
             "clocks": clocks,

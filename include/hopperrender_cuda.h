@@ -96,6 +96,12 @@ int hr_step_device(HrContext *ctx, const void *dYPlane, const void *dUvPlane, in
                    int neighborBiasScalar, int nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel,
                    float whiteLevel, void *const *outY, void *const *outUV);
 
+/* nSteps consecutive source frames in one call: hr_step_device for dY[i], dUV[i] with nWarps[i] warps each, their
+ * blending scalars and output planes taken in order from the flat arrays. Enqueue-only. */
+int hr_steps_device(HrContext *ctx, int nSteps, const void *const *dYPlanes, const void *const *dUvPlanes, int borrow, int searchRadius,
+                    int deltaScalar, int neighborBiasScalar, const int *nWarps, const float *blendingScalars, int frameOutputMode,
+                    float blackLevel, float whiteLevel, void *const *outY, void *const *outUV);
+
 /* ---- updateFrame, HR/opticalFlowCalc.c:96-107: blocking upload of the Y plane
  * (frameHeight*stride samples) and the interleaved UV plane (frameHeight/2*stride samples) from
  * HOST memory into the older frame slot, then swap, so that slot 1 is the newest frame. Also

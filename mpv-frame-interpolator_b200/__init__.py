@@ -55,6 +55,8 @@ ABI = {
     "hr_pipeline_join": (C.c_int, [C.c_void_p]),
     "hr_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                                  C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "hr_steps_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_calc_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "hr_warp": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]),
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
@@ -195,6 +197,21 @@ class HrCuda:
         ouv = (C.c_void_p * max(n, 1))(*[_ptr(o[1]) for o in outs[:n]])
         self._chk(self.lib.hr_step_device(self.h, _ptr(dy), _ptr(duv), 1 if borrow else 0, radius, deltaScalar, neighborBiasScalar, n, tarr,
                                           int(mode), float(black), float(white), oy, ouv))
+
+    def steps_device(self, frames, ts_per_step, outs, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6, mode=BlendedFrame,
+                     black=0.0, white=255.0, borrow=True):
+        """len(frames) consecutive source frames (dY, dUV) in one call; outs: one (dY, dUV) per warp, in order."""
+        n = len(frames)
+        fy = (C.c_void_p * max(n, 1))(*[_ptr(f[0]).value for f in frames])
+        fuv = (C.c_void_p * max(n, 1))(*[_ptr(f[1]).value for f in frames])
+        nw = (C.c_int * max(n, 1))(*[len(t) for t in ts_per_step])
+        flat = [float(t) for step in ts_per_step for t in step]
+        m = len(flat)
+        tarr = (C.c_float * max(m, 1))(*flat)
+        oy = (C.c_void_p * max(m, 1))(*[_ptr(o[0]).value for o in outs[:m]])
+        ouv = (C.c_void_p * max(m, 1))(*[_ptr(o[1]).value for o in outs[:m]])
+        self._chk(self.lib.hr_steps_device(self.h, n, fy, fuv, 1 if borrow else 0, radius, deltaScalar, neighborBiasScalar, nw, tarr, int(mode),
+                                           float(black), float(white), oy, ouv))
 
     def calc_flow(self, radius=MIN_SEARCH_RADIUS, deltaScalar=8, neighborBiasScalar=6, blocking=True):
         sec = C.c_double(0.0)

@@ -22,6 +22,8 @@
 
 #define MAX_CALC_RES 270 /* video/filter/HopperRender/config.h:2 */
 #define HR_WARP_STREAMS 3
+#define HR_FLOW_BUFS 4   /* blurred-flow ring: one being written per search lane, the rest read by warps in flight */
+#define HR_SEARCH_LANES 2
 #define HR_MAX_WARP_EVENTS 8
 
 struct HrContext {
@@ -69,15 +71,22 @@ struct HrContext {
      * pack(k) || search(k) (the search reads frame 2 as it arrived), the warps of one pair on HR_WARP_STREAMS
      * streams, search(k+1) || warps(k) (two flow buffers). Dependencies are CUDA events, never host waits. */
     int pipeline;
-    cudaStream_t sPack, sSearch, sWarp[HR_WARP_STREAMS];
+    cudaStream_t sPack, sSearch[HR_SEARCH_LANES], sWarp[HR_WARP_STREAMS];
     cudaEvent_t evIn;                          /* main stream: the newest frame's planes are complete          */
     cudaEvent_t evPack[2];                     /* by packed-buffer identity: its pack kernel is done           */
-    cudaEvent_t evSearch[2];                   /* by flow buffer: the search that filled it is done            */
-    cudaEvent_t evWarp[2][HR_MAX_WARP_EVENTS]; /* by flow buffer: the warps reading it                         */
-    int nWarpEv[2], haveSearch[2], havePack[2], packedId[2];
+    cudaEvent_t packRead[2];                   /* by packed-buffer identity: the search that read it last (not owned) */
+    cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
+    cudaEvent_t evWarp[HR_FLOW_BUFS][HR_MAX_WARP_EVENTS]; /* by flow buffer: the warps reading it              */
+    int nWarpEv[HR_FLOW_BUFS], haveSearch[HR_FLOW_BUFS], havePack[2], packedId[2];
     int flowCur;                               /* flow buffer of the most recent search                        */
-    int16_t *blurB[2];
-    uint32_t *blurXYB[2];
+    int16_t *blurB[HR_FLOW_BUFS];
+    uint32_t *blurXYB[HR_FLOW_BUFS];
+    /* two search lanes: consecutive pairs are independent (the offsets start from zero for every pair,
+     * opticalFlowCalc.c:153), so the search of pair k+1 is launched on the other lane — its own stream, window
+     * tables, tile totals and raw-offset array — and fills the launch gaps and hand-off waits of the search of pair k */
+    int lane;                                  /* lane of the most recent search                               */
+    int16_t *offL[HR_SEARCH_LANES];
+    unsigned long long *TL[HR_SEARCH_LANES], *partialL[HR_SEARCH_LANES];
     unsigned warpRR;
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
@@ -145,20 +154,33 @@ extern "C" int hr_destroy(HrContext *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
     if (ctx->sPack) cudaStreamDestroy(ctx->sPack);
-    if (ctx->sSearch) cudaStreamDestroy(ctx->sSearch);
+    for (int i = 0; i < HR_SEARCH_LANES; ++i)
+        if (ctx->sSearch[i]) cudaStreamDestroy(ctx->sSearch[i]);
     for (int i = 0; i < HR_WARP_STREAMS; ++i)
         if (ctx->sWarp[i]) cudaStreamDestroy(ctx->sWarp[i]);
     if (ctx->evIn) cudaEventDestroy(ctx->evIn);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 2; ++b)
         if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
+    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
         if (ctx->evSearch[b]) cudaEventDestroy(ctx->evSearch[b]);
         for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i)
             if (ctx->evWarp[b][i]) cudaEventDestroy(ctx->evWarp[b][i]);
     }
-    cudaFree(ctx->blurB[1]); /* ctx->blur / blurXY alias one of the two flow buffers: [0] is freed below through them */
-    cudaFree(ctx->blurXYB[1]);
+    /* ctx->blur / blurXY / off / T / partial alias entry [x] of their rings; entry [0] is freed below through them */
+    for (int b = 1; b < HR_FLOW_BUFS; ++b) {
+        cudaFree(ctx->blurB[b]);
+        cudaFree(ctx->blurXYB[b]);
+    }
+    for (int l = 1; l < HR_SEARCH_LANES; ++l) {
+        cudaFree(ctx->offL[l]);
+        cudaFree(ctx->TL[l]);
+        cudaFree(ctx->partialL[l]);
+    }
     ctx->blur = ctx->blurB[0];
     ctx->blurXY = ctx->blurXYB[0];
+    ctx->off = ctx->offL[0];
+    ctx->T = ctx->TL[0];
+    ctx->partial = ctx->partialL[0];
     cudaFree(ctx->frameBuf[0]);
     cudaFree(ctx->frameBuf[1]);
     cudaFree(ctx->packed[0]);
@@ -267,6 +289,9 @@ static int create_impl(HrContext *ctx) {
     ctx->epoch = 0;
     ctx->blurB[0] = ctx->blur;
     ctx->blurXYB[0] = ctx->blurXY;
+    ctx->offL[0] = ctx->off;
+    ctx->TL[0] = ctx->T;
+    ctx->partialL[0] = ctx->partial;
     ctx->packedId[0] = 0;
     ctx->packedId[1] = 1;
     ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 8 + 516;
@@ -435,11 +460,11 @@ static int launch_pack(HrContext *ctx) {
     const int id = ctx->packedId[1];
     if (pipe_on(ctx)) {
         /* on its own stream, next to the search of the same pair (which does not read this copy): after the
-         * frame has arrived and after the previous search, the last reader of the buffer being overwritten */
+         * frame has arrived and after the search that read the buffer being overwritten */
         st = ctx->sPack;
         CU(cudaEventRecord(ctx->evIn, ctx->stream));
         CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
-        if (ctx->haveSearch[ctx->flowCur]) CU(cudaStreamWaitEvent(st, ctx->evSearch[ctx->flowCur], 0));
+        if (ctx->packRead[id]) CU(cudaStreamWaitEvent(st, ctx->packRead[id], 0));
     }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[4], st));
     if (ctx->bps == 1) launch_pack_t<uint8_t>(ctx, st);
@@ -484,8 +509,9 @@ static int wait_warps(HrContext *ctx, cudaStream_t st, int b) {
 /* order the main stream after everything in flight on the internal streams (no host wait) */
 static int pipe_join(HrContext *ctx) {
     if (!ctx->sPack) return 0;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 2; ++b)
         if (ctx->havePack[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evPack[b], 0));
+    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
         if (ctx->haveSearch[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evSearch[b], 0));
         if (wait_warps(ctx, ctx->stream, b)) return 1;
     }
@@ -505,21 +531,42 @@ extern "C" int hr_set_pipeline(HrContext *ctx, int enable) {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         /* the search is the critical path of a pair: its CTAs are placed first */
-        CU(cudaStreamCreateWithPriority(&ctx->sSearch, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < HR_SEARCH_LANES; ++i) CU(cudaStreamCreateWithPriority(&ctx->sSearch[i], cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
         for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
         CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
-        for (int b = 0; b < 2; ++b) {
-            CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
+        for (int b = 0; b < HR_FLOW_BUFS; ++b) {
             CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
             for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) CU(cudaEventCreateWithFlags(&ctx->evWarp[b][i], cudaEventDisableTiming));
         }
         const size_t ln = (size_t)ctx->lw * ctx->lh;
-        CU(cudaMalloc(&ctx->blurB[1], 2 * ln * sizeof(int16_t)));
-        CU(cudaMalloc(&ctx->blurXYB[1], ln * sizeof(uint32_t)));
-        CU(cudaMemset(ctx->blurB[1], 0, 2 * ln * sizeof(int16_t)));
-        CU(cudaMemset(ctx->blurXYB[1], 0, ln * sizeof(uint32_t)));
-        ctx->deviceBytes += 2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t);
+        /* the flow buffer in use becomes entry 0 of the ring, the search scratch in use lane 0 */
+        ctx->blurB[0] = ctx->blur;
+        ctx->blurXYB[0] = ctx->blurXY;
+        ctx->flowCur = 0;
+        for (int b = 1; b < HR_FLOW_BUFS; ++b) {
+            CU(cudaMalloc(&ctx->blurB[b], 2 * ln * sizeof(int16_t)));
+            CU(cudaMalloc(&ctx->blurXYB[b], ln * sizeof(uint32_t)));
+            CU(cudaMemset(ctx->blurB[b], 0, 2 * ln * sizeof(int16_t)));
+            CU(cudaMemset(ctx->blurXYB[b], 0, ln * sizeof(uint32_t)));
+        }
+        const size_t tw = (size_t)(ctx->tWords ? ctx->tWords : 32) * sizeof(unsigned long long);
+        const size_t bw = (size_t)(ctx->bigWords ? ctx->bigWords : 32) * sizeof(unsigned long long);
+        ctx->offL[0] = ctx->off;
+        ctx->TL[0] = ctx->T;
+        ctx->partialL[0] = ctx->partial;
+        ctx->lane = 0;
+        for (int l = 1; l < HR_SEARCH_LANES; ++l) {
+            CU(cudaMalloc(&ctx->offL[l], 2 * ln * sizeof(int16_t)));
+            CU(cudaMalloc(&ctx->TL[l], tw));
+            CU(cudaMalloc(&ctx->partialL[l], bw));
+            CU(cudaMemset(ctx->offL[l], 0, 2 * ln * sizeof(int16_t)));
+            CU(cudaMemset(ctx->TL[l], 0, tw));
+            CU(cudaMemset(ctx->partialL[l], 0, bw));
+        }
+        ctx->deviceBytes += (HR_FLOW_BUFS - 1) * (2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t)) + (HR_SEARCH_LANES - 1) * (2 * ln * sizeof(int16_t) + tw + bw);
+        CU(cudaDeviceSynchronize());
     }
     ctx->pipeline = enable ? 1 : 0;
     return 0;
@@ -630,17 +677,19 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     P.tilesX = ctx->tilesX;
     P.tilesY = ctx->tilesY;
     P.numTiles = ctx->numTiles;
-    P.T = ctx->T;
     memcpy(P.tOff, ctx->tOff, sizeof(P.tOff));
-    P.partial = ctx->partial;
     memcpy(P.bigOff, ctx->bigOff, sizeof(P.bigOff));
     if (++ctx->epoch == 0) ctx->epoch = 1; /* 0 is the tag of never-written words */
     P.epoch = ctx->epoch;
     /* pipelined: into the flow buffer the warps of the previous pair are not reading */
     const int pl = pipe_on(ctx);
-    const int fb = pl ? (ctx->flowCur ^ 1) : ctx->flowCur;
-    cudaStream_t st = pl ? ctx->sSearch : ctx->stream;
-    P.off = ctx->off;
+    const int fb = pl ? (ctx->flowCur + 1) % HR_FLOW_BUFS : ctx->flowCur;
+    /* the other search lane — unless a tap wants to look at this launch's tables afterwards */
+    const int lane = (pl && !ctx->traceOn && !ctx->timelineOn) ? (ctx->lane + 1) % HR_SEARCH_LANES : ctx->lane;
+    cudaStream_t st = pl ? ctx->sSearch[lane] : ctx->stream;
+    P.T = ctx->TL[lane];
+    P.partial = ctx->partialL[lane];
+    P.off = ctx->offL[lane];
     P.blur = ctx->blurB[fb];
     P.blurXY = ctx->blurXYB[fb];
     P.trace = ctx->traceOn ? ctx->trace : NULL;
@@ -653,6 +702,8 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
         if (ctx->havePack[ctx->packedId[0]]) CU(cudaStreamWaitEvent(st, ctx->evPack[ctx->packedId[0]], 0));
         if (wait_warps(ctx, st, fb)) return 1;
         ctx->nWarpEv[fb] = 0;
+        /* the flow buffer was last written by a search four pairs back: on this lane (stream order) or on the
+         * other one, whose event the warps above waited for already */
     } else if (ctx->sPack) {
         /* the pipeline was used earlier: order this launch after what is left of it */
         if (pipe_join(ctx)) return 1;
@@ -668,9 +719,14 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
     ctx->flowCur = fb;
     ctx->blur = ctx->blurB[fb];
     ctx->blurXY = ctx->blurXYB[fb];
+    ctx->lane = lane;
+    ctx->off = ctx->offL[lane];
+    ctx->T = ctx->TL[lane];
+    ctx->partial = ctx->partialL[lane];
     if (ctx->sPack) {
         CU(cudaEventRecord(ctx->evSearch[fb], st));
         ctx->haveSearch[fb] = 1;
+        ctx->packRead[ctx->packedId[0]] = ctx->evSearch[fb];
     }
     if (!pl || seconds) CU(cudaEventRecord(ctx->evFlowEnd, st));
     if (seconds) {
@@ -857,6 +913,23 @@ extern "C" int hr_step_device(HrContext *ctx, const void *dY, const void *dUV, i
     ctx->outY = keepY;
     ctx->outUV = keepUV;
     return rc;
+}
+
+/* nSteps consecutive source frames in one call (hr_step_device in a loop): warps of step i use
+ * blendingScalars[first .. first + nWarps[i]) and the output planes at the same indices, first = sum of nWarps[0..i). */
+extern "C" int hr_steps_device(HrContext *ctx, int nSteps, const void *const *dY, const void *const *dUV, int borrow, int searchRadius, int deltaScalar,
+                               int neighborBiasScalar, const int *nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel,
+                               float whiteLevel, void *const *outY, void *const *outUV) {
+    if (!ctx) return 1;
+    if (nSteps < 0 || (nSteps > 0 && (!dY || !dUV || !nWarps))) return fail(ctx, "hr_steps_device: bad frame list");
+    int first = 0;
+    for (int i = 0; i < nSteps; ++i) {
+        if (hr_step_device(ctx, dY[i], dUV[i], borrow, searchRadius, deltaScalar, neighborBiasScalar, nWarps[i], blendingScalars ? blendingScalars + first : NULL,
+                           frameOutputMode, blackLevel, whiteLevel, outY ? outY + first : NULL, outUV ? outUV + first : NULL))
+            return 1;
+        first += nWarps[i];
+    }
+    return 0;
 }
 
 extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds) {

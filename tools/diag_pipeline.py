@@ -22,27 +22,37 @@ nout = max(8, (126 * 2**20) // fb + 2)
 outs = [(torch.empty((h, w), dtype=tdt, device="cuda"), torch.empty((h // 2, w), dtype=tdt, device="cuda")) for _ in range(nout)]
 p = pacing.Pacer(24.0, 60.0)
 p.next_source_frame()
-ts = [p.next_source_frame() for _ in range(steps + 40)]
+ts = [p.next_source_frame() for _ in range(steps + 80)]
 stream = torch.cuda.Stream()
-for pipe in (0, 1):
+for pipe in (0, 1, 2):          # 2: pipelined, 25 source frames per call (hr_steps_device)
     g = hr.HrCuda(h, w, w, pf)
     g.set_stream(stream.cuda_stream)
     g.set_pipeline(bool(pipe))
+    g.step_device(*ring[nring - 1], [], [])
     oi = 0
     def step(i):
         global oi
+        if pipe == 2:
+            if i % 25:
+                return 0
+            tl = ts[i:i + 25]
+            n = sum(len(t) for t in tl)
+            o = [outs[(oi + j) % nout] for j in range(n)]
+            oi += n
+            g.steps_device([ring[(i + j) % nring] for j in range(25)], tl, o, radius=radius)
+            return n
         o = [outs[(oi + j) % nout] for j in range(len(ts[i]))]
         oi += len(ts[i])
         g.step_device(*ring[i % nring], ts[i], o, radius=radius)
         return len(ts[i])
     with torch.cuda.stream(stream):
-        for i in range(20):
+        for i in range(25):
             step(i)
         g.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        n = sum(step(20 + i) for i in range(steps))
+        n = sum(step(25 + i) for i in range(steps))
         t1 = time.perf_counter()
         g.pipeline_join()
         e1.record(stream)
