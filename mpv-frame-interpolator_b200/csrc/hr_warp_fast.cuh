@@ -279,7 +279,12 @@ __device__ __forceinline__ void warp_fast_thread(const WarpParams<T> &P, const W
 
 /* grid: x = 128-sample column blocks, y = groups of 4 row groups; row groups of the luma plane first */
 template <typename T, int ROWS>
-__global__ void __launch_bounds__(128) warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A) {
+/* ten 128-thread CTAs per SM (<= 51 registers): the kernel is latency-bound at 4K and above, more resident warps pay
+ * (tools/diag_launch.py: 8K P010 80.4 -> 73.8 us, 4K P010 stream 80.9 -> 76.4 us per source frame; 12 gains nothing more) */
+#ifndef HR_WARP_MINBLOCKS
+#define HR_WARP_MINBLOCKS 10
+#endif
+__global__ void __launch_bounds__(128, HR_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A) {
     const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int rg = blockIdx.y * 4 + threadIdx.y;
     if (cx0 >= P.aW) return;
