@@ -42,8 +42,8 @@ WORKLOADS = {
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {
-    ("1080p-nv12-24to60", "search"): 5198080, ("1080p-nv12-24to60", "warp"): 6786560, ("1080p-nv12-24to60", "pack"): 3116288,
-    ("4k-p010-24to144", "warp"): 52152832, ("4k-p010-24to144", "pack"): 25096448,
+    ("1080p-nv12-24to60", "search"): 5203968, ("1080p-nv12-24to60", "warp"): 6787328, ("1080p-nv12-24to60", "pack"): 3116288,
+    ("4k-p010-24to144", "warp"): 52293120, ("4k-p010-24to144", "pack"): 25040640,
 }
 
 
