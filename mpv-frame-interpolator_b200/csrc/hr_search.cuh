@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t window_total(uint32_t sad, int c, int cur, u
  * is (x0,y0): positions +-2*ws clamped to the lattice, read from the previous level's table (words
  * hold x | y << 16). All points of a window resolve to the same four windows, so one lookup serves
  * the whole window and both axis steps of the level. */
-__device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int ws, int x0, int y0, uint32_t (&nw)[4]) {
+__device__ __forceinline__ void neighbour_ptrs(const FlowParams &P, int it, int ws, int x0, int y0, const unsigned long long *(&q)[4]) {
     const int pws = ws << 1;
     const int lgp = 31 - __clz(pws);
     const int pnwx = (P.lw + pws - 1) >> lgp;
@@ -75,16 +75,37 @@ __device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int
     const int yd = hr_min(y0 + pws, P.lh - 1) >> lgp, yu = hr_max(y0 - pws, 0) >> lgp;
     const int xr = hr_min(x0 + pws, P.lw - 1) >> lgp, xl = hr_max(x0 - pws, 0) >> lgp;
     const int xc = x0 >> lgp, yc = y0 >> lgp;
-    const unsigned long long *q[4] = {Tp + yd * pnwx + xc /* down */, Tp + yc * pnwx + xr /* right */, Tp + yc * pnwx + xl /* left */,
-                                      Tp + yu * pnwx + xc /* up */};
-    unsigned long long v[4];
+    q[0] = Tp + yd * pnwx + xc; /* down */
+    q[1] = Tp + yc * pnwx + xr; /* right */
+    q[2] = Tp + yc * pnwx + xl; /* left */
+    q[3] = Tp + yu * pnwx + xc; /* up */
+}
+/* first half: issue the four loads (they may come back stale: the producing tile has not got there yet) */
+__device__ __forceinline__ void neighbours_issue(const FlowParams &P, int it, int ws, int x0, int y0, unsigned long long (&v)[4]) {
+    const unsigned long long *q[4];
+    neighbour_ptrs(P, it, ws, x0, y0, q);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = ld_relaxed_u64(q[i]);
+}
+/* second half: re-load the words whose tag is stale, hand out the payloads */
+__device__ __forceinline__ void neighbours_wait(const FlowParams &P, int it, int ws, int x0, int y0, unsigned long long (&v)[4], uint32_t (&nw)[4]) {
+    bool stale = false;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        while ((uint32_t)(v[i] >> 32) != P.epoch) v[i] = ld_relaxed_u64(q[i]); /* the producing tile has not got there yet */
-        nw[i] = (uint32_t)v[i];
+    for (int i = 0; i < 4; ++i) stale |= (uint32_t)(v[i] >> 32) != P.epoch;
+    if (stale) {
+        const unsigned long long *q[4];
+        neighbour_ptrs(P, it, ws, x0, y0, q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            while ((uint32_t)(v[i] >> 32) != P.epoch) v[i] = ld_relaxed_u64(q[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nw[i] = (uint32_t)v[i];
+}
+__device__ __forceinline__ void load_neighbours(const FlowParams &P, int it, int ws, int x0, int y0, uint32_t (&nw)[4]) {
+    unsigned long long v[4];
+    neighbours_issue(P, it, ws, x0, y0, v);
+    neighbours_wait(P, it, ws, x0, y0, v, nw);
 }
 /* pick one axis out of the four neighbour words */
 __device__ __forceinline__ void neighbour_axis(const uint32_t (&nw)[4], int axis, int (&n)[4]) {
@@ -155,7 +176,10 @@ __device__ __forceinline__ void trace_store(const FlowParams &P, const Thr &t, i
  * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
  * For WS = 64 the step only publishes the tile's totals; big_finish() scores them. */
 template <int RT, int WS, int AXIS>
-__device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp) {
+__device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp, long long *fine = nullptr) {
+    /* DBG instantiations only (fine == nullptr folds away elsewhere): clock stamps of thread 0 inside the step */
+#define FST(k) if (fine) { asm volatile("" ::: "memory"); fine[k] = clock64(); asm volatile("" ::: "memory"); }
+    FST(0)
     constexpr bool small = WS <= 8;
     const int R = RT > 0 ? RT : P.R;
     const int s = P.s, m = (1 << s) - 1;
@@ -254,21 +278,32 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
         sy0 = t.ty0 + (warp >> 3) * 16;
         scorer = ((warp & 1) | ((warp >> 2) & 1)) == 0 && sx0 < P.lw && sy0 < P.lh;
     }
+    const bool wantNb = useNb && AXIS == 0 && WS <= HR_TILE && (small ? ownWindow : scorer);
+    const int nx0 = small ? x0 : sx0, ny0 = small ? y0 : sy0;
+    unsigned long long nbv[4] = {0ull, 0ull, 0ull, 0ull};
+    auto prefetch_neighbours = [&]() {
+        if (wantNb) neighbours_issue(P, it, WS, nx0, ny0, nbv);
+    };
     auto fetch_neighbours = [&]() {
-        if (useNb && AXIS == 0) {
-            if (small) {
-                if (ownWindow) load_neighbours(P, it, WS, x0, y0, t.nw);
-            } else if (WS <= HR_TILE) {
-                if (scorer) load_neighbours(P, it, WS, sx0, sy0, t.nw);
-            }
-        }
+        if (wantNb) neighbours_wait(P, it, WS, nx0, ny0, nbv, t.nw);
         if (small && useNb) neighbour_axis(t.nw, AXIS, nb);
     };
     if constexpr (RT > 0) {
         uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
+        prefetch_neighbours();
         issue(0, va, vb);
+        FST(1)
         fetch_neighbours();
+        FST(2)
+        if (fine) { /* make the stamp wait for the samples */
+            uint32_t x = 0;
+            for (int j = 0; j < HR_ZCHUNK; ++j)
+                if (j < R) x ^= va[j] ^ vb[j];
+            if (x == 0x12345679u) fine[5] = 0;
+            FST(3)
+        }
         consume(0, va, vb);
+        FST(4)
 #pragma unroll
         for (int z0 = HR_ZCHUNK; z0 < RT; z0 += HR_ZCHUNK) {
             uint32_t wa[HR_ZCHUNK], wb[HR_ZCHUNK];
@@ -277,6 +312,7 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
         }
     } else {
         uint32_t va[HR_ZCHUNK], vb[HR_ZCHUNK];
+        prefetch_neighbours();
         issue(0, va, vb);
         fetch_neighbours();
         consume(0, va, vb);
@@ -317,6 +353,7 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
         __syncthreads();
         winner = sh.winner[WS == HR_TILE ? 0 : (warp >> 3) * 2 + ((warp >> 1) & 1)];
     }
+    FST(5)
     if (AXIS) t.oy += P.cand[winner];
     else t.ox += P.cand[winner];
     trace_store(P, t, step, winner);
@@ -326,6 +363,8 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
         put_tagged(P.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw), P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
     }
 }
+
+#undef FST
 
 /* Second half of a step whose windows span several tiles: sum the totals of the window's tiles in a
  * fixed order (warp w takes tiles w, w+16, ... — independent L2 loads, lane = layer) and score. */
@@ -460,9 +499,13 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
             HR_STAMP();
         } else {
             for_tiles([&] {
-                search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp);
+                /* DBG: six stamps inside each step of the three warp-local levels, slots 40.. (tools/diag_fine.py) */
+                const int fineLevel = it - (P.iters - 3);
+                long long *fine = (DBG && P.timeline && tid == 0 && WS <= 8 && fineLevel >= 0 && fineLevel < 3)
+                                      ? P.timeline + blockIdx.x * HR_TIMELINE_SLOTS + 40 + fineLevel * 12 : nullptr;
+                search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp, fine);
                 HR_STAMP();
-                search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp);
+                search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp, fine ? fine + 6 : nullptr);
                 HR_STAMP();
             });
         }
