@@ -86,7 +86,12 @@ int hr_synchronize(HrContext *ctx);
  * bit-identical to the serial mode. Outputs in caller-owned planes are complete after hr_synchronize, or — for
  * work that the caller enqueues on the context's stream — after hr_pipeline_join; the same two calls are what
  * orders a caller's re-use of borrowed input planes after the warps that still read them. Calls that block or touch
- * host memory (hr_update_frame, hr_download, the taps) behave as before. Ignored while bands are configured. */
+ * host memory (hr_update_frame, hr_download, the taps) behave as before, except that two of them start work ahead
+ * of the call that will ask for it: hr_update_frame launches the search of the new pair with the knobs of the
+ * previous hr_calc_flow, hr_download warps the frame of the next blending scalar of the pacing (last scalar + last
+ * increment) into a second internal frame while its copy runs. A following call whose arguments match finds the
+ * work under way or done, any other call launches its own — the results are the same bits either way
+ * (HR_AHEAD=0 in the environment turns the guessing off). Ignored while bands are configured. */
 int hr_set_pipeline(HrContext *ctx, int enable);
 int hr_pipeline_join(HrContext *ctx);
 /* One source frame of a device-resident stream in one call (offline / batch interpolation):

@@ -89,6 +89,23 @@ struct HrContext {
     unsigned long long *TL[HR_SEARCH_LANES], *partialL[HR_SEARCH_LANES];
     unsigned warpRR;
 
+    /* Work started ahead of the blocking calls that ask for it (pipelined mode, host interface): the search of a
+     * new pair from hr_update_frame with the knobs of the previous hr_calc_flow, and the next warp of a pair from
+     * hr_download with the blending scalar the pacing will most likely ask for next. A call whose arguments match
+     * finds its work under way or done; one that does not match launches its own. Results are the same bits. */
+    struct FlowKnobs {
+        int valid, R, dS, nS, frames;
+    } lastFlow, specFlow;
+    struct WarpAhead {
+        int valid, mode, frames;
+        float t, black, white;
+        uint32_t epoch;
+        cudaEvent_t done; /* not owned: the flow-buffer reader event of the launch */
+    } specWarp;
+    uint8_t *outBuf2;      /* second internal output frame: what is warped ahead goes here                  */
+    float lastT, lastDelta, lastBlack, lastWhite;
+    int lastWarpFrames, lastMode, aheadOn;
+
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
     int profiling;
@@ -124,6 +141,7 @@ static int bind_device(HrContext *ctx) {
 static int sync_all(HrContext *ctx);
 static int pipe_join(HrContext *ctx);
 static int pipe_on(const HrContext *ctx);
+static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, cudaStream_t *stOut);
 
 extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
 
@@ -186,6 +204,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->packed[0]);
     cudaFree(ctx->packed[1]);
     cudaFree(ctx->outBuf);
+    cudaFree(ctx->outBuf2);
     cudaFree(ctx->off);
     cudaFree(ctx->blur);
     cudaFree(ctx->blurXY);
@@ -309,6 +328,8 @@ static int create_impl(HrContext *ctx) {
     for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ctx->evK[i]));
     const char *g = getenv("HR_WARP_GENERIC");
     ctx->useFastWarp = !(g && g[0] == '1');
+    const char *ah = getenv("HR_AHEAD");
+    ctx->aheadOn = !(ah && ah[0] == '0');
     CU(cudaDeviceSynchronize());
     return 0;
 }
@@ -565,10 +586,14 @@ extern "C" int hr_set_pipeline(HrContext *ctx, int enable) {
             CU(cudaMemset(ctx->TL[l], 0, tw));
             CU(cudaMemset(ctx->partialL[l], 0, bw));
         }
+        CU(cudaMalloc(&ctx->outBuf2, ctx->frameBytes));
+        CU(cudaMemset(ctx->outBuf2, 0, ctx->frameBytes));
+        ctx->deviceBytes += ctx->frameBytes;
         ctx->deviceBytes += (HR_FLOW_BUFS - 1) * (2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t)) + (HR_SEARCH_LANES - 1) * (2 * ln * sizeof(int16_t) + tw + bw);
         CU(cudaDeviceSynchronize());
     }
     ctx->pipeline = enable ? 1 : 0;
+    ctx->specWarp.valid = ctx->specFlow.valid = 0;
     return 0;
 }
 
@@ -600,6 +625,16 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     ctx->fslot[1] = slot;
     if (launch_pack(ctx)) return 1;
     ctx->framesSeen++;
+    ctx->specWarp.valid = ctx->specFlow.valid = 0;
+    if (pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn) {
+        /* the search the filter asks for next, with the knobs it used last time: under way while this call waits
+         * for the upload and the caller gets round to calculateOpticalFlow */
+        cudaStream_t st;
+        if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
+        CU(cudaEventRecord(ctx->evFlowEnd, st));
+        ctx->specFlow = ctx->lastFlow;
+        ctx->specFlow.frames = ctx->framesSeen;
+    }
     CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
     return 0;
 }
@@ -608,6 +643,7 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
     if (!ctx) return 1;
     if (!dY || !dUV) return fail(ctx, "hr_update_frame_device: NULL plane");
     if (bind_device(ctx)) return 1;
+    ctx->specWarp.valid = ctx->specFlow.valid = 0;
     if (!borrow && pipe_join(ctx)) return 1; /* the slot being overwritten may still be read by warps in flight */
     if (!pipe_on(ctx)) CU(cudaEventRecord(ctx->evUpdate, ctx->stream));
     int slot;
@@ -645,13 +681,8 @@ static const void *search_kernel_for(int R, int multi, int timeline) {
     }
 }
 
-extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, double *seconds) {
-    if (!ctx) return 1;
-    if (searchRadius < HR_MIN_SEARCH_RADIUS || searchRadius > HR_MAX_SEARCH_RADIUS)
-        return fail(ctx, "hr_calc_flow: search radius %d outside [%d, %d]", searchRadius, HR_MIN_SEARCH_RADIUS, HR_MAX_SEARCH_RADIUS);
-    if (deltaScalar < 0 || deltaScalar > 31 || neighborBiasScalar < 0 || neighborBiasScalar > 31)
-        return fail(ctx, "hr_calc_flow: scalar out of range");
-    if (bind_device(ctx)) return 1;
+/* enqueue K1-K4 for the current frame pair; *stOut = the stream it went to */
+static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, cudaStream_t *stOut) {
     FlowParams P;
     memset(&P, 0, sizeof(P));
     P.p1 = ctx->packed[0];
@@ -728,7 +759,33 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
         ctx->haveSearch[fb] = 1;
         ctx->packRead[ctx->packedId[0]] = ctx->evSearch[fb];
     }
-    if (!pl || seconds) CU(cudaEventRecord(ctx->evFlowEnd, st));
+    *stOut = st;
+    return 0;
+}
+
+extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, double *seconds) {
+    if (!ctx) return 1;
+    if (searchRadius < HR_MIN_SEARCH_RADIUS || searchRadius > HR_MAX_SEARCH_RADIUS)
+        return fail(ctx, "hr_calc_flow: search radius %d outside [%d, %d]", searchRadius, HR_MIN_SEARCH_RADIUS, HR_MAX_SEARCH_RADIUS);
+    if (deltaScalar < 0 || deltaScalar > 31 || neighborBiasScalar < 0 || neighborBiasScalar > 31)
+        return fail(ctx, "hr_calc_flow: scalar out of range");
+    if (bind_device(ctx)) return 1;
+    const int pl = pipe_on(ctx);
+    ctx->specWarp.valid = 0; /* a new flow: whatever was warped ahead is void */
+    if (ctx->specFlow.valid && ctx->specFlow.frames == ctx->framesSeen && ctx->specFlow.R == searchRadius && ctx->specFlow.dS == deltaScalar &&
+        ctx->specFlow.nS == neighborBiasScalar) {
+        /* hr_update_frame launched exactly this search already (same frame pair, same knobs): nothing to enqueue */
+        ctx->specFlow.valid = 0;
+    } else {
+        ctx->specFlow.valid = 0;
+        cudaStream_t st;
+        if (launch_flow(ctx, searchRadius, deltaScalar, neighborBiasScalar, &st)) return 1;
+        if (!pl || seconds) CU(cudaEventRecord(ctx->evFlowEnd, st));
+    }
+    ctx->lastFlow.valid = 1;
+    ctx->lastFlow.R = searchRadius;
+    ctx->lastFlow.dS = deltaScalar;
+    ctx->lastFlow.nS = neighborBiasScalar;
     if (seconds) {
         CU(cudaEventSynchronize(ctx->evFlowEnd));
         float ms = 0.f;
@@ -844,7 +901,8 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     const int pl = pipe_on(ctx), fb = ctx->flowCur;
     cudaStream_t st = ctx->stream;
     if (pl) {
-        if (ctx->outY != ctx->outBuf) st = ctx->sWarp[ctx->warpRR++ % HR_WARP_STREAMS];
+        if (ctx->outY == ctx->outBuf2) st = ctx->sWarp[0]; /* warped ahead: one stream, so that they never overlap one another */
+        else if (ctx->outY != ctx->outBuf) st = ctx->sWarp[ctx->warpRR++ % HR_WARP_STREAMS];
         if (ctx->haveSearch[fb]) CU(cudaStreamWaitEvent(st, ctx->evSearch[fb], 0));
         else CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
     }
@@ -887,7 +945,59 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
     if (bind_device(ctx)) return 1;
     if (!ctx->pipeline && ctx->sPack && pipe_join(ctx)) return 1; /* leftovers of an earlier pipelined phase */
     if (!pipe_on(ctx) || ctx->outY == ctx->outBuf) CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
+    const int internal = ctx->outY == ctx->outBuf;
+    if (internal) {
+        /* history for hr_download's guess of the next blending scalar (vf_HopperRender.c:371-374: t advances by a
+         * constant ratio within a source frame) */
+        if (ctx->lastWarpFrames == ctx->framesSeen && t > ctx->lastT) ctx->lastDelta = t - ctx->lastT;
+        ctx->lastT = t;
+        ctx->lastWarpFrames = ctx->framesSeen;
+        ctx->lastMode = mode;
+        ctx->lastBlack = black;
+        ctx->lastWhite = white;
+        if (ctx->specWarp.valid) {
+            const HrContext::WarpAhead w = ctx->specWarp;
+            ctx->specWarp.valid = 0;
+            if (w.frames == ctx->framesSeen && w.epoch == ctx->epoch && w.mode == mode && memcmp(&w.t, &t, sizeof(float)) == 0 && w.black == black &&
+                w.white == white) {
+                /* hr_download warped exactly this frame ahead into the second internal frame: make it the output */
+                uint8_t *b = ctx->outBuf;
+                ctx->outBuf = ctx->outBuf2;
+                ctx->outBuf2 = b;
+                ctx->outY = ctx->outBuf;
+                ctx->outUV = ctx->outBuf + (size_t)ctx->H * ctx->W * ctx->bps;
+                CU(cudaStreamWaitEvent(ctx->stream, w.done, 0));
+                return 0;
+            }
+        }
+    }
     return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, t, mode, black, white) : launch_warp<uint16_t>(ctx, t, mode, black, white);
+}
+
+/* hr_download, after its copy has been enqueued: warp the frame the pacing will most likely ask for next */
+static int warp_ahead(HrContext *ctx) {
+    if (!pipe_on(ctx) || !ctx->aheadOn || ctx->outY != ctx->outBuf || !ctx->outBuf2 || ctx->specWarp.valid) return 0;
+    if (!(ctx->lastDelta > 0.0f) || ctx->lastWarpFrames != ctx->framesSeen) return 0;
+    const float tp = ctx->lastT + ctx->lastDelta;
+    if (!(tp < 1.0f)) return 0; /* the next source frame comes first */
+    const int fb = ctx->flowCur;
+    void *keepY = ctx->outY, *keepUV = ctx->outUV;
+    ctx->outY = ctx->outBuf2;
+    ctx->outUV = ctx->outBuf2 + (size_t)ctx->H * ctx->W * ctx->bps;
+    const int rc = ctx->bps == 1 ? launch_warp<uint8_t>(ctx, tp, ctx->lastMode, ctx->lastBlack, ctx->lastWhite)
+                                 : launch_warp<uint16_t>(ctx, tp, ctx->lastMode, ctx->lastBlack, ctx->lastWhite);
+    ctx->outY = keepY;
+    ctx->outUV = keepUV;
+    if (rc) return 1;
+    ctx->specWarp.valid = 1;
+    ctx->specWarp.t = tp;
+    ctx->specWarp.mode = ctx->lastMode;
+    ctx->specWarp.black = ctx->lastBlack;
+    ctx->specWarp.white = ctx->lastWhite;
+    ctx->specWarp.frames = ctx->framesSeen;
+    ctx->specWarp.epoch = ctx->epoch;
+    ctx->specWarp.done = ctx->evWarp[fb][ctx->nWarpEv[fb] - 1];
+    return 0;
 }
 
 /* One source frame of a device-resident stream in ONE call: update + flow + nWarps warps, each into its own
@@ -944,6 +1054,7 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
         CU(cudaMemcpyAsync(uvPlane, ctx->outUV, uvlen, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
+    if (warp_ahead(ctx)) return 1;
     CU(cudaEventSynchronize(ctx->evDlEnd));
     if (seconds) {
         float ms = 0.f;
@@ -1168,6 +1279,7 @@ extern "C" int hr_get_output_device(HrContext *ctx, void **dY, void **dUV) {
 extern "C" int hr_set_output_device(HrContext *ctx, void *dY, void *dUV) {
     if (!ctx) return 1;
     if ((dY == NULL) != (dUV == NULL)) return fail(ctx, "hr_set_output_device: give both planes or neither");
+    ctx->specWarp.valid = 0;
     if (dY) {
         ctx->outY = dY;
         ctx->outUV = dUV;
@@ -1192,6 +1304,7 @@ extern "C" int hr_set_blurred_offsets(HrContext *ctx, const int16_t *blurred) {
     if (!ctx || !blurred) return 1;
     if (bind_device(ctx)) return 1;
     const size_t n = 2 * (size_t)ctx->lw * ctx->lh * sizeof(int16_t);
+    ctx->specWarp.valid = 0;
     if (sync_all(ctx)) return 1;
     CU(cudaMemcpy(ctx->blur, blurred, n, cudaMemcpyHostToDevice));
     const int ln = ctx->lw * ctx->lh;
