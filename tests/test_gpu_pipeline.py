@@ -124,3 +124,51 @@ def test_c_host_layer_replay_equals_call_by_call(hr, synth):
     assert np.array_equal(oy.numpy(), want[0]) and np.array_equal(ouv.numpy(), want[1])
     lib.freeOFC(ctypes.byref(c))
     assert not c.isInitialized
+
+
+def test_work_ahead_never_changes_results(hr, synth):
+    """The host interface in pipelined mode starts the next search and the next warp ahead of the calls that ask for
+    them. Whatever the caller then asks for — the guessed values or anything else — the frames are those of a
+    plain context that guesses nothing."""
+    w, h = 1280, 720
+    clip = synth.MovingTextureClip(w, h)
+    frames = [clip.frame(k) for k in range(6)]
+    # (radius, [(t, mode, black, white), ...]) per source frame: regular pacing, a radius change, an irregular t, a
+    # repeated t, a mode change and a level change right after a regular run
+    script = [
+        (5, [(0.0, 2, 0.0, 255.0), (0.4, 2, 0.0, 255.0), (0.8, 2, 0.0, 255.0)]),
+        (5, [(0.2, 2, 0.0, 255.0), (0.6, 2, 0.0, 255.0)]),
+        (6, [(0.0, 2, 0.0, 255.0), (0.4, 2, 0.0, 255.0), (0.5, 2, 0.0, 255.0), (0.5, 2, 0.0, 255.0)]),
+        (6, [(0.1, 2, 0.0, 255.0), (0.3, 2, 0.0, 255.0), (0.5, 0, 0.0, 255.0), (0.7, 2, 16.0, 219.0), (0.9, 2, 16.0, 219.0)]),
+        (9, [(0.25, 5, 0.0, 255.0), (0.5, 5, 0.0, 255.0), (0.75, 5, 0.0, 255.0)]),
+    ]
+    plain = hr.HrCuda(h, w, w)
+    plain.update_frame(*frames[0])
+    ofc = hr.OpticalFlowCalc()
+    assert not hr.initOpticalFlowCalc(ofc, h, w, w)           # pipelined, guessing
+    assert not hr.updateFrame(ofc, list(frames[0]))
+    for k, (radius, warps) in enumerate(script):
+        plain.update_frame(*frames[k + 1])
+        plain.calc_flow(radius, 8, 6)
+        assert not hr.updateFrame(ofc, list(frames[k + 1]))
+        ofc.opticalFlowSearchRadius = radius
+        assert not hr.calculateOpticalFlow(ofc)
+        if k == 2:                                            # the flow is asked for twice, with other knobs in between
+            ofc.deltaScalar = 4
+            assert not hr.calculateOpticalFlow(ofc)
+            ofc.deltaScalar = 8
+            assert not hr.calculateOpticalFlow(ofc)
+        assert np.array_equal(ofc.impl.get_offsets()[1], plain.get_offsets()[1]), "flow of pair %d" % k
+        for t, mode, black, white in warps:
+            plain.warp(t, mode, black, white)
+            py, puv, _ = plain.download()
+            ofc.outputBlackLevel, ofc.outputWhiteLevel = black, white
+            gy, guv = np.zeros((h, w), np.uint8), np.zeros((h // 2, w), np.uint8)
+            assert not hr.warpFrames(ofc, t, mode)
+            assert not hr.downloadFrame(ofc, [gy, guv])
+            assert np.array_equal(gy, py) and np.array_equal(guv, puv), "pair %d t=%g mode %d" % (k, t, mode)
+            if t == 0.4:                                      # the same frame once more
+                assert not hr.downloadFrame(ofc, [gy, guv])
+                assert np.array_equal(gy, py) and np.array_equal(guv, puv)
+    hr.freeOFC(ofc)
+    plain.close()
