@@ -43,7 +43,7 @@ L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {
     ("1080p-nv12-24to60", "search"): 5203968, ("1080p-nv12-24to60", "warp"): 6787328, ("1080p-nv12-24to60", "pack"): 3116288,
-    ("4k-p010-24to144", "warp"): 52293120, ("4k-p010-24to144", "pack"): 25040640,
+    ("4k-p010-24to144", "warp"): 53419008, ("4k-p010-24to144", "pack"): 25016576,
 }
 
 

@@ -836,9 +836,13 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.t21 = 1.0f - t;
     P.black = black;
     P.white = white;
-    /* thread = 4 samples x ROWS rows (8 when the lattice cell is at least 8 rows tall, else 4); row groups of
-     * the luma plane, then of the chroma plane */
-    const int ROWS = ctx->s >= 3 ? 8 : 4;
+    /* thread = 4 samples x 4 rows (cells of 8 rows and more are covered by several threads: measured, smaller
+     * units and more resident warps beat fewer flow look-ups per sample: 8K P010 74 -> 67 us); row groups of the
+     * luma plane, then of the chroma plane */
+#ifndef HR_WARP_ROWS
+#define HR_WARP_ROWS 4
+#endif
+    const int ROWS = HR_WARP_ROWS;
     int r0 = 0, r1 = ctx->H;
     if (ctx->bandWorld > 1) {
         r0 = ctx->bandRow0[ctx->bandRank];
@@ -910,8 +914,7 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     if (fast) {
         dim3 block(32, 4);
         dim3 grid((ctx->aW + 127) / 128, (groups + 3) / 4);
-        if (ROWS == 8) warp_fast_kernel<T, 8><<<grid, block, 0, st>>>(P, A);
-        else warp_fast_kernel<T, 4><<<grid, block, 0, st>>>(P, A);
+        warp_fast_kernel<T, HR_WARP_ROWS><<<grid, block, 0, st>>>(P, A);
     } else {
         /* per-sample kernel, row groups of 4 */
         const int lg0 = r0 / 4, lgn = (r1 + 3) / 4 - lg0, cg0 = (r0 >> 1) / 4, cgn = ((r1 >> 1) + 3) / 4 - cg0;

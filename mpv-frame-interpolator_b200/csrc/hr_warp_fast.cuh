@@ -7,7 +7,7 @@
  * HBM-bound by nature (2 frames read, 1 written, 518 KB of flow), issue-bound in practice: the work per
  * output sample is two byte->float conversions, the blend, two truncations and the level map. The kernel
  * is organised around the instruction count:
- *   - thread = 4 samples x ROWS rows inside ONE lattice cell (ROWS = 4 for 4x4 cells, 8 above), so that
+ *   - thread = 4 samples x 4 rows inside ONE lattice cell, so that
  *     the flow vector, the flipped vector (warpFrameKernel.cl:155-156), the four roundings and every
  *     bounds test are done once per thread; the flow comes as one packed (x | y << 16) word per cell
  *     (written by the search kernel's blur tail next to the planar array of the C interface);
@@ -279,10 +279,11 @@ __device__ __forceinline__ void warp_fast_thread(const WarpParams<T> &P, const W
 
 /* grid: x = 128-sample column blocks, y = groups of 4 row groups; row groups of the luma plane first */
 template <typename T, int ROWS>
-/* ten 128-thread CTAs per SM (<= 51 registers): the kernel is latency-bound at 4K and above, more resident warps pay
- * (tools/diag_launch.py: 8K P010 80.4 -> 73.8 us, 4K P010 stream 80.9 -> 76.4 us per source frame; 12 gains nothing more) */
+/* twelve 128-thread CTAs per SM (40 registers): the kernel is latency-bound at 4K and above, resident warps are what
+ * hides its three dependent round trips (tools/diag_launch.py, 8K P010: 80 us at 9 CTAs of 8-row units, 74 us at 10,
+ * 67 us with 4-row units at 10-12) */
 #ifndef HR_WARP_MINBLOCKS
-#define HR_WARP_MINBLOCKS 10
+#define HR_WARP_MINBLOCKS 12
 #endif
 __global__ void __launch_bounds__(128, HR_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A) {
     const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
