@@ -90,6 +90,20 @@ def main():
                "-L", str(csrc), "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../mpv-frame-interpolator_b200/csrc", "-lm", "-lpthread"]
         subprocess.run(cmd, check=True)
         print("build_ref: built", OUT / "libhr_filter_sim.so", "(reference filter + this repo's OFC layer)")
+        # 4. the same for P010: the reference filter source is still compiled as it is; the two
+        #    changes a maintainer makes in it for P010 — `ofc->pixelFormat = 1` before initOpticalFlowCalc and the
+        #    stride in samples instead of bytes (vf_HopperRender.c:446; format negotiation :385, :668 is the harness's
+        #    business here) — are expressed as a function-like macro seen by that translation unit only.
+        with tempfile.TemporaryDirectory(dir=str(OUT)) as td:
+            o1, o2, o3 = (str(pathlib.Path(td) / n) for n in ("vf.o", "sim.o", "ofc.o"))
+            common = [CC, "-O2", "-std=gnu11", "-w", "-fPIC", "-c", "-include", str(pkg_hr / "opticalFlowCalc.h"),
+                      "-I", str(pkg_hr), "-I", str(HERE / "mpv_shim"), "-I", str(root / "include")]
+            subprocess.run(common + ["-include", str(HERE / "mpv_shim" / "hr_p010_patch.h"), "-o", o1, str(REF / "vf_HopperRender.c")], check=True)
+            subprocess.run(common + ["-DHR_SIM_BPS=2", "-o", o2, str(HERE / "filter_host_sim.c")], check=True)
+            subprocess.run(common + ["-o", o3, str(pkg_hr / "opticalFlowCalc.c")], check=True)
+            subprocess.run([CC, "-shared", "-o", str(OUT / "libhr_filter_sim_p010.so"), o1, o2, o3,
+                            "-L", str(csrc), "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../mpv-frame-interpolator_b200/csrc", "-lm", "-lpthread"], check=True)
+        print("build_ref: built", OUT / "libhr_filter_sim_p010.so", "(the same, P010)")
     else:
         print("build_ref: libhopperrender_cuda.so not built yet — filter host sim skipped")
     return 0

@@ -14,9 +14,17 @@ extern const struct mp_user_filter_entry vf_HopperRender; /* vf_HopperRender.c:7
 /* ---- talloc / images -------------------------------------------------------------------------- */
 void talloc_free(void *p) { free(p); }
 
+/* bytes per sample of the images the harness hands to the filter: 1 = NV12 (what the reference negotiates), 2 = the
+ * P010 build of the harness (oracle/build_ref.py: the same unmodified filter source, compiled with the two changes a
+ * maintainer makes for P010 expressed as a macro — pixelFormat = 1 and the stride in samples instead of bytes) */
+#ifndef HR_SIM_BPS
+#define HR_SIM_BPS 1
+#endif
+int hr_sim_bytes_per_sample(void) { return HR_SIM_BPS; }
+
 static struct mp_image *image_alloc(int w, int h) {
     struct mp_image *img = calloc(1, sizeof(*img));
-    const int stride = (w + 63) & ~63; /* mpv aligns strides to 64 bytes (video/mp_image.h:35) */
+    const int stride = (w * HR_SIM_BPS + 63) & ~63; /* mpv aligns strides to 64 bytes (video/mp_image.h:35) */
     img->w = w;
     img->h = h;
     img->imgfmt = IMGFMT_NV12;
@@ -177,12 +185,13 @@ struct mp_filter_sim *hr_sim_create(int frameOutput, double displayFps) {
 }
 const char *hr_sim_filter_name(void) { return vf_HopperRender.desc.name; }
 
-/* feed one NV12 source frame (tightly packed planes of w x h) and run the filter until it stalls;
+/* feed one NV12 (P010 build: P010) source frame (tightly packed planes of w x h samples) and run the filter until it stalls;
  * returns the number of output frames waiting, or -1 if the filter marked itself failed */
 int hr_sim_push(struct mp_filter_sim *s, const unsigned char *y, const unsigned char *uv, int w, int h, double pts, double nominalFps) {
     struct mp_image *img = image_alloc(w, h);
-    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * w, w);
-    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * w, w);
+    const size_t rowBytes = (size_t)w * HR_SIM_BPS;
+    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * rowBytes, rowBytes);
+    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * rowBytes, rowBytes);
     img->pts = pts;
     img->nominal_fps = nominalFps;
     s->in.slot = MAKE_FRAME(MP_FRAME_VIDEO, img);
@@ -198,8 +207,9 @@ int hr_sim_pop(struct mp_filter_sim *s, unsigned char *y, unsigned char *uv, dou
     if (s->n_out == 0) return 1;
     struct mp_image *img = s->outputs[0];
     memmove(s->outputs, s->outputs + 1, sizeof(s->outputs[0]) * (size_t)(--s->n_out));
-    for (int r = 0; r < img->h; ++r) memcpy(y + (size_t)r * img->w, img->planes[0] + (size_t)r * img->stride[0], img->w);
-    for (int r = 0; r < img->h / 2; ++r) memcpy(uv + (size_t)r * img->w, img->planes[1] + (size_t)r * img->stride[1], img->w);
+    const size_t rowBytes = (size_t)img->w * HR_SIM_BPS;
+    for (int r = 0; r < img->h; ++r) memcpy(y + (size_t)r * rowBytes, img->planes[0] + (size_t)r * img->stride[0], rowBytes);
+    for (int r = 0; r < img->h / 2; ++r) memcpy(uv + (size_t)r * rowBytes, img->planes[1] + (size_t)r * img->stride[1], rowBytes);
     if (pts) *pts = img->pts;
     if (stride) *stride = img->stride[0];
     mp_image_unrefp(&img);

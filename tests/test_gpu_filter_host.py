@@ -103,3 +103,62 @@ def test_reset_and_speed_command(hr, synth, sim):
     n = sim.hr_sim_push(s, C.c_void_p(y.ctypes.data), C.c_void_p(uv.ctypes.data), w, h, 4 / 24.0, 24.0)
     assert n in (1, 2)
     sim.hr_sim_destroy(s)
+
+
+SIM_P010 = ROOT / "oracle" / "_ref" / "libhr_filter_sim_p010.so"
+
+
+def test_reference_filter_p010(hr, oracle, synth):
+    """the reference's filter source, compiled with the P010 change of INTEGRATION.md §1 stated as
+    a macro (oracle/mpv_shim/hr_p010_patch.h), driving the P010 path: frame counts of the pacing rule, and every
+    delivered frame against direct C-ABI calls and against the CPU oracle (+-4 LSB of the 10-bit value)."""
+    from hopperrender_b200 import pacing
+    if not SIM_P010.exists():
+        pytest.skip("oracle/_ref/libhr_filter_sim_p010.so not built")
+    L = C.CDLL(str(SIM_P010))
+    L.hr_sim_create.restype = C.c_void_p
+    L.hr_sim_create.argtypes = [C.c_int, C.c_double]
+    L.hr_sim_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.hr_sim_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.hr_sim_destroy.argtypes = [C.c_void_p]
+    assert L.hr_sim_bytes_per_sample() == 2
+    w, h, fps, disp = 1280, 720, 24.0, 60.0
+    clip = synth.MovingTextureClip(w, h, pixfmt=1)
+    s = L.hr_sim_create(2, disp)
+    assert s
+    direct = hr.HrCuda(h, w, w, 1)
+    o = oracle.Oracle(h, w, w, 1)
+    pacer = pacing.Pacer(fps, disp)
+    checked = 0
+    for k in range(4):
+        y, uv = clip.frame(k)
+        assert y.dtype == np.uint16
+        n = L.hr_sim_push(s, C.c_void_p(y.ctypes.data), C.c_void_p(uv.ctypes.data), w, h, k / fps, fps)
+        assert n >= 0, "the filter marked itself failed"
+        outs = []
+        while True:
+            oy, ouv = np.empty((h, w), np.uint16), np.empty((h // 2, w), np.uint16)
+            if L.hr_sim_pop(s, C.c_void_p(oy.ctypes.data), C.c_void_p(ouv.ctypes.data), None, None):
+                break
+            outs.append((oy, ouv))
+        ts = pacer.next_source_frame()
+        direct.update_frame(y, uv)
+        o.update_frame(y, uv)
+        if k == 0:
+            assert len(outs) == 1 and np.array_equal(outs[0][0], y) and np.array_equal(outs[0][1], uv)
+            continue
+        assert len(outs) == len(ts)
+        direct.calc_flow(5)
+        o.calc_flow(5, 8, 6)
+        for (oy, ouv), t in zip(outs, ts):
+            direct.warp(np.float32(t), 2)
+            ey, euv, _ = direct.download()
+            assert np.array_equal(oy, ey) and np.array_equal(ouv, euv), "frame %d t=%.3f differs from the direct calls" % (k, t)
+            assert o.warp(np.float32(t), 2, 0.0, 255.0) == 0
+            ry, ruv = o.download()
+            assert np.abs(oy.astype(np.int32) - ry.astype(np.int32)).max() <= 4 * 64
+            assert np.abs(ouv.astype(np.int32) - ruv.astype(np.int32)).max() <= 4 * 64
+            checked += 1
+    assert checked == 8
+    L.hr_sim_destroy(s)
+    direct.close()
