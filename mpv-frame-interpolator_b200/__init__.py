@@ -503,6 +503,11 @@ class COpticalFlowCalc(C.Structure):
     ]
 
 
+class HrControlState(C.Structure):
+    """`HrControlState` of mpv/video/filter/HopperRender/hrControl.h."""
+    _fields_ = [("interpolationActive", C.c_int), ("frameOutputMode", C.c_int), ("restartCounters", C.c_int), ("pinnedRadius", C.c_int)]
+
+
 _ofc_lib = None
 
 
@@ -525,6 +530,10 @@ def load_ofc_library():
         ("downloadFrame", C.c_bool, [P, PP]),
         ("calculateOpticalFlow", C.c_bool, [P]),
         ("warpFrames", C.c_bool, [P, C.c_float, C.c_int]),
+        ("hrControlParse", C.c_int, [C.c_char_p]),
+        ("hrControlApply", C.c_int, [P, C.POINTER(HrControlState), C.c_int]),
+        ("hrControlPoll", C.c_int, [C.c_int, P, C.POINTER(HrControlState)]),
+        ("hrControlStatus", C.c_int, [C.c_char_p, C.c_size_t, P, C.c_double, C.c_double, C.c_double, C.c_double]),
         ("hrReplayStream", C.c_longlong, [P, PP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, PP]),
     ):
         fn = getattr(lib, name)

@@ -66,10 +66,10 @@ def build_host(force=False):
     """The reference-language (C) host: opticalFlowCalc.c forwarding to the C ABI, and the
     filter_host_sim harness that replays vf_HopperRender's call order."""
     build_cuda()
-    srcs = [HOSTC / "opticalFlowCalc.c", HOSTC / "hrReplay.c", HOSTC / "opticalFlowCalc.h", HOSTC / "config.h"]
+    srcs = [HOSTC / "opticalFlowCalc.c", HOSTC / "hrReplay.c", HOSTC / "hrControl.c", HOSTC / "hrControl.h", HOSTC / "opticalFlowCalc.h", HOSTC / "config.h"]
     if force or not _newer(OFC_LIB, srcs):
         _run([HOST_CC, "-O2", "-std=c11", "-Wall", "-fPIC", "-shared", "-I", ROOT / "include", "-o", OFC_LIB,
-              HOSTC / "opticalFlowCalc.c", HOSTC / "hrReplay.c", "-L", CSRC, "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../../../csrc", "-lm"])
+              HOSTC / "opticalFlowCalc.c", HOSTC / "hrReplay.c", HOSTC / "hrControl.c", "-L", CSRC, "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../../../csrc", "-lm"])
     sim_src = PKG / "host" / "filter_host_sim.c"
     if sim_src.exists() and (force or not _newer(HOST_SIM, [sim_src, *srcs])):
         _run([HOST_CC, "-O2", "-std=c11", "-Wall", "-I", ROOT / "include", "-I", HOSTC, "-o", HOST_SIM, sim_src,
