@@ -40,6 +40,20 @@ def test_pipelined_steps_equal_serial(hr, synth, w, h, pixfmt):
         b.step_device(*dev[k], ts[k], outs[oi:oi + n], radius=5 + (k % 2) * 3)
         oi += n
     b.synchronize()
+    # the same stream once more, several source frames per call (hr_steps_device; one radius per call)
+    c = hr.HrCuda(h, w, w, pixfmt)
+    c.set_pipeline(True)
+    outs_c = [(torch.zeros((h, w), dtype=tdt, device="cuda"), torch.zeros((h // 2, w), dtype=tdt, device="cuda")) for _ in want]
+    c.steps_device([dev[0]], [[]], [])
+    oc = 0
+    for k in range(1, nfr):     # radius alternates per frame in the serial run: one frame per call here, two calls share a list
+        n = len(ts[k])
+        c.steps_device([dev[k]], [ts[k]], outs_c[oc:oc + n], radius=5 + (k % 2) * 3)
+        oc += n
+    c.synchronize()
+    for i in range(len(want)):
+        assert torch.equal(outs_c[i][0], outs[i][0]) and torch.equal(outs_c[i][1], outs[i][1]), "hr_steps_device output %d" % i
+    c.close()
     assert np.array_equal(b.get_offsets()[1], flows[-1])
     for i, (wy, wuv) in enumerate(want):
         gy, guv = outs[i][0].cpu().numpy().view(wy.dtype), outs[i][1].cpu().numpy().view(wuv.dtype)
@@ -172,3 +186,34 @@ def test_work_ahead_never_changes_results(hr, synth):
                 assert np.array_equal(gy, py) and np.array_equal(guv, puv)
     hr.freeOFC(ofc)
     plain.close()
+
+
+def test_many_frames_per_call(hr, synth):
+    """hr_steps_device with a run of source frames per call equals one hr_step_device call per frame."""
+    import torch
+
+    w, h = 1280, 720
+    clip = synth.MovingTextureClip(w, h)
+    frames = [clip.frame(k) for k in range(9)]
+    dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
+    ts = [[]] + [[0.0, 0.4, 0.8], [0.2, 0.6]] * 4
+    nout = sum(len(t) for t in ts)
+    mk = lambda: [(torch.zeros((h, w), dtype=torch.uint8, device="cuda"), torch.zeros((h // 2, w), dtype=torch.uint8, device="cuda")) for _ in range(nout)]
+    a, oa = hr.HrCuda(h, w, w), mk()
+    a.set_pipeline(True)
+    i = 0
+    for k in range(9):
+        a.step_device(*dev[k], ts[k], oa[i:i + len(ts[k])], radius=7)
+        i += len(ts[k])
+    a.synchronize()
+    b, ob = hr.HrCuda(h, w, w), mk()
+    b.set_pipeline(True)
+    b.steps_device(dev[:4], ts[:4], ob[:sum(len(t) for t in ts[:4])], radius=7)
+    first = sum(len(t) for t in ts[:4])
+    b.steps_device(dev[4:], ts[4:], ob[first:], radius=7)
+    b.synchronize()
+    assert np.array_equal(a.get_offsets()[1], b.get_offsets()[1])
+    for i in range(nout):
+        assert torch.equal(oa[i][0], ob[i][0]) and torch.equal(oa[i][1], ob[i][1]), "output %d" % i
+    a.close()
+    b.close()
