@@ -22,7 +22,7 @@ nout = 48
 outs = [(torch.empty((h, w), dtype=torch.uint8, device="cuda"), torch.empty((h // 2, w), dtype=torch.uint8, device="cuda")) for _ in range(nout)]
 p = pacing.Pacer(24.0, 60.0)
 p.next_source_frame()
-ts = [p.next_source_frame() for _ in range(steps + 40)]
+ts = [p.next_source_frame() for _ in range(steps + 60)]
 ctxs = []
 for k in range(nctx):
     st = torch.cuda.Stream()
@@ -32,14 +32,19 @@ for k in range(nctx):
     g.step_device(*ring[nring - 1 - k], [], [])
     ctxs.append((g, st))
 oi = 0
+CH = 10
 def step(i):
     global oi
+    if i % CH:
+        return 0
     n = 0
     for k, (g, st) in enumerate(ctxs):
-        o = [outs[(oi + j) % nout] for j in range(len(ts[i]))]
-        oi += len(ts[i])
-        g.step_device(*ring[(i + 7 * k) % nring], ts[i], o, radius=radius)
-        n += len(ts[i])
+        tl = ts[i:i + CH]
+        m = sum(len(t) for t in tl)
+        o = [outs[(oi + j) % nout] for j in range(m)]
+        oi += m
+        g.steps_device([ring[(i + j + 7 * k) % nring] for j in range(CH)], tl, o, radius=radius)
+        n += m
     return n
 for i in range(20):
     step(i)
