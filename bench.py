@@ -500,6 +500,12 @@ def run_ours(args):
                            "traffic": NCU_TRAFFIC.get((args.workload, k)), "avg_us": avg[k] * 1e3, "share_of_step": per_step[k] / max(1e-12, sum(per_step.values())),
                            "algorithmic_bytes": alg[k], "peak_source": pk_src}
         evals = 2 * g.info.iterations * radius * lw * lh
+        if avg["search"] > 0 and args.workload == "1080p-nv12-24to60" and radius == 5:
+            # the search's own limiter is instruction issue and dependent latency: executed warp instructions per launch
+            # from the committed ncu capture (profiles/r01_ncu_1080p_nv12.txt) against the issue slots of the launch
+            slots = pk.get("sm_max_mhz", 1965.0) * 1e6 * 4 * g.info.smCount * (avg["search"] * 1e-3)
+            roof["search"]["issue"] = {"warp_instructions_per_launch": 14027307, "issue_slots_in_launch": slots, "frac": 14027307 / slots,
+                                       "source": "smsp__inst_executed.sum of the ncu capture; 4 schedulers x SMs x max clock x measured launch time"}
         if avg["search"] > 0:
             roof["search"]["candidate_evals_per_s"] = evals / (avg["search"] * 1e-3)
             roof["search"]["note"] = ("latency/issue bound, not HBM: 16 dependent steps with tile-to-tile hand-offs; ncu (profiles/): issue slots 39 % busy, "
