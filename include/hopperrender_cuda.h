@@ -186,6 +186,13 @@ int hr_get_step_layers(HrContext *ctx, int step, uint8_t *layers);
  * The CPU oracle's NVIDIA-OpenCL arithmetic reads it from tests/golden/mufu_rcp_table.npy. */
 int hr_debug_rcp_table(float *out, int n);
 
+/* Developer tap: the INT-pipe roofline denominator of the search. A kernel that issues nothing but
+ * independent vabsdiff4...add chains (SASS VABSDIFF4.U8.ACC, the one instruction a candidate evaluation of
+ * HR/Kernels/calcDeltaSumsKernel.cl:96-99 costs here) at full occupancy on `device` (< 0: current):
+ * evalsPerSecond = thread-level packed SADs per second over the whole GPU (CUDA events), warpInstrPerClkPerSm = the
+ * same as warp instructions per SM clock. Either pointer may be NULL. Blocking. */
+int hr_debug_int_peak(int device, double *evalsPerSecond, double *warpInstrPerClkPerSm);
+
 /* Developer tap: SM-clock stamps taken by thread 0 of every search CTA at fixed points of the launch
  * (step start, layers reduced, window published / complete, level done, search done, blur done).
  * stamps: int64 [min(maxCtas, searchCtas)][HR_TIMELINE_SLOTS]; unused slots are 0. Blocking. */

@@ -76,6 +76,7 @@ ABI = {
     "hr_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hr_debug_rcp_table": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_debug_int_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hr_set_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hr_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -136,6 +137,15 @@ def debug_rcp_table(n=1024):
     if load_library().hr_debug_rcp_table(_ptr(out), n):
         raise HrError(load_library().hr_last_error(None).decode())
     return out
+
+
+def debug_int_peak(device=-1):
+    """(packed-byte SADs per second over the whole GPU, VABSDIFF4 warp instructions per SM clock): the INT roofline
+    denominator of the search, measured live (developer tap)."""
+    a, b = C.c_double(0.0), C.c_double(0.0)
+    if load_library().hr_debug_int_peak(int(device), C.byref(a), C.byref(b)):
+        raise HrError(load_library().hr_last_error(None).decode())
+    return a.value, b.value
 
 
 class HrCuda:
@@ -505,7 +515,8 @@ class COpticalFlowCalc(C.Structure):
 
 class HrControlState(C.Structure):
     """`HrControlState` of mpv/video/filter/HopperRender/hrControl.h."""
-    _fields_ = [("interpolationActive", C.c_int), ("frameOutputMode", C.c_int), ("restartCounters", C.c_int), ("pinnedRadius", C.c_int)]
+    _fields_ = [("interpolationActive", C.c_int), ("frameOutputMode", C.c_int), ("restartCounters", C.c_int), ("pinnedRadius", C.c_int),
+                ("pendingLength", C.c_int), ("pending", C.c_char * 28)]
 
 
 _ofc_lib = None

@@ -139,6 +139,7 @@ static int bind_device(HrContext *ctx) {
 }
 
 static int sync_all(HrContext *ctx);
+static void pipeline_release(HrContext *ctx);
 static int pipe_join(HrContext *ctx);
 static int pipe_on(const HrContext *ctx);
 static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, cudaStream_t *stOut);
@@ -148,6 +149,55 @@ extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
 extern "C" const char *hr_last_error(const HrContext *ctx) { return ctx ? ctx->err : g_createErr; }
 
 extern "C" uint64_t hr_get_launch_count(const HrContext *ctx) { return ctx ? ctx->launches : 0; }
+
+/* Everything hr_set_pipeline allocates (streams, events, ring entries >= 1, the second output frame). Safe on a
+ * partly built set: every handle is NULL until created and NULL again afterwards. */
+static void pipeline_release(HrContext *ctx) {
+    if (ctx->sPack) cudaStreamDestroy(ctx->sPack);
+    ctx->sPack = NULL;
+    for (int i = 0; i < HR_SEARCH_LANES; ++i) {
+        if (ctx->sSearch[i]) cudaStreamDestroy(ctx->sSearch[i]);
+        ctx->sSearch[i] = NULL;
+    }
+    for (int i = 0; i < HR_WARP_STREAMS; ++i) {
+        if (ctx->sWarp[i]) cudaStreamDestroy(ctx->sWarp[i]);
+        ctx->sWarp[i] = NULL;
+    }
+    if (ctx->evIn) cudaEventDestroy(ctx->evIn);
+    ctx->evIn = NULL;
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
+        ctx->evPack[b] = NULL;
+        ctx->packRead[b] = NULL;
+        ctx->havePack[b] = 0;
+    }
+    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
+        if (ctx->evSearch[b]) cudaEventDestroy(ctx->evSearch[b]);
+        ctx->evSearch[b] = NULL;
+        ctx->haveSearch[b] = 0;
+        ctx->nWarpEv[b] = 0;
+        for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) {
+            if (ctx->evWarp[b][i]) cudaEventDestroy(ctx->evWarp[b][i]);
+            ctx->evWarp[b][i] = NULL;
+        }
+    }
+    for (int b = 1; b < HR_FLOW_BUFS; ++b) {
+        cudaFree(ctx->blurB[b]);
+        cudaFree(ctx->blurXYB[b]);
+        ctx->blurB[b] = NULL;
+        ctx->blurXYB[b] = NULL;
+    }
+    for (int l = 1; l < HR_SEARCH_LANES; ++l) {
+        cudaFree(ctx->offL[l]);
+        cudaFree(ctx->TL[l]);
+        cudaFree(ctx->partialL[l]);
+        ctx->offL[l] = NULL;
+        ctx->TL[l] = NULL;
+        ctx->partialL[l] = NULL;
+    }
+    cudaFree(ctx->outBuf2);
+    ctx->outBuf2 = NULL;
+}
 
 static void window_schedule(int lw, int lh, int *first, int *iters) {
     /* opticalFlowCalc.c:133-149 */
@@ -171,40 +221,19 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
-    if (ctx->sPack) cudaStreamDestroy(ctx->sPack);
-    for (int i = 0; i < HR_SEARCH_LANES; ++i)
-        if (ctx->sSearch[i]) cudaStreamDestroy(ctx->sSearch[i]);
-    for (int i = 0; i < HR_WARP_STREAMS; ++i)
-        if (ctx->sWarp[i]) cudaStreamDestroy(ctx->sWarp[i]);
-    if (ctx->evIn) cudaEventDestroy(ctx->evIn);
-    for (int b = 0; b < 2; ++b)
-        if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
-    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
-        if (ctx->evSearch[b]) cudaEventDestroy(ctx->evSearch[b]);
-        for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i)
-            if (ctx->evWarp[b][i]) cudaEventDestroy(ctx->evWarp[b][i]);
-    }
     /* ctx->blur / blurXY / off / T / partial alias entry [x] of their rings; entry [0] is freed below through them */
-    for (int b = 1; b < HR_FLOW_BUFS; ++b) {
-        cudaFree(ctx->blurB[b]);
-        cudaFree(ctx->blurXYB[b]);
-    }
-    for (int l = 1; l < HR_SEARCH_LANES; ++l) {
-        cudaFree(ctx->offL[l]);
-        cudaFree(ctx->TL[l]);
-        cudaFree(ctx->partialL[l]);
-    }
-    ctx->blur = ctx->blurB[0];
-    ctx->blurXY = ctx->blurXYB[0];
-    ctx->off = ctx->offL[0];
-    ctx->T = ctx->TL[0];
-    ctx->partial = ctx->partialL[0];
+    pipeline_release(ctx);
+    /* (a context whose creation failed half-way has no ring yet: keep what was allocated directly) */
+    if (ctx->blurB[0]) ctx->blur = ctx->blurB[0];
+    if (ctx->blurXYB[0]) ctx->blurXY = ctx->blurXYB[0];
+    if (ctx->offL[0]) ctx->off = ctx->offL[0];
+    if (ctx->TL[0]) ctx->T = ctx->TL[0];
+    if (ctx->partialL[0]) ctx->partial = ctx->partialL[0];
     cudaFree(ctx->frameBuf[0]);
     cudaFree(ctx->frameBuf[1]);
     cudaFree(ctx->packed[0]);
     cudaFree(ctx->packed[1]);
     cudaFree(ctx->outBuf);
-    cudaFree(ctx->outBuf2);
     cudaFree(ctx->off);
     cudaFree(ctx->blur);
     cudaFree(ctx->blurXY);
@@ -236,6 +265,8 @@ static int create_impl(HrContext *ctx) {
     while ((ctx->H >> ctx->s) > MAX_CALC_RES) ctx->s++;
     ctx->lw = (int)ceil(ctx->W / pow(2, ctx->s));
     ctx->lh = (int)ceil(ctx->H / pow(2, ctx->s));
+    if (ctx->s > 4)
+        return fail(ctx, "frames of more than %d lines are not supported (resolution scalar %d > 4)", MAX_CALC_RES << 4, ctx->s);
     window_schedule(ctx->lw, ctx->lh, &ctx->first, &ctx->iters);
     if (ctx->iters < 1 || ctx->iters > HR_MAX_LEVELS) return fail(ctx, "unsupported lattice %dx%d", ctx->lw, ctx->lh);
 
@@ -428,6 +459,82 @@ extern "C" int hr_debug_rcp_table(float *out, int n) {
     return 0;
 }
 
+/* ---- INT-pipe roofline denominator: issue rate of the packed-byte SAD ----------------------
+ * Every candidate evaluation of the search is ONE vabsdiff4.u32.u32.u32.add (SASS: VABSDIFF4.U8.ACC). This kernel
+ * issues nothing else: CHAINS independent accumulator chains per thread, fully unrolled, 2048 resident threads per
+ * SM, so that the result is the pipe's issue rate and not its latency. */
+#define HR_PEAK_CHAINS 8
+#define HR_PEAK_UNROLL 8
+__global__ void __launch_bounds__(1024, 2) int_peak_kernel(uint32_t *out, int iters, long long *cycles) {
+    uint32_t acc[HR_PEAK_CHAINS], a[HR_PEAK_CHAINS];
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+#pragma unroll
+    for (int j = 0; j < HR_PEAK_CHAINS; ++j) {
+        acc[j] = j;
+        a[j] = b ^ (0x01020408u * (j + 1));
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < HR_PEAK_UNROLL; ++u)
+#pragma unroll
+            for (int j = 0; j < HR_PEAK_CHAINS; ++j) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[j]) : "r"(a[j]), "r"(b));
+    }
+    const long long t1 = clock64();
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < HR_PEAK_CHAINS; ++j) x ^= acc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+/* Developer tap: packed-SAD issue rate of `device` (< 0: current). evalsPerSecond = thread-level VABSDIFF4.U8.ACC per
+ * second over the whole GPU by CUDA events (= candidate evaluations per second if the search did nothing but its
+ * SADs); warpInstrPerClkPerSm from the SM clock counter of the slowest CTA. Either pointer may be NULL. */
+extern "C" int hr_debug_int_peak(int device, double *evalsPerSecond, double *warpInstrPerClkPerSm) {
+    HrContext *ctx = NULL;
+    if (device < 0) CU(cudaGetDevice(&device));
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
+    uint32_t *out = NULL;
+    long long *cyc = NULL, *hcyc = (long long *)malloc(sizeof(long long) * blocks);
+    cudaEvent_t e0 = NULL, e1 = NULL;
+    cudaError_t e = hcyc ? cudaSuccess : cudaErrorMemoryAllocation;
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaMalloc(&out, (size_t)blocks * threads * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&cyc, (size_t)blocks * sizeof(long long));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        int_peak_kernel<<<blocks, threads>>>(out, 64, cyc); /* warm-up */
+        e = cudaEventRecord(e0, 0);
+        int_peak_kernel<<<blocks, threads>>>(out, iters, cyc);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess) e = cudaMemcpy(hcyc, cyc, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) {
+        const double perThread = (double)iters * HR_PEAK_UNROLL * HR_PEAK_CHAINS;
+        long long worst = 1;
+        for (int i = 0; i < blocks; ++i) worst = hcyc[i] > worst ? hcyc[i] : worst;
+        if (evalsPerSecond) *evalsPerSecond = perThread * blocks * threads / ((double)ms * 1e-3);
+        /* two 1024-thread CTAs per SM = 64 warps share the SM for `worst` cycles */
+        if (warpInstrPerClkPerSm) *warpInstrPerClkPerSm = perThread * 64.0 / (double)worst;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(out);
+    cudaFree(cyc);
+    free(hcyc);
+    if (e != cudaSuccess) return fail(NULL, "CUDA error in hr_debug_int_peak: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int hr_set_timeline(HrContext *ctx, int enable) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
@@ -469,14 +576,13 @@ static void launch_pack_t(HrContext *ctx, cudaStream_t st) {
 #undef HR_PCASE
         }
     } else {
-        const int bx = ctx->s <= 3 ? 128 : 64;
+        const int bx = ctx->s <= 3 ? 128 : 64; /* s <= 4 (hr_create): at most 64 x 16 threads */
         dim3 block(bx, 1 << ctx->s);
         dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
         pack_frame_kernel<T><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
     }
 }
 static int launch_pack(HrContext *ctx) {
-    if (ctx->s > 6) return fail(ctx, "frames of more than %d lines are not supported", MAX_CALC_RES << 6);
     cudaStream_t st = ctx->stream;
     const int id = ctx->packedId[1];
     if (pipe_on(ctx)) {
@@ -544,53 +650,67 @@ static int sync_all(HrContext *ctx) {
     return 0;
 }
 
+/* streams, events, the ring of flow buffers, the second search lane, the second output frame */
+static int pipeline_alloc(HrContext *ctx) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    /* the search is the critical path of a pair: its CTAs are placed first */
+    for (int i = 0; i < HR_SEARCH_LANES; ++i) CU(cudaStreamCreateWithPriority(&ctx->sSearch[i], cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
+    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
+        CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
+        for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) CU(cudaEventCreateWithFlags(&ctx->evWarp[b][i], cudaEventDisableTiming));
+    }
+    const size_t ln = (size_t)ctx->lw * ctx->lh;
+    /* the flow buffer in use becomes entry 0 of the ring, the search scratch in use lane 0 */
+    ctx->blurB[0] = ctx->blur;
+    ctx->blurXYB[0] = ctx->blurXY;
+    ctx->flowCur = 0;
+    for (int b = 1; b < HR_FLOW_BUFS; ++b) {
+        CU(cudaMalloc(&ctx->blurB[b], 2 * ln * sizeof(int16_t)));
+        CU(cudaMalloc(&ctx->blurXYB[b], ln * sizeof(uint32_t)));
+        CU(cudaMemset(ctx->blurB[b], 0, 2 * ln * sizeof(int16_t)));
+        CU(cudaMemset(ctx->blurXYB[b], 0, ln * sizeof(uint32_t)));
+    }
+    const size_t tw = (size_t)(ctx->tWords ? ctx->tWords : 32) * sizeof(unsigned long long);
+    const size_t bw = (size_t)(ctx->bigWords ? ctx->bigWords : 32) * sizeof(unsigned long long);
+    ctx->offL[0] = ctx->off;
+    ctx->TL[0] = ctx->T;
+    ctx->partialL[0] = ctx->partial;
+    ctx->lane = 0;
+    for (int l = 1; l < HR_SEARCH_LANES; ++l) {
+        CU(cudaMalloc(&ctx->offL[l], 2 * ln * sizeof(int16_t)));
+        CU(cudaMalloc(&ctx->TL[l], tw));
+        CU(cudaMalloc(&ctx->partialL[l], bw));
+        CU(cudaMemset(ctx->offL[l], 0, 2 * ln * sizeof(int16_t)));
+        CU(cudaMemset(ctx->TL[l], 0, tw));
+        CU(cudaMemset(ctx->partialL[l], 0, bw));
+    }
+    CU(cudaMalloc(&ctx->outBuf2, ctx->frameBytes));
+    CU(cudaMemset(ctx->outBuf2, 0, ctx->frameBytes));
+    ctx->deviceBytes += ctx->frameBytes;
+    ctx->deviceBytes += (HR_FLOW_BUFS - 1) * (2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t)) + (HR_SEARCH_LANES - 1) * (2 * ln * sizeof(int16_t) + tw + bw);
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
 extern "C" int hr_set_pipeline(HrContext *ctx, int enable) {
     if (!ctx) return 1;
     if (bind_device(ctx)) return 1;
     if (sync_all(ctx)) return 1;
-    if (enable && !ctx->sPack) {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        /* the search is the critical path of a pair: its CTAs are placed first */
-        for (int i = 0; i < HR_SEARCH_LANES; ++i) CU(cudaStreamCreateWithPriority(&ctx->sSearch[i], cudaStreamNonBlocking, hi));
-        CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
-        for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
-        CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
-        for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
-        for (int b = 0; b < HR_FLOW_BUFS; ++b) {
-            CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
-            for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) CU(cudaEventCreateWithFlags(&ctx->evWarp[b][i], cudaEventDisableTiming));
-        }
-        const size_t ln = (size_t)ctx->lw * ctx->lh;
-        /* the flow buffer in use becomes entry 0 of the ring, the search scratch in use lane 0 */
-        ctx->blurB[0] = ctx->blur;
-        ctx->blurXYB[0] = ctx->blurXY;
+    if (enable && !ctx->sPack && pipeline_alloc(ctx)) {
+        /* half a pipeline is none: give back what was created, stay in (or return to) the serial mode on ring entry 0 */
+        pipeline_release(ctx);
+        ctx->blur = ctx->blurB[0] ? ctx->blurB[0] : ctx->blur;
+        ctx->blurXY = ctx->blurXYB[0] ? ctx->blurXYB[0] : ctx->blurXY;
         ctx->flowCur = 0;
-        for (int b = 1; b < HR_FLOW_BUFS; ++b) {
-            CU(cudaMalloc(&ctx->blurB[b], 2 * ln * sizeof(int16_t)));
-            CU(cudaMalloc(&ctx->blurXYB[b], ln * sizeof(uint32_t)));
-            CU(cudaMemset(ctx->blurB[b], 0, 2 * ln * sizeof(int16_t)));
-            CU(cudaMemset(ctx->blurXYB[b], 0, ln * sizeof(uint32_t)));
-        }
-        const size_t tw = (size_t)(ctx->tWords ? ctx->tWords : 32) * sizeof(unsigned long long);
-        const size_t bw = (size_t)(ctx->bigWords ? ctx->bigWords : 32) * sizeof(unsigned long long);
-        ctx->offL[0] = ctx->off;
-        ctx->TL[0] = ctx->T;
-        ctx->partialL[0] = ctx->partial;
         ctx->lane = 0;
-        for (int l = 1; l < HR_SEARCH_LANES; ++l) {
-            CU(cudaMalloc(&ctx->offL[l], 2 * ln * sizeof(int16_t)));
-            CU(cudaMalloc(&ctx->TL[l], tw));
-            CU(cudaMalloc(&ctx->partialL[l], bw));
-            CU(cudaMemset(ctx->offL[l], 0, 2 * ln * sizeof(int16_t)));
-            CU(cudaMemset(ctx->TL[l], 0, tw));
-            CU(cudaMemset(ctx->partialL[l], 0, bw));
-        }
-        CU(cudaMalloc(&ctx->outBuf2, ctx->frameBytes));
-        CU(cudaMemset(ctx->outBuf2, 0, ctx->frameBytes));
-        ctx->deviceBytes += ctx->frameBytes;
-        ctx->deviceBytes += (HR_FLOW_BUFS - 1) * (2 * ln * sizeof(int16_t) + ln * sizeof(uint32_t)) + (HR_SEARCH_LANES - 1) * (2 * ln * sizeof(int16_t) + tw + bw);
-        CU(cudaDeviceSynchronize());
+        ctx->pipeline = 0;
+        cudaGetLastError();
+        return 1;
     }
     ctx->pipeline = enable ? 1 : 0;
     ctx->specWarp.valid = ctx->specFlow.valid = 0;
@@ -1107,10 +1227,12 @@ extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int 
         ctx->bandRow1[r] = row1[r];
     }
     if (expect != ctx->H) return fail(ctx, "hr_band_configure: the bands cover %d rows, the frame has %d", expect, ctx->H);
-    if (!ctx->mail) {
-        CU(cudaMalloc(&ctx->mail, 256));
-        CU(cudaMemset(ctx->mail, 0, 256));
-    }
+    /* a (re)configuration restarts the frame count: every rank of the group reconfigures together, the mailbox
+     * counters start from zero again once nothing of the old stream is in flight */
+    if (sync_all(ctx)) return 1;
+    if (!ctx->mail) CU(cudaMalloc(&ctx->mail, 256));
+    CU(cudaMemset(ctx->mail, 0, 256));
+    CU(cudaDeviceSynchronize());
     ctx->bandWorld = world;
     ctx->bandRank = rank;
     ctx->bandFrames = 0;

@@ -51,19 +51,47 @@ int hrControlApply(struct OpticalFlowCalc *ofc, HrControlState *st, int code) {
     return 0;
 }
 
+/* one line of the channel: complete lines are applied; `last` without a terminator is parked in the state */
+static int control_line(struct OpticalFlowCalc *ofc, HrControlState *st, const char *line, size_t len) {
+    char text[sizeof(st->pending) + 4];
+    if (len >= sizeof(text)) len = sizeof(text) - 1; /* a code has at most six digits: the tail of a longer line carries nothing */
+    memcpy(text, line, len);
+    text[len] = '\0';
+    const int code = hrControlParse(text);
+    return code >= 0 && hrControlApply(ofc, st, code) == 0;
+}
+
 int hrControlPoll(int fd, struct OpticalFlowCalc *ofc, HrControlState *st) {
-    char buf[512];
+    char buf[512 + sizeof(st->pending)];
     int applied = 0;
+    if (!ofc || !st) return -1;
+    if (st->pendingLength < 0 || st->pendingLength > (int)sizeof(st->pending)) st->pendingLength = 0;
     for (;;) {
-        const ssize_t n = read(fd, buf, sizeof(buf) - 1);
+        /* what the previous read left unfinished goes in front of what this one brings */
+        size_t have = (size_t)st->pendingLength;
+        memcpy(buf, st->pending, have);
+        const ssize_t n = read(fd, buf + have, 512);
         if (n < 0) return (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) ? applied : -1;
-        if (n == 0) return applied;
-        buf[n] = '\0';
-        for (char *line = strtok(buf, "\r\n"); line; line = strtok(NULL, "\r\n")) {
-            const int code = hrControlParse(line);
-            if (code >= 0 && hrControlApply(ofc, st, code) == 0) ++applied;
+        if (n == 0) { /* end of file: the writer will not finish the line */
+            if (have) applied += control_line(ofc, st, buf, have);
+            st->pendingLength = 0;
+            return applied;
         }
-        if ((size_t)n < sizeof(buf) - 1) return applied;
+        have += (size_t)n;
+        size_t start = 0;
+        for (size_t i = 0; i < have; ++i) {
+            if (buf[i] == '\n' || buf[i] == '\r') {
+                if (i > start) applied += control_line(ofc, st, buf + start, i - start);
+                start = i + 1;
+            }
+        }
+        size_t rest = have - start;
+        if (rest > sizeof(st->pending)) { /* no code is that long: keep its head, which is all hrControlParse looks at */
+            rest = sizeof(st->pending);
+        }
+        memcpy(st->pending, buf + start, rest);
+        st->pendingLength = (int)rest;
+        if (n < 512) return applied;
     }
 }
 

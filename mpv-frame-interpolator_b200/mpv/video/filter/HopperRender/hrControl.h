@@ -30,6 +30,9 @@ typedef struct HrControlState {
     int frameOutputMode;     /* enum FrameOutput, 0 .. 6                                               */
     int restartCounters;     /* set when code 0 arrives: sourceFrameNum, interpolatedFrameNum, blendingScalar := 0 */
     int pinnedRadius;        /* 0: the filter's timing rule moves the radius; otherwise keep this one  */
+    /* hrControlPoll: a line cut in two by the end of a read is kept here until its rest arrives        */
+    int pendingLength;
+    char pending[28];
 } HrControlState;
 
 /* first decimal integer of a text line, as the applet channel reads it (a line that does not start with a digit
@@ -37,8 +40,9 @@ typedef struct HrControlState {
 int hrControlParse(const char *text);
 /* apply one code; returns 0 when the code is known, 1 otherwise (state untouched) */
 int hrControlApply(struct OpticalFlowCalc *ofc, HrControlState *st, int code);
-/* read whatever is waiting on fd (non-blocking descriptors welcome), apply every complete line; returns the number
- * of codes applied, -1 on a read error other than "nothing there" */
+/* read whatever is waiting on fd (non-blocking descriptors welcome), apply every complete line; an unfinished last
+ * line waits in the state for the next call (at end of file it is applied as it is); returns the number of codes
+ * applied, -1 on a read error other than "nothing there" */
 int hrControlPoll(int fd, struct OpticalFlowCalc *ofc, HrControlState *st);
 /* the status text the applet's widget shows (reference :188-207), for whoever wants to display it; returns the length */
 int hrControlStatus(char *buf, size_t size, const struct OpticalFlowCalc *ofc, double targetFrameTime, double sourceFrameTime, double playbackSpeed,

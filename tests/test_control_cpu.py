@@ -67,6 +67,33 @@ def test_poll_reads_lines_from_a_pipe(hr, ctl):
     assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == -1           # a real read error
 
 
+def test_poll_keeps_a_line_cut_by_the_end_of_a_read(hr, ctl):
+    """A code split over two reads ('455' arriving as '45' and '5\\n') must not be taken for two codes."""
+    ofc, st = _fresh(hr)
+    r, w = os.pipe()
+    os.set_blocking(r, False)
+    os.write(w, b"3\n45")
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 1 and st.frameOutputMode == 1
+    assert ofc.outputWhiteLevel == 255.0                                     # '45' is not a code yet
+    os.write(w, b"5\n70")
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 1 and ofc.outputWhiteLevel == 55.0 and st.frameOutputMode == 1
+    os.write(w, b"4")
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 0 and ofc.deltaScalar == 8
+    os.close(w)                                                              # end of file finishes the last line
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 1 and ofc.deltaScalar == 4
+    os.close(r)
+    # a read that ends exactly on the buffer size boundary and a long run of junk
+    ofc, st = _fresh(hr)
+    r, w = os.pipe()
+    os.set_blocking(r, False)
+    os.write(w, b"x" * 700 + b"\n" + b"6\n" * 300 + b"81")
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 300 and st.frameOutputMode == 4
+    os.write(w, b"2\n")
+    assert ctl.hrControlPoll(r, C.byref(ofc), C.byref(st)) == 1 and ofc.neighborBiasScalar == 12
+    os.close(w)
+    os.close(r)
+
+
 def test_status_text(hr, ctl):
     ofc, st = _fresh(hr)
     ofc.frameWidth, ofc.frameHeight, ofc.opticalFlowResScalar = 1920, 1080, 2

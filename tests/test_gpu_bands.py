@@ -1,7 +1,10 @@
 """Spatial bands: a frame stream split over N contexts must produce exactly the frames
-of the single-context path — same flow on every rank, every output row bit-identical. Runs with the
-bands on distinct GPUs when the box has them (gpurun --gpus 2), else with N contexts on one GPU (the
-protocol's one-thread wait kernels are then always preceded by their signal in stream order)."""
+of the single-context path — same flow on every rank, every output row bit-identical.
+
+placement "distinct": one band per GPU (peer access over NVLink); SKIPPED with a reason on a box with fewer GPUs than
+bands (run it under `gpurun --gpus 2` / `--gpus 4`; log kept under profiles/). placement "one-gpu": all band contexts
+on GPU 0 — says so in its id — which exercises the row bookkeeping and the mailbox kernels in stream order, not
+NVLink. The two-process CUDA-IPC form is tests/test_gpu_bands_ipc.py."""
 import ctypes
 
 import numpy as np
@@ -18,10 +21,18 @@ def _ndev():
     return n.value
 
 
+@pytest.mark.parametrize("placement", ["distinct", "one-gpu"])
 @pytest.mark.parametrize("w,h,pixfmt,world", [(1920, 1080, 0, 2), (1920, 1080, 0, 4), (3840, 2160, 1, 2), (1280, 720, 0, 3)])
-def test_banded_stream_equals_single_context(hr, synth, w, h, pixfmt, world):
+def test_banded_stream_equals_single_context(hr, synth, w, h, pixfmt, world, placement):
     nd = _ndev()
-    devices = [r % nd for r in range(world)]
+    if placement == "distinct":
+        if nd < world:
+            pytest.skip("%d bands on distinct GPUs need %d GPUs, this box has %d (run under gpurun --gpus %d)" % (world, world, nd, world))
+        devices = list(range(world))
+    else:
+        if world > 2 and pixfmt == 0 and h == 1080:
+            pytest.skip("one-GPU protocol check: the 2- and 3-band cases are enough")
+        devices = [0] * world
     c = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
     single = hr.HrCuda(h, w, w, pixfmt, 0)
     bands = hr.BandGroup(h, w, w, pixfmt, devices)

@@ -1,7 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle
 on the same seeded inputs. Integer flow offsets must be bit-exact; NV12 pixels must be equal for
 the non-HSV modes (the CUDA kernels round after every float operation exactly like the oracle)
-and within +-1 LSB for HSV (atan2f/fmodf implementations differ); P010 within +-4 LSB10.
+and within +-1 LSB for HSV (atan2f/fmodf implementations differ); P010 likewise identical (the oracle implements the
+same P010 definition), HSV within one 8-bit step.
 """
 import numpy as np
 import pytest
@@ -199,7 +200,10 @@ def test_p010_flow_and_warp(hr, oracle, synth):
     msgs = []
     for mode in range(7):
         gy, guv, oy, ouv = _warp_both(g, o, 0.4, mode)
-        tol = 4 * 64  # +-4 LSB of the 10-bit value, MSB-aligned in 16 bits
+        # oracle and CUDA implement the same P010 definition: identical, except the HSV hue (atan2f of
+        # libm vs CUDA: one 8-bit step, stored << 8). north_star's +-4 LSB10 is the bound against a 16-bit reading of
+        # the reference; against our own oracle anything but 0 would hide a regression.
+        tol = 256 if mode == 3 else 0
         for nm, a, b in (("Y", gy, oy), ("UV", guv, ouv)):
             r = _diff_report("P010 mode %d %s" % (mode, nm), a, b, tol)
             if r:
@@ -290,7 +294,7 @@ def test_p010_levels_and_large_flow(hr, oracle, synth, w, h):
     g, o = _run_pair(hr, oracle, noisy[0], noisy[1], h, w, w, 5, pixfmt=1)
     _assert_flow_equal(g, o)
     msgs = []
-    tol = 4 * 64
+    tol = 0
     for black, white in ((0.0, 255.0), (16.0, 219.0), (10.0, 219.0), (30.0, 255.0)):
         for mode in (2, 5):
             gy, guv, oy, ouv = _warp_both(g, o, 0.6, mode, black, white)
