@@ -132,6 +132,12 @@ int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighbor
  * black/white are outputBlackLevel/outputWhiteLevel (HR/opticalFlowCalc.c:225-226). Enqueue-only. */
 int hr_warp(HrContext *ctx, float blendingScalar, int frameOutputMode, float blackLevel, float whiteLevel);
 
+/* The same K5 for several output frames of the current pair at once (what the filter asks for one after the other,
+ * HR/vf_HopperRender.c:357-405: 2 or 3 per source frame at 24->60, up to 6 at 24->144): warp i with blendingScalars[i]
+ * into the caller-owned DEVICE planes outY[i] / outUV[i], one kernel launch for up to 8 of them. Enqueue-only. */
+int hr_warp_batch(HrContext *ctx, int nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel, float whiteLevel,
+                  void *const *outY, void *const *outUV);
+
 /* ---- downloadFrame, HR/opticalFlowCalc.c:109-124: blocking copy of the output frame to HOST
  * planes; `seconds` (may be NULL) receives warp-start -> download-end (= warpCalcTime). */
 int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds);

@@ -59,6 +59,7 @@ ABI = {
                                   C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_calc_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "hr_warp": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]),
+    "hr_warp_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -230,6 +231,14 @@ class HrCuda:
 
     def warp(self, t, mode=BlendedFrame, black=0.0, white=255.0):
         self._chk(self.lib.hr_warp(self.h, float(t), int(mode), float(black), float(white)))
+
+    def warp_batch(self, ts, outs, mode=BlendedFrame, black=0.0, white=255.0):
+        """len(ts) output frames of the current pair into outs[i] = (dY, dUV) (device planes), one launch per 8."""
+        n = len(ts)
+        tarr = (C.c_float * max(n, 1))(*[float(t) for t in ts])
+        oy = (C.c_void_p * max(n, 1))(*[_ptr(o[0]).value for o in outs[:n]])
+        ouv = (C.c_void_p * max(n, 1))(*[_ptr(o[1]).value for o in outs[:n]])
+        self._chk(self.lib.hr_warp_batch(self.h, n, tarr, int(mode), float(black), float(white), oy, ouv))
 
     def download(self, y=None, uv=None):
         H, W = self.info.frameHeight, self.info.frameWidth

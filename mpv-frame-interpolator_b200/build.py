@@ -64,7 +64,7 @@ def build_cuda(force=False, verbose_ptxas=False):
 def build_host(force=False):
     """The reference-language (C) host: opticalFlowCalc.c forwarding to the C ABI, hrReplay.c (the filter's call
     order as a loop) and hrControl.c. (The mpv-runtime stand-in that runs the reference's own filter source on top of
-    this layer is test infrastructure: oracle/filter_host_sim.c, built by oracle/build_ref.py.)"""
+    this layer is test infrastructure and is built by the test tree, not from here.)"""
     build_cuda()
     srcs = [HOSTC / "opticalFlowCalc.c", HOSTC / "hrReplay.c", HOSTC / "hrControl.c", HOSTC / "hrControl.h", HOSTC / "opticalFlowCalc.h", HOSTC / "config.h"]
     if force or not _newer(OFC_LIB, srcs):

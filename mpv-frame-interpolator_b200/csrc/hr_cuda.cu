@@ -25,6 +25,10 @@
 #define HR_FLOW_BUFS 4   /* blurred-flow ring: one being written per search lane, the rest read by warps in flight */
 #define HR_SEARCH_LANES 2
 #define HR_MAX_WARP_EVENTS 8
+#ifndef HR_WARP_ROWS
+#define HR_WARP_ROWS 4
+#endif
+#define HR_WARP_ROWS_DEFAULT HR_WARP_ROWS
 
 struct HrContext {
     int H, W, aW, pixfmt, bps;
@@ -103,6 +107,11 @@ struct HrContext {
         cudaEvent_t done; /* not owned: the flow-buffer reader event of the launch */
     } specWarp;
     uint8_t *outBuf2;      /* second internal output frame: what is warped ahead goes here                  */
+    /* HSV output mode: flow colours per lattice cell, by flow buffer (built lazily, once per flow) */
+    uint32_t *colours[HR_FLOW_BUFS];
+    cudaEvent_t evColour[HR_FLOW_BUFS];
+    unsigned long long flowSerial[HR_FLOW_BUFS], colourSerial[HR_FLOW_BUFS]; /* content stamps: flow buffer / its colour table */
+    unsigned long long flowStamp;
     float lastT, lastDelta, lastBlack, lastWhite;
     int lastWarpFrames, lastMode, aheadOn;
 
@@ -240,6 +249,10 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaFree(ctx->T);
     cudaFree(ctx->partial);
     cudaFree(ctx->trace);
+    for (int b = 0; b < HR_FLOW_BUFS; ++b) {
+        cudaFree(ctx->colours[b]);
+        if (ctx->evColour[b]) cudaEventDestroy(ctx->evColour[b]);
+    }
     cudaFree(ctx->mail);
     cudaFree(ctx->timeline);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
@@ -868,6 +881,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     }
     ctx->launches++;
     ctx->flowCur = fb;
+    ctx->flowSerial[fb] = ++ctx->flowStamp;
     ctx->blur = ctx->blurB[fb];
     ctx->blurXY = ctx->blurXYB[fb];
     ctx->lane = lane;
@@ -934,15 +948,55 @@ static int device_rcp(HrContext *ctx, const float *den, float *out) {
     return 0;
 }
 
+/* (v, v) as one 64-bit word of two fp32 */
+static F2 pair_f32(float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return ((F2)b << 32) | b;
+}
+
 template <typename T>
-static int launch_warp(HrContext *ctx, float t, int mode, float black, float white) {
+static void launch_wide16(dim3 grid, dim3 block, cudaStream_t st, const WarpParams<T> &P, const WarpFastArgs &A, const WarpBatch &B);
+template <>
+void launch_wide16<uint8_t>(dim3 grid, dim3 block, cudaStream_t st, const WarpParams<uint8_t> &P, const WarpFastArgs &A, const WarpBatch &B) {
+    warp_fast_kernel<uint8_t, HR_WARP_ROWS_DEFAULT, 16><<<grid, block, 0, st>>>(P, A, B);
+}
+template <>
+void launch_wide16<uint16_t>(dim3, dim3, cudaStream_t, const WarpParams<uint16_t> &, const WarpFastArgs &, const WarpBatch &) {} /* 32-byte units are not built */
+
+/* flow colours of the HSV mode for flow buffer fb (hr_warp.cuh): built once per flow, on the stream of the first warp
+ * that needs them; later warps of the same flow on other streams wait for evColour[fb] */
+static int ensure_colours(HrContext *ctx, int fb, cudaStream_t st) {
+    const int ln = ctx->lw * ctx->lh;
+    if (!ctx->colours[fb]) {
+        CU(cudaMalloc(&ctx->colours[fb], (size_t)ln * sizeof(uint32_t)));
+        ctx->deviceBytes += (size_t)ln * sizeof(uint32_t);
+        ctx->colourSerial[fb] = ~0ull; /* nothing built yet */
+    }
+    if (!ctx->evColour[fb]) CU(cudaEventCreateWithFlags(&ctx->evColour[fb], cudaEventDisableTiming));
+    if (ctx->colourSerial[fb] != ctx->flowSerial[fb]) {
+        flow_colour_kernel<<<(ln + 255) / 256, 256, 0, st>>>(ctx->blurXY, ctx->colours[fb], ln, ctx->s <= 2 ? 4 : 1); /* fb is the current flow buffer */
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->evColour[fb], st));
+        ctx->colourSerial[fb] = ctx->flowSerial[fb];
+        ctx->launches++;
+    } else {
+        CU(cudaStreamWaitEvent(st, ctx->evColour[fb], 0));
+    }
+    return 0;
+}
+
+/* K5 for n output frames of the current pair (same mode and levels, blend scalars ts[i], planes outY[i] / outUV[i]):
+ * one launch per HR_WARP_BATCH outputs when the fast kernel applies, one per output otherwise */
+template <typename T>
+static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY, void *const *outUV, int mode, float black, float white, int warpStream) {
     WarpParams<T> P;
     P.f1y = (const T *)ctx->fy[0];
     P.f1uv = (const T *)ctx->fuv[0];
     P.f2y = (const T *)ctx->fy[1];
     P.f2uv = (const T *)ctx->fuv[1];
-    P.outY = (T *)ctx->outY;
-    P.outUV = (T *)ctx->outUV;
+    P.outY = (T *)outY[0];
+    P.outUV = (T *)outUV[0];
     P.flow = ctx->blur;
     P.flowXY = ctx->blurXY;
     P.lw = ctx->lw;
@@ -952,16 +1006,13 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     P.aW = ctx->aW;
     P.s = ctx->s;
     P.mode = mode;
-    P.t12 = t;            /* opticalFlowCalc.c:215-216, float */
-    P.t21 = 1.0f - t;
+    P.t12 = ts[0];            /* opticalFlowCalc.c:215-216, float */
+    P.t21 = 1.0f - ts[0];
     P.black = black;
     P.white = white;
-    /* thread = 4 samples x 4 rows (cells of 8 rows and more are covered by several threads: measured, smaller
-     * units and more resident warps beat fewer flow look-ups per sample: 8K P010 74 -> 67 us); row groups of the
-     * luma plane, then of the chroma plane */
-#ifndef HR_WARP_ROWS
-#define HR_WARP_ROWS 4
-#endif
+    /* thread = UW samples x 4 rows (cells of 8 rows and more are covered by several threads: measured, smaller
+     * units and more resident warps beat fewer flow look-ups per sample); row groups of the luma plane, then of the
+     * chroma plane */
     const int ROWS = HR_WARP_ROWS;
     int r0 = 0, r1 = ctx->H;
     if (ctx->bandWorld > 1) {
@@ -975,10 +1026,11 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
     A.lumaGroups = (r1 + ROWS - 1) / ROWS - A.lumaG0;
     A.chromaG0 = (r0 >> 1) / ROWS;
     A.chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - A.chromaG0;
+    A.white = white;
     const int groups = A.lumaGroups + A.chromaGN;
-    /* level constants (hr_warp.cuh: 8-bit = the reference's expressions as NVIDIA OpenCL compiles them; 16-bit =
-     * DESIGN.md §P010, correctly rounded reciprocals) */
-    const bool is16 = sizeof(T) == 2;
+    /* level constants (hr_warp.cuh: 8-bit = the reference's expressions as NVIDIA OpenCL compiles them — also what the
+     * HSV mode of P010 uses; 16-bit = DESIGN.md §P010, correctly rounded reciprocals) */
+    const bool is16 = sizeof(T) == 2 && mode != HR_MODE_HSV_FLOW;
     volatile float b16 = black / 255.0f, w16 = white / 255.0f;
     b16 = b16 * 65472.0f;
     w16 = w16 * 65472.0f;
@@ -1012,35 +1064,87 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
             }
             const float mn = fminf(lo, hi), mx = fmaxf(lo, hi);
             A.clampNeeded[c] = !(mn >= 0.0f && mx < (is16 ? 65536.0f : 256.0f));
+            /* the same constants as fp32 pairs (hr_warp_fast.cuh, blend_pair) */
+            volatile float msub = HR_MAGIC + A.sub[c];
+            A.lc[c].rcp = pair_f32(rc);
+            A.lc[c].mul = pair_f32(outMax);
+            A.lc[c].add = pair_f32(mid);
+            A.lc[c].negSub = pair_f32(-A.sub[c]);
+            A.lc[c].negMsub = pair_f32(-msub);
+            A.lc[c].lo = 0.0f;
+            A.lc[c].hi = outMax;
         }
     }
-    /* the block path: blocks inside one lattice cell, aligned 32/64-bit accesses, blend scalars in [0,1], level
-     * denominators for which div.full.f32 is MUFU.RCP * x (hr_warp.cuh) */
-    const int fast = ctx->useFastWarp && ctx->s >= 2 && (mode <= 2 || mode == 5) && (ctx->W % 4 == 0) && t >= 0.0f && t <= 1.0f && denOk &&
-                     ctx->H >= 2 * (ROWS + 2) && ctx->aW >= 8 &&
-                     (((uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv | (uintptr_t)P.outY | (uintptr_t)P.outUV) % 8 == 0);
+    A.negM = pair_f32(-HR_MAGIC);
+    A.M = pair_f32(HR_MAGIC);
+    /* The unit of the fast kernel: as wide as a lattice cell, at most 16 bytes per row; every plane and the row pitch
+     * aligned to it, blend scalars in [0,1], level denominators for which div.full.f32 is MUFU.RCP * x (hr_warp.cuh).
+     * A frame that misses the wide unit's alignment falls back to the 4-sample unit, then to the per-sample kernel. */
+    uintptr_t align = (uintptr_t)P.f1y | (uintptr_t)P.f1uv | (uintptr_t)P.f2y | (uintptr_t)P.f2uv;
+    int tsOk = 1;
+    for (int i = 0; i < n; ++i) {
+        align |= (uintptr_t)outY[i] | (uintptr_t)outUV[i];
+        tsOk = tsOk && ts[i] >= 0.0f && ts[i] <= 1.0f;
+    }
+    int uw = ctx->s == 2 ? 4 : (ctx->s == 3 ? 8 : (sizeof(T) == 2 ? 8 : 16));
+    const char *uwEnv = getenv("HR_WARP_UNIT"); /* developer knob: force a narrower unit */
+    if (uwEnv && atoi(uwEnv) >= 4 && atoi(uwEnv) < uw) uw = atoi(uwEnv) >= 8 ? 8 : 4;
+    for (; uw >= 4; uw >>= 1) {
+        const uintptr_t ub = (uintptr_t)uw * sizeof(T);
+        if (ctx->W % uw == 0 && ctx->aW >= 2 * uw && align % ub == 0) break;
+    }
+    const int fast = ctx->useFastWarp && ctx->s >= 2 && uw >= 4 && mode != HR_MODE_SIDE_BY_SIDE_2 && tsOk && denOk && ctx->H >= 2 * (ROWS + 2);
     /* pipelined: warps into caller-owned planes are independent of one another -> round-robin over the warp
      * streams, each after the search that produced the flow; warps into the internal output frame stay on the
      * main stream (the download that follows is ordered there) */
     const int pl = pipe_on(ctx), fb = ctx->flowCur;
     cudaStream_t st = ctx->stream;
     if (pl) {
-        if (ctx->outY == ctx->outBuf2) st = ctx->sWarp[0]; /* warped ahead: one stream, so that they never overlap one another */
-        else if (ctx->outY != ctx->outBuf) st = ctx->sWarp[ctx->warpRR++ % HR_WARP_STREAMS];
+        if (warpStream == 2) st = ctx->sWarp[0]; /* warped ahead: one stream, so that they never overlap one another */
+        else if (warpStream == 1) st = ctx->sWarp[ctx->warpRR++ % HR_WARP_STREAMS];
         if (ctx->haveSearch[fb]) CU(cudaStreamWaitEvent(st, ctx->evSearch[fb], 0));
         else CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
     }
+    if (fast && mode == HR_MODE_HSV_FLOW) {
+        if (ensure_colours(ctx, fb, st)) return 1;
+        A.colours = ctx->colours[fb];
+    }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[2], st));
     if (fast) {
-        dim3 block(32, 4);
-        dim3 grid((ctx->aW + 127) / 128, (groups + 3) / 4);
-        warp_fast_kernel<T, HR_WARP_ROWS><<<grid, block, 0, st>>>(P, A);
+        for (int i0 = 0; i0 < n; i0 += HR_WARP_BATCH) {
+            WarpBatch B;
+            memset(&B, 0, sizeof(B));
+            B.n = n - i0 < HR_WARP_BATCH ? n - i0 : HR_WARP_BATCH;
+            for (int i = 0; i < B.n; ++i) {
+                volatile float t12 = ts[i0 + i], t21 = 1.0f - t12, mt = HR_MAGIC * t12;
+                B.t12[i] = t12;
+                B.t21[i] = t21;
+                B.t12x2[i] = pair_f32(t12);
+                B.t21x2[i] = pair_f32(t21);
+                B.negMt12[i] = pair_f32(-mt);
+                B.outY[i] = outY[i0 + i];
+                B.outUV[i] = outUV[i0 + i];
+            }
+            dim3 block(32, 4);
+            dim3 grid((ctx->aW + 32 * uw - 1) / (32 * uw), (groups + 3) / 4, B.n);
+            if (uw == 4) warp_fast_kernel<T, HR_WARP_ROWS, 4><<<grid, block, 0, st>>>(P, A, B);
+            else if (uw == 8) warp_fast_kernel<T, HR_WARP_ROWS, 8><<<grid, block, 0, st>>>(P, A, B);
+            else launch_wide16<T>(grid, block, st, P, A, B);
+            ctx->launches++;
+        }
     } else {
         /* per-sample kernel, row groups of 4 */
         const int lg0 = r0 / 4, lgn = (r1 + 3) / 4 - lg0, cg0 = (r0 >> 1) / 4, cgn = ((r1 >> 1) + 3) / 4 - cg0;
         dim3 block(32, 8);
         dim3 grid((ctx->aW + 127) / 128, (lgn + cgn + 7) / 8);
-        warp_generic_kernel<T><<<grid, block, 0, st>>>(P, lgn, lg0, cg0, cgn);
+        for (int i = 0; i < n; ++i) {
+            P.t12 = ts[i];
+            P.t21 = 1.0f - ts[i];
+            P.outY = (T *)outY[i];
+            P.outUV = (T *)outUV[i];
+            warp_generic_kernel<T><<<grid, block, 0, st>>>(P, lgn, lg0, cg0, cgn);
+            ctx->launches++;
+        }
     }
     CU(cudaGetLastError());
     if (ctx->profiling) {
@@ -1054,8 +1158,18 @@ static int launch_warp(HrContext *ctx, float t, int mode, float black, float whi
         }
         CU(cudaEventRecord(ctx->evWarp[fb][ctx->nWarpEv[fb]++], st));
     }
-    ctx->launches++;
     return 0;
+}
+/* which stream a warp launch goes to in pipelined mode: internal output frame -> main stream (0), caller-owned planes ->
+ * round robin (1), the frame warped ahead -> its own stream (2) */
+static int warp_stream_kind(const HrContext *ctx) {
+    if (ctx->outY == ctx->outBuf2) return 2;
+    return ctx->outY != ctx->outBuf ? 1 : 0;
+}
+static int launch_warp_one(HrContext *ctx, float t, int mode, float black, float white) {
+    void *oy = ctx->outY, *ouv = ctx->outUV;
+    const int kind = warp_stream_kind(ctx);
+    return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, 1, &t, &oy, &ouv, mode, black, white, kind) : launch_warp<uint16_t>(ctx, 1, &t, &oy, &ouv, mode, black, white, kind);
 }
 
 extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float white) {
@@ -1094,7 +1208,7 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
             }
         }
     }
-    return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, t, mode, black, white) : launch_warp<uint16_t>(ctx, t, mode, black, white);
+    return launch_warp_one(ctx, t, mode, black, white);
 }
 
 /* hr_download, after its copy has been enqueued: warp the frame the pacing will most likely ask for next */
@@ -1107,8 +1221,7 @@ static int warp_ahead(HrContext *ctx) {
     void *keepY = ctx->outY, *keepUV = ctx->outUV;
     ctx->outY = ctx->outBuf2;
     ctx->outUV = ctx->outBuf2 + (size_t)ctx->H * ctx->W * ctx->bps;
-    const int rc = ctx->bps == 1 ? launch_warp<uint8_t>(ctx, tp, ctx->lastMode, ctx->lastBlack, ctx->lastWhite)
-                                 : launch_warp<uint16_t>(ctx, tp, ctx->lastMode, ctx->lastBlack, ctx->lastWhite);
+    const int rc = launch_warp_one(ctx, tp, ctx->lastMode, ctx->lastBlack, ctx->lastWhite);
     ctx->outY = keepY;
     ctx->outUV = keepUV;
     if (rc) return 1;
@@ -1133,19 +1246,24 @@ extern "C" int hr_step_device(HrContext *ctx, const void *dY, const void *dUV, i
     if (hr_update_frame_device(ctx, dY, dUV, borrow)) return 1;
     if (ctx->framesSeen < 2) return 0; /* the first frame of a stream has no partner yet (vf_HopperRender.c:490-495) */
     if (hr_calc_flow(ctx, searchRadius, deltaScalar, neighborBiasScalar, NULL)) return 1;
-    void *keepY = ctx->outY, *keepUV = ctx->outUV;
-    int rc = 0;
-    for (int i = 0; i < nWarps && !rc; ++i) {
-        if (!outY[i] || !outUV[i]) rc = fail(ctx, "hr_step_device: NULL output plane");
-        else {
-            ctx->outY = outY[i];
-            ctx->outUV = outUV[i];
-            rc = hr_warp(ctx, blendingScalars[i], frameOutputMode, blackLevel, whiteLevel);
-        }
+    return hr_warp_batch(ctx, nWarps, blendingScalars, frameOutputMode, blackLevel, whiteLevel, outY, outUV);
+}
+
+/* n output frames of the current pair into caller-owned device planes, one launch (include/hopperrender_cuda.h) */
+extern "C" int hr_warp_batch(HrContext *ctx, int nWarps, const float *blendingScalars, int frameOutputMode, float blackLevel, float whiteLevel,
+                             void *const *outY, void *const *outUV) {
+    if (!ctx) return 1;
+    if (nWarps < 0 || (nWarps > 0 && (!blendingScalars || !outY || !outUV))) return fail(ctx, "hr_warp_batch: bad warp list");
+    if (frameOutputMode < 0 || frameOutputMode > 6) return fail(ctx, "hr_warp_batch: unknown output mode %d", frameOutputMode);
+    for (int i = 0; i < nWarps; ++i) {
+        if (blendingScalars[i] > 1.0f) return fail(ctx, "hr_warp_batch: blending scalar %f is greater than 1.0", (double)blendingScalars[i]); /* opticalFlowCalc.c:209-212 */
+        if (!outY[i] || !outUV[i]) return fail(ctx, "hr_warp_batch: NULL output plane");
     }
-    ctx->outY = keepY;
-    ctx->outUV = keepUV;
-    return rc;
+    if (nWarps == 0) return 0;
+    if (bind_device(ctx)) return 1;
+    if (!ctx->pipeline && ctx->sPack && pipe_join(ctx)) return 1; /* leftovers of an earlier pipelined phase */
+    return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, nWarps, blendingScalars, outY, outUV, frameOutputMode, blackLevel, whiteLevel, 1)
+                         : launch_warp<uint16_t>(ctx, nWarps, blendingScalars, outY, outUV, frameOutputMode, blackLevel, whiteLevel, 1);
 }
 
 /* nSteps consecutive source frames in one call (hr_step_device in a loop): warps of step i use
@@ -1432,6 +1550,7 @@ extern "C" int hr_set_blurred_offsets(HrContext *ctx, const int16_t *blurred) {
     ctx->specWarp.valid = 0;
     if (sync_all(ctx)) return 1;
     CU(cudaMemcpy(ctx->blur, blurred, n, cudaMemcpyHostToDevice));
+    ctx->flowSerial[ctx->flowCur] = ++ctx->flowStamp;
     const int ln = ctx->lw * ctx->lh;
     pack_flow_kernel<<<(ln + 255) / 256, 256, 0, ctx->stream>>>(ctx->blur, ctx->blurXY, ln);
     CU(cudaGetLastError());

@@ -1,25 +1,30 @@
 /*
- * hr_warp_fast.cuh — K5 (warpFrameKernel.cl:114-182) for the cases a player produces: output modes 0, 1,
- * 2 and 5, resolution scalar >= 2 (every frame taller than 540 lines), planes aligned to 8 bytes, level
- * knobs for which the reference's division is MUFU.RCP * x. Everything else runs warp_generic_kernel
- * (hr_warp.cuh), which computes the same numbers one sample at a time.
+ * hr_warp_fast.cuh — K5 (warpFrameKernel.cl:114-182) for the cases a player produces: output modes 0..5, resolution
+ * scalar >= 2 (every frame taller than 540 lines), planes and strides aligned to the access width, level knobs for
+ * which the reference's division is MUFU.RCP * x. Everything else runs warp_generic_kernel (hr_warp.cuh), which
+ * computes the same numbers one sample at a time.
  *
- * HBM-bound by nature (2 frames read, 1 written, 518 KB of flow), issue-bound in practice: the work per
- * output sample is two byte->float conversions, the blend, two truncations and the level map. The kernel
- * is organised around the instruction count:
- *   - thread = 4 samples x 4 rows inside ONE lattice cell, so that
- *     the flow vector, the flipped vector (warpFrameKernel.cl:155-156), the four roundings and every
- *     bounds test are done once per thread; the flow comes as one packed (x | y << 16) word per cell
- *     (written by the search kernel's blur tail next to the planar array of the C interface);
- *   - a source run = 4 consecutive samples at an arbitrary displacement = two aligned 32-bit loads and a
- *     funnel shift (chroma with an odd displacement: warpFrameKernel.cl:171 picks U from column c+d-1 and
- *     V from c+d+1: six samples, one byte permute);
+ * HBM-bound by nature (2 frames read, 1 written, 518 KB of flow), issue- and load-request-bound in practice. The
+ * kernel is organised around both counts:
+ *   - thread = UW samples x ROWS rows inside ONE lattice cell, UW chosen per resolution scalar so that a unit is as
+ *     wide as one displacement allows: a cell is 4 samples wide at 1080p, 8 at 4K, 16 at 8K. A unit row is one access
+ *     of UB = UW * sizeof(sample) bytes: 32 bits (NV12 1080p), 64 bits (P010 1080p, NV12 4K) or 128 bits (P010 4K and 8K,
+ *     NV12 8K); the flow vector, the flipped vector (warpFrameKernel.cl:155-156), the four roundings and every bounds
+ *     test are done once per unit. The flow comes as one packed (x | y << 16) word per cell.
+ *   - a source run = UW consecutive samples at an arbitrary displacement = TWO aligned UB-byte loads (the vector that
+ *     holds the run's first sample and the next one) and a register barrel: word select by the offset's word part,
+ *     funnel shift by its byte part. The row pitch is a multiple of UB, so the barrel setting is the same for every
+ *     row of the unit. Chroma with an odd displacement (warpFrameKernel.cl:171 takes U from column c+d-1 and V from
+ *     c+d+1) reads one word more from the same two vectors and fixes the pairs with one byte permute per word.
  *   - conversions through the 2^23 magic number, with the subtractions folded into the arithmetic where
  *     that is exact:  fl(b * t) == fma(2^23 + b, t, -(2^23 * t))   (one rounding of the exact product),
  *                     v - sub   == (2^23 + v) - (2^23 + sub)       (integers below 2^24),
  *     all of it two samples per instruction on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2);
- *   - 128-thread CTAs (4 row groups x 128 samples), about ten per SM at 1080p, so that the block
- *     scheduler evens out the border CTAs.
+ *   - output modes: 0 / 1 copy a run, 2 / 5 blend + levels, 3 (HSV flow) adds the cell's colour from the per-flow
+ *     table (hr_warp.cuh) to half of the blend — its chroma plane is a per-cell constant and reads no picture at
+ *     all —, 4 (grey flow) is a per-cell constant;
+ *   - several output frames of one frame pair (same flow, same sources, different blend scalars) in ONE launch:
+ *     grid.z = output (WarpBatch), so a 24->60 source frame costs one warp launch instead of two or three.
  * The float expressions are those of hr_warp.cuh (header there): bit-identical to the reference kernel
  * as the NVIDIA OpenCL compiler builds it.
  */
@@ -27,273 +32,376 @@
 #include "hr_warp.cuh"
 #include <type_traits>
 
+/* Constants of the packed blend + level arithmetic as fp32 pairs (both halves equal), prepared by the host so that the
+ * kernel reads them as 64-bit constant-bank operands instead of building and holding them in registers. */
+struct LevelConsts {           /* per plane kind */
+    F2 rcp, mul, add, negSub, negMsub;
+    float lo, hi;
+};
+#define HR_WARP_BATCH 8
+struct WarpBatch {
+    int n;
+    float t12[HR_WARP_BATCH], t21[HR_WARP_BATCH];
+    F2 t12x2[HR_WARP_BATCH], t21x2[HR_WARP_BATCH], negMt12[HR_WARP_BATCH]; /* (t, t), (1-t, 1-t), -(2^23 * t) twice */
+    void *outY[HR_WARP_BATCH], *outUV[HR_WARP_BATCH];
+};
+
 struct WarpFastArgs {
     int lumaGroups, lumaG0, chromaG0, chromaGN; /* row groups of the launch: luma first, then chroma       */
-    /* level map, per plane kind [0] luma [1] chroma. 8-bit: sub = black / 128, rcp = MUFU.RCP of den (read back
-     * from the device by the host once per knob setting). 16-bit: sub = b16 / 32768, rcp = correctly rounded
-     * reciprocal (host). */
+    /* level map, per plane kind [0] luma [1] chroma. 8-bit (NV12, and the HSV mode of either format): sub = black /
+     * 128, rcp = MUFU.RCP of den (read back from the device by the host once per knob setting). 16-bit: sub = b16 /
+     * 32768, rcp = correctly rounded reciprocal (host). */
     float sub[2], den[2], rcp[2];
     int clampNeeded[2];    /* the map can leave [0, max]: clamp in float before the truncation             */
     int subIsInt[2];       /* sub is an integer below 2^22: (2^23 + v) - (2^23 + sub) is exact              */
+    const uint32_t *colours; /* HSV mode: flow colour per lattice cell (flow_colour_kernel)                 */
+    float white;           /* HSV mode: the chroma constants go through the 8-bit level map per unit        */
+    LevelConsts lc[2];     /* the same level map as packed constants ([0] luma, [1] chroma)                 */
+    F2 negM, M;            /* (-2^23, -2^23), (2^23, 2^23)                                                   */
 };
 
-__device__ __forceinline__ int round_half_away(float x) {
-    /* round() of the reference as compiled: trunc(x + copysign(0.5, x)), the add rounded toward zero */
-    return __float2int_rz(__fadd_rz(x, copysignf(0.5f, x)));
+/* ---- aligned vectors of UB bytes -------------------------------------------------------------------------- */
+template <int UB>
+struct Vec {
+    uint32_t w[UB / 4];
+};
+template <int UB>
+__device__ __forceinline__ Vec<UB> vec_load(const unsigned char *p);
+template <>
+__device__ __forceinline__ Vec<4> vec_load<4>(const unsigned char *p) {
+    Vec<4> v;
+    v.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+    return v;
 }
+template <>
+__device__ __forceinline__ Vec<8> vec_load<8>(const unsigned char *p) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    Vec<8> v;
+    v.w[0] = t.x;
+    v.w[1] = t.y;
+    return v;
+}
+template <>
+__device__ __forceinline__ Vec<16> vec_load<16>(const unsigned char *p) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    Vec<16> v;
+    v.w[0] = t.x;
+    v.w[1] = t.y;
+    v.w[2] = t.z;
+    v.w[3] = t.w;
+    return v;
+}
+__device__ __forceinline__ void vec_store(unsigned char *p, const Vec<4> &v) { *reinterpret_cast<uint32_t *>(p) = v.w[0]; }
+__device__ __forceinline__ void vec_store(unsigned char *p, const Vec<8> &v) { *reinterpret_cast<uint2 *>(p) = make_uint2(v.w[0], v.w[1]); }
+__device__ __forceinline__ void vec_store(unsigned char *p, const Vec<16> &v) { *reinterpret_cast<uint4 *>(p) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]); }
 
-/* ---- source runs ----------------------------------------------------------------------------------- */
-template <typename T>
-struct RunSrc; /* where a thread's source block starts: aligned word pointer, bit shift, chroma-odd flag */
-template <>
-struct RunSrc<uint8_t> {
-    const uint32_t *q;
-    unsigned sh;
-    bool more, odd;
-    int rowWords;
-    __device__ __forceinline__ void set(const uint8_t *plane, int o, int W, bool oddDisp) {
-        odd = oddDisp;
-        if (odd) o -= 1;
-        q = reinterpret_cast<const uint32_t *>(plane) + (o >> 2);
-        sh = (unsigned)(o & 3) * 8;
-        more = sh != 0 || odd; /* an odd chroma displacement reads six samples */
-        rowWords = W >> 2;
+/* ---- source runs ----------------------------------------------------------------------------------------- */
+/* Where a unit's source block starts: the aligned vector that holds its first sample, the run's word and bit offset
+ * inside it. An odd chroma displacement starts one sample earlier (pair-aligned) and reads one word more. */
+template <int UB, bool IS16>
+struct RunSource {
+    static constexpr int NW = UB / 4;
+    const unsigned char *base;
+    unsigned wordOff, bitOff;
+    bool second, odd;
+    size_t pitch;
+    __device__ __forceinline__ void set(const void *plane, long long firstSample, size_t pitchBytes, bool oddDisplacement) {
+        odd = oddDisplacement;
+        if (odd) firstSample -= 1;
+        const uintptr_t a = (uintptr_t)plane + (uintptr_t)(firstSample * (IS16 ? 2 : 1));
+        const unsigned k = (unsigned)(a & (UB - 1));
+        base = reinterpret_cast<const unsigned char *>(a - k);
+        wordOff = k >> 2;
+        bitOff = (k & 3u) * 8u;
+        second = k != 0 || odd; /* the run ends in the next vector */
+        pitch = pitchBytes;
     }
+    /* the UW samples of row r, in output order */
     template <bool CHROMA>
-    __device__ __forceinline__ uint32_t row(int r) const {
-        const uint32_t *p = q + r * rowWords;
-        const uint32_t w0 = __ldg(p), w1 = more ? __ldg(p + 1) : 0u;
-        const uint32_t lo = __funnelshift_r(w0, w1, sh);
-        if (!CHROMA) return lo;
-        const uint32_t w2 = (odd && sh == 24) ? __ldg(p + 2) : 0u;
-        const uint32_t hi = __funnelshift_r(w1, w2, sh);
-        return __byte_perm(lo, hi, odd ? 0x5230u : 0x3210u);
-    }
-};
-template <>
-struct RunSrc<uint16_t> {
-    const uint32_t *q;
-    unsigned sh;
-    bool more, odd;
-    int rowWords;
-    __device__ __forceinline__ void set(const uint16_t *plane, int o, int W, bool oddDisp) {
-        odd = oddDisp;
-        if (odd) o -= 1;
-        q = reinterpret_cast<const uint32_t *>(plane) + (o >> 1);
-        sh = (unsigned)(o & 1) * 16;
-        more = sh != 0;
-        rowWords = W >> 1;
-    }
-    template <bool CHROMA>
-    __device__ __forceinline__ uint2 row(int r) const {
-        const uint32_t *p = q + r * rowWords;
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1);
-        if (!CHROMA) {
-            const uint32_t w2 = more ? __ldg(p + 2) : 0u;
-            return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+    __device__ __forceinline__ Vec<UB> row(int r) const {
+        const unsigned char *p = base + (size_t)r * pitch;
+        const Vec<UB> lo = vec_load<UB>(p);
+        Vec<UB> hi;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) hi.w[i] = 0u;
+        if (second) hi = vec_load<UB>(p + UB);
+        uint32_t w[2 * NW + 2];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            w[i] = lo.w[i];
+            w[NW + i] = hi.w[i];
         }
-        const uint32_t w2 = (more || odd) ? __ldg(p + 2) : 0u;
-        const uint32_t w3 = (more && odd) ? __ldg(p + 3) : 0u;
-        const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh);
-        /* even displacement: samples 0,1 | 2,3; odd: 0,3 | 2,5 */
-        return odd ? make_uint2(__byte_perm(s0, s1, 0x7610), __byte_perm(s1, s2, 0x7610)) : make_uint2(s0, s1);
+        w[2 * NW] = w[2 * NW + 1] = 0u;
+        /* barrel: shift the 2 NW words down by wordOff (one conditional move per word and offset bit) ... */
+        if (NW >= 4) {
+            const bool by2 = wordOff & 2u;
+#pragma unroll
+            for (int i = 0; i < 2 * NW; ++i) w[i] = by2 ? w[i + 2] : w[i];
+        }
+        if (NW >= 2) {
+            const bool by1 = wordOff & 1u;
+#pragma unroll
+            for (int i = 0; i < 2 * NW; ++i) w[i] = by1 ? w[i + 1] : w[i];
+        }
+        /* ... and by bitOff inside the words */
+        uint32_t o[NW + 1];
+#pragma unroll
+        for (int i = 0; i < NW + 1; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], bitOff);
+        Vec<UB> out;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            /* odd chroma displacement: sample j of the output pair (U, V) comes from run sample j (U) and j + 2 (V) */
+            if (CHROMA) out.w[i] = __byte_perm(o[i], o[i + 1], odd ? (IS16 ? 0x7610u : 0x5230u) : 0x3210u);
+            else out.w[i] = o[i];
+        }
+        return out;
     }
 };
+
+/* UW samples at a frame border: each through reflect_inner() and, for chroma, the pair rule */
+template <int UB, bool IS16>
+__device__ __forceinline__ Vec<UB> border_row(const void *rowBase, int cx0, int dx, int aW, bool chroma) {
+    constexpr int UW = UB / (IS16 ? 2 : 1);
+    Vec<UB> v;
+#pragma unroll
+    for (int i = 0; i < UB / 4; ++i) v.w[i] = 0u;
+#pragma unroll
+    for (int k = 0; k < UW; ++k) {
+        const int x = reflect_inner(cx0 + k + dx, aW);
+        const int col = chroma ? (x & ~1) + (k & 1) : x;
+        if (IS16) v.w[k >> 1] |= (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(rowBase) + col) << (16 * (k & 1));
+        else v.w[k >> 2] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(rowBase) + col) << (8 * (k & 3));
+    }
+    return v;
+}
 
 /* ---- blend + levels, two samples per instruction ----------------------------------------------------- */
+/* what a unit needs of the constants: references into the kernel's parameter space plus its own HSV term */
 struct BlendK {
-    F2 t12, t21, negM, negMt12, M, rcp, mul, add, negSub, negMsub;
-    float lo, hi;
+    const LevelConsts &L;
+    const F2 &t12, &t21, &negMt12, &negM, &M;
+    uint32_t lumaColour; /* HSV mode: 0x4B000000 + the cell's halved colour luma */
 };
-template <bool IS16>
-__device__ __forceinline__ BlendK make_blendk(float t12, float t21, const WarpFastArgs &A, int cz) {
-    BlendK K;
-    const float sub = A.sub[cz];
-    const float rcp = A.rcp[cz];
-    const float mul = IS16 ? 65472.0f : 255.0f, add = IS16 ? 32768.0f : 128.0f;
-    K.t12 = f2_make(t12, t12);
-    K.t21 = f2_make(t21, t21);
-    K.negM = f2_make(-HR_MAGIC, -HR_MAGIC);
-    K.negMt12 = f2_make(-(HR_MAGIC * t12), -(HR_MAGIC * t12));
-    K.M = f2_make(HR_MAGIC, HR_MAGIC);
-    K.rcp = f2_make(rcp, rcp);
-    K.mul = f2_make(mul, mul);
-    K.add = f2_make(add, add);
-    K.negSub = f2_make(-sub, -sub);
-    K.negMsub = f2_make(-(HR_MAGIC + sub), -(HR_MAGIC + sub));
-    K.lo = 0.0f;
-    K.hi = mul;
-    return K;
-}
-/* one pair: A, B = the bit patterns 0x4B000000 | sample of the frame-1 / frame-2 samples; returns the bit
- * patterns 0x4B000000 | output of the pair */
-template <bool CHROMA, bool CLAMP, bool SUBINT>
-__device__ __forceinline__ F2 blend_pair(const BlendK &K, F2 A, F2 B) {
-    const F2 a = f2_add(A, K.negM);                         /* (float)f1                                  */
-    const F2 p = f2_fma(B, K.t12, K.negMt12);               /* (float)f2 * t12, one rounding               */
-    const F2 bl = f2_fma(a, K.t21, p);                      /* fma(f1, t21, f2 * t12)                      */
-    const F2 vM = f2_add_rz(bl, K.M);                       /* 2^23 + trunc(blend)                         */
-    const F2 d = SUBINT ? f2_add(vM, K.negMsub) : f2_add(f2_add(vM, K.negM), K.negSub); /* v - sub            */
-    F2 x = f2_mul(d, K.rcp);
-    x = CHROMA ? f2_fma(x, K.mul, K.add) : f2_mul(x, K.mul);
-    if (CLAMP) x = f2_make(fmaxf(fminf(f2_lo(x), K.hi), K.lo), fmaxf(fminf(f2_hi(x), K.hi), K.lo));
-    return f2_add_rz(x, K.M);
-}
 __device__ __forceinline__ uint32_t f2_lo_bits(F2 v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t f2_hi_bits(F2 v) { return (uint32_t)(v >> 32); }
 
-template <bool CHROMA, bool CLAMP, bool SUBINT>
-__device__ __forceinline__ uint32_t blend_run(const BlendK &K, uint32_t wa, uint32_t wb) {
-    const F2 r0 = blend_pair<CHROMA, CLAMP, SUBINT>(K, f2_bits(__byte_perm(wa, 0x4B000000u, 0x7540u), __byte_perm(wa, 0x4B000000u, 0x7541u)),
-                                                    f2_bits(__byte_perm(wb, 0x4B000000u, 0x7540u), __byte_perm(wb, 0x4B000000u, 0x7541u)));
-    const F2 r1 = blend_pair<CHROMA, CLAMP, SUBINT>(K, f2_bits(__byte_perm(wa, 0x4B000000u, 0x7542u), __byte_perm(wa, 0x4B000000u, 0x7543u)),
-                                                    f2_bits(__byte_perm(wb, 0x4B000000u, 0x7542u), __byte_perm(wb, 0x4B000000u, 0x7543u)));
+/* one pair: A, B = the bit patterns 0x4B000000 | sample of the frame-1 / frame-2 samples; returns the bit
+ * patterns 0x4B000000 | output of the pair. HSV (luma only): the blend's 8-bit reading is halved and the cell's
+ * colour added before the level map (hr_warp.cuh, blend_finish); PICSHIFT = 1 (8-bit samples) or 9 (16-bit). */
+template <bool CHROMA, bool CLAMP, bool SUBINT, int PICSHIFT>
+__device__ __forceinline__ F2 blend_pair(const BlendK &K, F2 A, F2 B) {
+    const LevelConsts &L = K.L;
+    const F2 a = f2_add(A, K.negM);                         /* (float)f1                                  */
+    const F2 p = f2_fma(B, K.t12, K.negMt12);               /* (float)f2 * t12, one rounding               */
+    const F2 bl = f2_fma(a, K.t21, p);                      /* fma(f1, t21, f2 * t12)                      */
+    F2 vM = f2_add_rz(bl, K.M);                             /* 2^23 + trunc(blend)                         */
+    if (PICSHIFT) {
+        vM = f2_bits(((f2_lo_bits(vM) >> PICSHIFT) & 0x7Fu) + K.lumaColour, ((f2_hi_bits(vM) >> PICSHIFT) & 0x7Fu) + K.lumaColour);
+    }
+    const F2 d = SUBINT ? f2_add(vM, L.negMsub) : f2_add(f2_add(vM, K.negM), L.negSub); /* v - sub            */
+    F2 x = f2_mul(d, L.rcp);
+    x = CHROMA ? f2_fma(x, L.mul, L.add) : f2_mul(x, L.mul);
+    if (CLAMP) x = f2_make(fmaxf(fminf(f2_lo(x), L.hi), L.lo), fmaxf(fminf(f2_hi(x), L.hi), L.lo));
+    return f2_add_rz(x, K.M);
+}
+
+/* one 32-bit word of samples. 8-bit: four samples in, four out. */
+template <bool CHROMA, bool CLAMP, bool SUBINT, bool HSV>
+__device__ __forceinline__ uint32_t blend_word8(const BlendK &K, uint32_t wa, uint32_t wb) {
+    constexpr int PS = HSV ? 1 : 0;
+    const F2 r0 = blend_pair<CHROMA, CLAMP, SUBINT, PS>(K, f2_bits(__byte_perm(wa, 0x4B000000u, 0x7540u), __byte_perm(wa, 0x4B000000u, 0x7541u)),
+                                                        f2_bits(__byte_perm(wb, 0x4B000000u, 0x7540u), __byte_perm(wb, 0x4B000000u, 0x7541u)));
+    const F2 r1 = blend_pair<CHROMA, CLAMP, SUBINT, PS>(K, f2_bits(__byte_perm(wa, 0x4B000000u, 0x7542u), __byte_perm(wa, 0x4B000000u, 0x7543u)),
+                                                        f2_bits(__byte_perm(wb, 0x4B000000u, 0x7542u), __byte_perm(wb, 0x4B000000u, 0x7543u)));
     return __byte_perm(__byte_perm(f2_lo_bits(r0), f2_hi_bits(r0), 0x0040), __byte_perm(f2_lo_bits(r1), f2_hi_bits(r1), 0x0040), 0x5410);
 }
-/* P010: the low 16 bits of each result hold trunc(x) < 65536; clamp to 65472, round to the nearest 10-bit
- * code ((v + 32) & 0xFFC0) on both halves at once */
-template <bool CHROMA, bool CLAMP, bool SUBINT>
-__device__ __forceinline__ uint2 blend_run(const BlendK &K, uint2 wa, uint2 wb) {
-    const F2 r0 = blend_pair<CHROMA, CLAMP, SUBINT>(K, f2_bits(__byte_perm(wa.x, 0x4B000000u, 0x7510u), __byte_perm(wa.x, 0x4B000000u, 0x7532u)),
-                                                    f2_bits(__byte_perm(wb.x, 0x4B000000u, 0x7510u), __byte_perm(wb.x, 0x4B000000u, 0x7532u)));
-    const F2 r1 = blend_pair<CHROMA, CLAMP, SUBINT>(K, f2_bits(__byte_perm(wa.y, 0x4B000000u, 0x7510u), __byte_perm(wa.y, 0x4B000000u, 0x7532u)),
-                                                    f2_bits(__byte_perm(wb.y, 0x4B000000u, 0x7510u), __byte_perm(wb.y, 0x4B000000u, 0x7532u)));
-    const uint32_t p0 = __vminu2(__byte_perm(f2_lo_bits(r0), f2_hi_bits(r0), 0x5410), 0xFFC0FFC0u);
-    const uint32_t p1 = __vminu2(__byte_perm(f2_lo_bits(r1), f2_hi_bits(r1), 0x5410), 0xFFC0FFC0u);
-    return make_uint2((p0 + 0x00200020u) & 0xFFC0FFC0u, (p1 + 0x00200020u) & 0xFFC0FFC0u);
+/* 16-bit: two samples per word. The low 16 bits of each result hold trunc(x) < 65536; clamp to 65472, round to the
+ * nearest 10-bit code ((v + 32) & 0xFFC0) on both halves at once. HSV: the 8-bit result, << 8. */
+template <bool CHROMA, bool CLAMP, bool SUBINT, bool HSV>
+__device__ __forceinline__ uint32_t blend_word16(const BlendK &K, uint32_t wa, uint32_t wb) {
+    constexpr int PS = HSV ? 9 : 0;
+    const F2 r = blend_pair<CHROMA, CLAMP, SUBINT, PS>(K, f2_bits(__byte_perm(wa, 0x4B000000u, 0x7510u), __byte_perm(wa, 0x4B000000u, 0x7532u)),
+                                                       f2_bits(__byte_perm(wb, 0x4B000000u, 0x7510u), __byte_perm(wb, 0x4B000000u, 0x7532u)));
+    if (HSV) return __byte_perm(f2_lo_bits(r), f2_hi_bits(r), 0x4101u); /* bytes: 0, lo, 0, hi */
+    const uint32_t p = __vminu2(__byte_perm(f2_lo_bits(r), f2_hi_bits(r), 0x5410), 0xFFC0FFC0u);
+    return (p + 0x00200020u) & 0xFFC0FFC0u;
+}
+template <bool IS16, int UB, bool CHROMA, bool CLAMP, bool SUBINT, bool HSV>
+__device__ __forceinline__ Vec<UB> blend_vec(const BlendK &K, const Vec<UB> &a, const Vec<UB> &b) {
+    Vec<UB> o;
+#pragma unroll
+    for (int i = 0; i < UB / 4; ++i)
+        o.w[i] = IS16 ? blend_word16<CHROMA, CLAMP, SUBINT, HSV>(K, a.w[i], b.w[i]) : blend_word8<CHROMA, CLAMP, SUBINT, HSV>(K, a.w[i], b.w[i]);
+    return o;
 }
 
-__device__ __forceinline__ void store_run(uint8_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
-__device__ __forceinline__ void store_run(uint16_t *p, uint2 v) { *reinterpret_cast<uint2 *>(p) = v; }
-__device__ __forceinline__ uint32_t load_own(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
-__device__ __forceinline__ uint2 load_own(const uint16_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
-
-/* rare threads: a partial column / row group, or the column that straddles the middle in mode 5 */
+/* rare units: a partial column / row group, or the column that straddles the middle in mode 5 */
 template <typename T>
-__device__ __noinline__ void warp_thread_slow(const WarpParams<T> &P, int cx0, int cy0, int cz, int nrows) {
-    T *out = cz ? P.outUV : P.outY;
+__device__ __noinline__ void unit_by_samples(const WarpParams<T> &P, float t12, float t21, T *out, int cx0, int cy0, bool chroma, int ncols, int nrows) {
     for (int r = 0; r < nrows; ++r)
-        for (int k = 0; k < 4; ++k)
-            if (cx0 + k < P.aW) out[(size_t)(cy0 + r) * P.W + cx0 + k] = (T)warp_sample(P, cx0 + k, cy0 + r, cz);
+        for (int k = 0; k < ncols; ++k)
+            if (cx0 + k < P.aW) out[(size_t)(cy0 + r) * P.W + cx0 + k] = (T)sample_value(P, t12, t21, cx0 + k, cy0 + r, chroma);
 }
 
-template <typename T, int ROWS, bool CHROMA>
-__device__ __forceinline__ void warp_fast_thread(const WarpParams<T> &P, const WarpFastArgs &A, int cx0, int cy0) {
+/* A unit whose source blocks touch a frame border: every sample through the reflection, chroma through the pair rule;
+ * the blend in its general form (float clamp, unfolded subtraction: the same numbers as the specialised forms). Out of
+ * line, so that the interior path does not carry its registers. */
+template <typename T, int ROWS, int UW, bool CHROMA>
+__device__ __noinline__ void border_unit(const WarpParams<T> &P, const WarpFastArgs &A, const WarpBatch &B, int z, uint32_t lumaColour, unsigned char *po, int cx0,
+                                         Shift d, int b12, int b21) {
     constexpr bool is16 = SampleTraits<T>::is16;
-    typedef typename RunType<T>::type Run;
+    const BlendK K = {A.lc[CHROMA ? 1 : 0], B.t12x2[z], B.t21x2[z], B.negMt12[z], A.negM, A.M, lumaColour};
+    constexpr int UB = UW * (int)sizeof(T);
+    typedef Vec<UB> Run;
+    const int planeH = CHROMA ? (P.H >> 1) : P.H;
+    const T *s12 = CHROMA ? P.f1uv : P.f1y;
+    const T *s21 = CHROMA ? P.f2uv : P.f2y;
+    const size_t pitch = (size_t)P.W * sizeof(T);
+    const int mode = P.mode;
+#pragma unroll 1
+    for (int r = 0; r < ROWS; ++r) {
+        Run a = Run(), b = Run();
+        if (mode != HR_MODE_WARPED_21) a = border_row<UB, is16>(s12 + (size_t)reflect_inner(b12 + r, planeH) * P.W, cx0, d.x1, P.aW, CHROMA);
+        if (mode != HR_MODE_WARPED_12) b = border_row<UB, is16>(s21 + (size_t)reflect_inner(b21 + r, planeH) * P.W, cx0, d.x2, P.aW, CHROMA);
+        Run o;
+        if (mode == HR_MODE_WARPED_12) o = a;
+        else if (mode == HR_MODE_WARPED_21) o = b;
+        else if (mode == HR_MODE_HSV_FLOW) o = blend_vec<is16, UB, false, true, false, true>(K, a, b); /* luma only: chroma never gets here */
+        else o = blend_vec<is16, UB, CHROMA, true, false, false>(K, a, b);
+        vec_store(po + r * pitch, o);
+    }
+}
+
+template <typename T, int ROWS, int UW, bool CHROMA>
+__device__ __forceinline__ void warp_unit(const WarpParams<T> &P, const WarpFastArgs &A, const WarpBatch &B, int z, T *outPlane, int cx0, int cy0) {
+    const float t12 = B.t12[z], t21 = B.t21[z];
+    constexpr bool is16 = SampleTraits<T>::is16;
+    constexpr int UB = UW * (int)sizeof(T);
+    typedef Vec<UB> Run;
     constexpr int cz = CHROMA ? 1 : 0;
     const int planeH = CHROMA ? (P.H >> 1) : P.H;
     const T *s12 = CHROMA ? P.f1uv : P.f1y;
     const T *s21 = CHROMA ? P.f2uv : P.f2y;
-    T *po = (CHROMA ? P.outUV : P.outY) + cy0 * P.W + cx0;
+    const size_t pitch = (size_t)P.W * sizeof(T);
+    unsigned char *po = reinterpret_cast<unsigned char *>(outPlane + (size_t)cy0 * P.W + cx0);
     const int mode = P.mode;
 
-    if (cx0 + 3 >= P.aW || cy0 + ROWS > planeH) {
-        warp_thread_slow(P, cx0, cy0, cz, hr_min(ROWS, planeH - cy0));
+    if (cx0 + UW > P.aW || cy0 + ROWS > planeH) {
+        unit_by_samples(P, t12, t21, outPlane, cx0, cy0, CHROMA, UW, hr_min(ROWS, planeH - cy0));
         return;
     }
-    if (mode == 5) {
+    if (mode == HR_MODE_SIDE_BY_SIDE_1) {
         const int half = P.aW >> 1;
-        if (cx0 + 3 < half) { /* left half of SideBySide1: frame 1 as it is (warpFrameKernel.cl:131-133) */
+        if (cx0 + UW <= half) { /* left half: frame 1 as it is (warpFrameKernel.cl:131-133) */
+            const unsigned char *ps = reinterpret_cast<const unsigned char *>(s12 + (size_t)cy0 * P.W + cx0);
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) store_run(po + r * P.W, load_own(s12 + (cy0 + r) * P.W + cx0));
+            for (int r = 0; r < ROWS; ++r) vec_store(po + r * pitch, vec_load<UB>(ps + r * pitch));
             return;
         }
         if (cx0 < half) {
-            warp_thread_slow(P, cx0, cy0, cz, ROWS);
+            unit_by_samples(P, t12, t21, outPlane, cx0, cy0, CHROMA, UW, ROWS);
             return;
         }
     }
 
     /* the cell's flow and its flip (warpFrameKernel.cl:151-156) */
-    const int s = P.s;
-    int lx = cx0 >> s, ly = cy0 >> s;
-    if (CHROMA) {
-        lx &= ~1;
-        ly <<= 1;
+    const int2 cell = lattice_cell(cx0, cy0, P.s, CHROMA);
+    if (mode == HR_MODE_HSV_FLOW && CHROMA) {
+        /* flow colours: the chroma plane of a cell is one (U, V) pair, through the 8-bit level map */
+        const uint32_t colour = __ldg(A.colours + cell.y * P.lw + cell.x);
+        const unsigned u = levels_uv8((float)((colour >> 8) & 255u), A.white), v = levels_uv8((float)((colour >> 16) & 255u), A.white);
+        Run fill;
+#pragma unroll
+        for (int i = 0; i < UB / 4; ++i) fill.w[i] = is16 ? (u << 8) | (v << 24) : u | (v << 8) | (u << 16) | (v << 24);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) vec_store(po + r * pitch, fill);
+        return;
     }
-    const uint32_t w12 = __ldg(P.flowXY + ly * P.lw + lx);
-    const int x12 = (int)(int16_t)w12, y12 = (int)w12 >> 16;
-    const int fy = hr_min(hr_max(ly - (y12 >> s), 0), P.lh - 1);
-    const int fx = hr_min(hr_max(lx - (x12 >> s), 0), P.lw - 1);
-    const uint32_t w21 = __ldg(P.flowXY + fy * P.lw + fx);
-    const int x21 = (int)(int16_t)w21, y21 = (int)w21 >> 16;
+    const VectorPair v = vector_pair(P, cell);
+    if (mode == HR_MODE_GREY_FLOW) {
+        const unsigned len4 = (unsigned)(abs(v.fx) + abs(v.fy)) << 2;
+        const unsigned g8 = CHROMA ? 128u : (len4 < 255u ? len4 : 255u);
+        Run fill;
+#pragma unroll
+        for (int i = 0; i < UB / 4; ++i) fill.w[i] = is16 ? (g8 << 8) * 0x00010001u : g8 * 0x01010101u;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) vec_store(po + r * pitch, fill);
+        return;
+    }
 
     /* displacements (warpFrameKernel.cl:165-168) */
-    float fe12 = (float)y12 * P.t12, fe21 = (float)y21 * P.t21;
-    if (CHROMA) {
-        fe12 *= 0.5f;
-        fe21 *= 0.5f;
-    }
-    const int d12 = round_half_away((float)x12 * P.t12), d21 = -round_half_away((float)x21 * P.t21);
-    const int e12 = round_half_away(fe12), e21 = -round_half_away(fe21);
-    const int a12 = cx0 + d12, a21 = cx0 + d21, b12 = cy0 + e12, b21 = cy0 + e21;
-    /* all four source blocks inside [1, aW-2] x [1, planeH-2]: the mirror/clamp of warpFrameKernel.cl:10-18 is
-     * the identity, rows and columns are consecutive */
-    const bool interior = (unsigned)(a12 - 1) <= (unsigned)(P.aW - 6) && (unsigned)(a21 - 1) <= (unsigned)(P.aW - 6) &&
+    const Shift d = shift_for(v, t12, t21, CHROMA);
+    const int a12 = cx0 + d.x1, a21 = cx0 + d.x2, b12 = cy0 + d.y1, b21 = cy0 + d.y2;
+    /* all four source blocks inside [1, aW-2] x [1, planeH-2]: reflect_inner() is the identity, rows and columns are
+     * consecutive */
+    const bool interior = (unsigned)(a12 - 1) <= (unsigned)(P.aW - UW - 2) && (unsigned)(a21 - 1) <= (unsigned)(P.aW - UW - 2) &&
                           (unsigned)(b12 - 1) <= (unsigned)(planeH - ROWS - 2) && (unsigned)(b21 - 1) <= (unsigned)(planeH - ROWS - 2);
-    const int var = mode < 2 ? 0 : (A.subIsInt[cz] ? (A.clampNeeded[cz] ? 2 : 1) : 3);
-    const BlendK K = make_blendk<is16>(P.t12, P.t21, A, cz);
-    /* one output row from its two source runs. VAR 0: WarpedFrame12 / WarpedFrame21, the sample as it is
-     * (warpFrameKernel.cl:170-173); 1..3: blend + levels (no clamp / clamp / clamp and non-integer black) */
-    auto emit = [&](auto varTag, int r, Run a, Run b) {
-        constexpr int VAR = decltype(varTag)::value;
-        if (VAR == 0) store_run(po + r * P.W, mode == 0 ? a : b);
-        else store_run(po + r * P.W, blend_run<CHROMA, VAR >= 2, VAR != 3>(K, a, b));
-    };
+    const bool hsv = mode == HR_MODE_HSV_FLOW;
+    uint32_t lumaColour = 0x4B000000u;
+    if (hsv) lumaColour += __ldg(A.colours + cell.y * P.lw + cell.x) & 255u;
+    if (!interior) {
+        border_unit<T, ROWS, UW, CHROMA>(P, A, B, z, lumaColour, po, cx0, d, b12, b21);
+        return;
+    }
+    const BlendK K = {A.lc[cz], B.t12x2[z], B.t21x2[z], B.negMt12[z], A.negM, A.M, lumaColour};
+    /* one output row from its two source runs. VAR 0: WarpedFrame12 / WarpedFrame21, the run as it is
+     * (warpFrameKernel.cl:170-173); 1..3: blend + levels (no clamp / clamp / clamp and non-integer black); 4: HSV luma */
+    const int var = mode < 2 ? 0 : (hsv ? 4 : (A.subIsInt[cz] ? (A.clampNeeded[cz] ? 2 : 1) : 3));
     auto rows = [&](auto varTag) {
         constexpr int VAR = decltype(varTag)::value;
-        if (interior) {
-            Run ra[ROWS], rb[ROWS];
-            RunSrc<T> A12, A21;
-            if (VAR != 0 || mode == 0) {
-                A12.set(s12, b12 * P.W + a12, P.W, CHROMA && (d12 & 1));
+        Run ra[ROWS], rb[ROWS];
+        RunSource<UB, is16> A12, A21;
+        if (VAR != 0 || mode == 0) {
+            A12.set(s12, (long long)b12 * P.W + a12, pitch, CHROMA && (d.x1 & 1));
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) ra[r] = A12.template row<CHROMA>(r);
-            }
-            if (VAR != 0 || mode == 1) {
-                A21.set(s21, b21 * P.W + a21, P.W, CHROMA && (d21 & 1));
+            for (int r = 0; r < ROWS; ++r) ra[r] = A12.template row<CHROMA>(r);
+        }
+        if (VAR != 0 || mode == 1) {
+            A21.set(s21, (long long)b21 * P.W + a21, pitch, CHROMA && (d.x2 & 1));
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) rb[r] = A21.template row<CHROMA>(r);
-            }
+            for (int r = 0; r < ROWS; ++r) rb[r] = A21.template row<CHROMA>(r);
+        }
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) emit(varTag, r, ra[r], rb[r]);
-        } else {
-            /* a frame border is involved: every sample through the mirror + clamp, chroma through the pair rule */
-#pragma unroll 1
-            for (int r = 0; r < ROWS; ++r) {
-                Run a = Run(), b = Run();
-                if (VAR != 0 || mode == 0) a = load_run4_border(s12 + (size_t)warp_mirror(b12 + r, planeH) * P.W, cx0, d12, P.aW, cz);
-                if (VAR != 0 || mode == 1) b = load_run4_border(s21 + (size_t)warp_mirror(b21 + r, planeH) * P.W, cx0, d21, P.aW, cz);
-                emit(varTag, r, a, b);
-            }
+        for (int r = 0; r < ROWS; ++r) {
+            if (VAR == 0) vec_store(po + r * pitch, mode == 0 ? ra[r] : rb[r]);
+            else if (VAR == 4) vec_store(po + r * pitch, blend_vec<is16, UB, CHROMA, true, false, true>(K, ra[r], rb[r]));
+            else vec_store(po + r * pitch, blend_vec<is16, UB, CHROMA, VAR >= 2, VAR != 3, false>(K, ra[r], rb[r]));
         }
     };
     switch (var) {
         case 0: rows(std::integral_constant<int, 0>()); break;
         case 1: rows(std::integral_constant<int, 1>()); break;
         case 2: rows(std::integral_constant<int, 2>()); break;
-        default: rows(std::integral_constant<int, 3>()); break;
+        case 3: rows(std::integral_constant<int, 3>()); break;
+        default:
+            if (!CHROMA) rows(std::integral_constant<int, 4>());
+            break;
     }
 }
 
-/* grid: x = 128-sample column blocks, y = groups of 4 row groups; row groups of the luma plane first */
-template <typename T, int ROWS>
-/* twelve 128-thread CTAs per SM (40 registers): the kernel is latency-bound at 4K and above, resident warps are what
- * hides its three dependent round trips (tools/diag_launch.py, 8K P010: 80 us at 9 CTAs of 8-row units, 74 us at 10,
- * 67 us with 4-row units at 10-12) */
+/* grid: x = column blocks of 32 units, y = groups of 4 row groups (row groups of the luma plane first, then of the
+ * chroma plane), z = output frame of the batch.
+ * HR_WARP_MINBLOCKS 128-thread CTAs per SM: the kernel is latency-bound at 4K and above, resident warps are what hides
+ * its three dependent round trips (flow word -> flipped flow word -> samples). */
 #ifndef HR_WARP_MINBLOCKS
 #define HR_WARP_MINBLOCKS 12
 #endif
-__global__ void __launch_bounds__(128, HR_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A) {
-    const int cx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+#ifndef HR_WARP_MINBLOCKS_WIDE
+#define HR_WARP_MINBLOCKS_WIDE 8
+#endif
+template <typename T, int ROWS, int UW>
+__global__ void __launch_bounds__(128, (UW * sizeof(T) >= 16 ? HR_WARP_MINBLOCKS_WIDE : HR_WARP_MINBLOCKS))
+    warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A, const __grid_constant__ WarpBatch B) {
+    const int cx0 = (blockIdx.x * 32 + threadIdx.x) * UW;
     const int rg = blockIdx.y * 4 + threadIdx.y;
     if (cx0 >= P.aW) return;
+    /* blend scalars and output planes of this output frame; P.t12 / P.t21 / P.outY / P.outUV are not used here */
+    const int z = blockIdx.z;
     if (rg < A.lumaGroups) {
-        warp_fast_thread<T, ROWS, false>(P, A, cx0, (A.lumaG0 + rg) * ROWS);
+        warp_unit<T, ROWS, UW, false>(P, A, B, z, (T *)B.outY[z], cx0, (A.lumaG0 + rg) * ROWS);
     } else if (rg - A.lumaGroups < A.chromaGN) {
         const int cy0 = (A.chromaG0 + rg - A.lumaGroups) * ROWS;
-        if (cy0 < (P.H >> 1)) warp_fast_thread<T, ROWS, true>(P, A, cx0, cy0);
+        if (cy0 < (P.H >> 1)) warp_unit<T, ROWS, UW, true>(P, A, B, z, (T *)B.outUV[z], cx0, cy0);
     }
 }
 

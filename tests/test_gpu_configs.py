@@ -159,5 +159,5 @@ def test_4k_p010_24_to_144_replay_through_the_c_host(hr, oracle, synth, mode):
 
 def test_frames_taller_than_8k_are_refused(hr):
     with pytest.raises(hr.HrError, match="not supported"):
-        hr.HrCuda(4322, 256, 256)
+        hr.HrCuda(4352, 256, 256)
     hr.HrCuda(4320, 64, 64).close()
