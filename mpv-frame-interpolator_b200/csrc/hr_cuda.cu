@@ -25,10 +25,6 @@
 #define HR_FLOW_BUFS 4   /* blurred-flow ring: one being written per search lane, the rest read by warps in flight */
 #define HR_SEARCH_LANES 2
 #define HR_MAX_WARP_EVENTS 8
-#ifndef HR_WARP_ROWS
-#define HR_WARP_ROWS 4
-#endif
-#define HR_WARP_ROWS_DEFAULT HR_WARP_ROWS
 
 struct HrContext {
     int H, W, aW, pixfmt, bps;
@@ -959,7 +955,7 @@ template <typename T>
 static void launch_wide16(dim3 grid, dim3 block, cudaStream_t st, const WarpParams<T> &P, const WarpFastArgs &A, const WarpBatch &B);
 template <>
 void launch_wide16<uint8_t>(dim3 grid, dim3 block, cudaStream_t st, const WarpParams<uint8_t> &P, const WarpFastArgs &A, const WarpBatch &B) {
-    warp_fast_kernel<uint8_t, HR_WARP_ROWS_DEFAULT, 16><<<grid, block, 0, st>>>(P, A, B);
+    warp_fast_kernel<uint8_t, 16><<<grid, block, 0, st>>>(P, A, B);
 }
 template <>
 void launch_wide16<uint16_t>(dim3, dim3, cudaStream_t, const WarpParams<uint16_t> &, const WarpFastArgs &, const WarpBatch &) {} /* 32-byte units are not built */
@@ -1010,24 +1006,14 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
     P.t21 = 1.0f - ts[0];
     P.black = black;
     P.white = white;
-    /* thread = UW samples x 4 rows (cells of 8 rows and more are covered by several threads: measured, smaller
-     * units and more resident warps beat fewer flow look-ups per sample); row groups of the luma plane, then of the
-     * chroma plane */
-    const int ROWS = HR_WARP_ROWS;
     int r0 = 0, r1 = ctx->H;
     if (ctx->bandWorld > 1) {
         r0 = ctx->bandRow0[ctx->bandRank];
         r1 = ctx->bandRow1[ctx->bandRank];
     }
-    /* band boundaries are multiples of 2^(s+1) rows, so luma and chroma row groups do not straddle them */
     WarpFastArgs A;
     memset(&A, 0, sizeof(A));
-    A.lumaG0 = r0 / ROWS;
-    A.lumaGroups = (r1 + ROWS - 1) / ROWS - A.lumaG0;
-    A.chromaG0 = (r0 >> 1) / ROWS;
-    A.chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - A.chromaG0;
     A.white = white;
-    const int groups = A.lumaGroups + A.chromaGN;
     /* level constants (hr_warp.cuh: 8-bit = the reference's expressions as NVIDIA OpenCL compiles them — also what the
      * HSV mode of P010 uses; 16-bit = DESIGN.md §P010, correctly rounded reciprocals) */
     const bool is16 = sizeof(T) == 2 && mode != HR_MODE_HSV_FLOW;
@@ -1093,6 +1079,15 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
         const uintptr_t ub = (uintptr_t)uw * sizeof(T);
         if (ctx->W % uw == 0 && ctx->aW >= 2 * uw && align % ub == 0) break;
     }
+    /* thread = uw samples x ROWS rows (cells taller than that are covered by several threads: measured, smaller units
+     * and more resident warps beat fewer flow look-ups per sample); row groups of the luma plane, then of the chroma
+     * plane. Band boundaries are multiples of 2^(s+1) rows, so row groups do not straddle them. */
+    const int ROWS = warp_rows((uw >= 4 ? uw : 4) * (int)sizeof(T));
+    A.lumaG0 = r0 / ROWS;
+    A.lumaGroups = (r1 + ROWS - 1) / ROWS - A.lumaG0;
+    A.chromaG0 = (r0 >> 1) / ROWS;
+    A.chromaGN = ((r1 >> 1) + ROWS - 1) / ROWS - A.chromaG0;
+    const int groups = A.lumaGroups + A.chromaGN;
     const int fast = ctx->useFastWarp && ctx->s >= 2 && uw >= 4 && mode != HR_MODE_SIDE_BY_SIDE_2 && tsOk && denOk && ctx->H >= 2 * (ROWS + 2);
     /* pipelined: warps into caller-owned planes are independent of one another -> round-robin over the warp
      * streams, each after the search that produced the flow; warps into the internal output frame stay on the
@@ -1126,9 +1121,12 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
                 B.outUV[i] = outUV[i0 + i];
             }
             dim3 block(32, 4);
-            dim3 grid((ctx->aW + 32 * uw - 1) / (32 * uw), (groups + 3) / 4, B.n);
-            if (uw == 4) warp_fast_kernel<T, HR_WARP_ROWS, 4><<<grid, block, 0, st>>>(P, A, B);
-            else if (uw == 8) warp_fast_kernel<T, HR_WARP_ROWS, 8><<<grid, block, 0, st>>>(P, A, B);
+            A.unitsX = (ctx->aW + uw - 1) / uw;
+            A.edgeBlocks = (2 * groups + 127) / 128;
+            A.coreBlocksX = A.unitsX > 2 ? (A.unitsX - 2 + 31) / 32 : 0;
+            dim3 grid(A.edgeBlocks + A.coreBlocksX * ((groups + 3) / 4), 1, B.n);
+            if (uw == 4) warp_fast_kernel<T, 4><<<grid, block, 0, st>>>(P, A, B);
+            else if (uw == 8) warp_fast_kernel<T, 8><<<grid, block, 0, st>>>(P, A, B);
             else launch_wide16<T>(grid, block, st, P, A, B);
             ctx->launches++;
         }

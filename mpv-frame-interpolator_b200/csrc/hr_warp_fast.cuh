@@ -48,6 +48,7 @@ struct WarpBatch {
 
 struct WarpFastArgs {
     int lumaGroups, lumaG0, chromaG0, chromaGN; /* row groups of the launch: luma first, then chroma       */
+    int unitsX, edgeBlocks, coreBlocksX;        /* unit columns; CTAs of the two edge columns; CTAs per row of the rest */
     /* level map, per plane kind [0] luma [1] chroma. 8-bit (NV12, and the HSV mode of either format): sub = black /
      * 128, rcp = MUFU.RCP of den (read back from the device by the host once per knob setting). 16-bit: sub = b16 /
      * 32768, rcp = correctly rounded reciprocal (host). */
@@ -95,53 +96,64 @@ __device__ __forceinline__ void vec_store(unsigned char *p, const Vec<4> &v) { *
 __device__ __forceinline__ void vec_store(unsigned char *p, const Vec<8> &v) { *reinterpret_cast<uint2 *>(p) = make_uint2(v.w[0], v.w[1]); }
 __device__ __forceinline__ void vec_store(unsigned char *p, const Vec<16> &v) { *reinterpret_cast<uint4 *>(p) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]); }
 
+/* bytes per source load by unit size (tools/diag_warp.py): HR_WARP_LG8 in {4, 8}, HR_WARP_LG16 in {4, 8, 16} */
+#ifndef HR_WARP_LG8
+#define HR_WARP_LG8 4
+#endif
+#ifndef HR_WARP_LG16
+#define HR_WARP_LG16 8
+#endif
+__host__ __device__ constexpr int warp_load_bytes(int unitBytes) { return unitBytes >= 16 ? HR_WARP_LG16 : (unitBytes >= 8 ? HR_WARP_LG8 : 4); }
+
 /* ---- source runs ----------------------------------------------------------------------------------------- */
-/* Where a unit's source block starts: the aligned vector that holds its first sample, the run's word and bit offset
- * inside it. An odd chroma displacement starts one sample earlier (pair-aligned) and reads one word more. */
-template <int UB, bool IS16>
+/* Where a unit's source block starts, and how it is fetched: aligned loads of LG bytes (LG <= UB; LG = UB: two loads per
+ * row, LG = 4: one per word) from the one that holds the run's first sample; the run's word and bit offset inside it.
+ * An odd chroma displacement starts one sample earlier (pair-aligned) and reads one word more. */
+template <int UB, int LG, bool IS16>
 struct RunSource {
-    static constexpr int NW = UB / 4;
+    static constexpr int NW = UB / 4;          /* words per run                          */
+    static constexpr int LW = LG / 4;          /* words per load                         */
+    static constexpr int NL = UB / LG + 1;     /* loads that can be needed               */
     const unsigned char *base;
     unsigned wordOff, bitOff;
-    bool second, odd;
+    bool last, odd;
     size_t pitch;
     __device__ __forceinline__ void set(const void *plane, long long firstSample, size_t pitchBytes, bool oddDisplacement) {
         odd = oddDisplacement;
         if (odd) firstSample -= 1;
         const uintptr_t a = (uintptr_t)plane + (uintptr_t)(firstSample * (IS16 ? 2 : 1));
-        const unsigned k = (unsigned)(a & (UB - 1));
+        const unsigned k = (unsigned)(a & (LG - 1));
         base = reinterpret_cast<const unsigned char *>(a - k);
         wordOff = k >> 2;
         bitOff = (k & 3u) * 8u;
-        second = k != 0 || odd; /* the run ends in the next vector */
+        last = k != 0 || odd; /* the run ends in the last load */
         pitch = pitchBytes;
     }
     /* the UW samples of row r, in output order */
     template <bool CHROMA>
     __device__ __forceinline__ Vec<UB> row(int r) const {
         const unsigned char *p = base + (size_t)r * pitch;
-        const Vec<UB> lo = vec_load<UB>(p);
-        Vec<UB> hi;
+        uint32_t w[NL * LW + 2];
 #pragma unroll
-        for (int i = 0; i < NW; ++i) hi.w[i] = 0u;
-        if (second) hi = vec_load<UB>(p + UB);
-        uint32_t w[2 * NW + 2];
+        for (int l = 0; l < NL; ++l) {
+            Vec<LG> v;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            w[i] = lo.w[i];
-            w[NW + i] = hi.w[i];
+            for (int i = 0; i < LW; ++i) v.w[i] = 0u;
+            if (l + 1 < NL || last) v = vec_load<LG>(p + l * LG);
+#pragma unroll
+            for (int i = 0; i < LW; ++i) w[l * LW + i] = v.w[i];
         }
-        w[2 * NW] = w[2 * NW + 1] = 0u;
-        /* barrel: shift the 2 NW words down by wordOff (one conditional move per word and offset bit) ... */
-        if (NW >= 4) {
+        w[NL * LW] = w[NL * LW + 1] = 0u;
+        /* barrel: shift the words down by wordOff (one conditional move per word and offset bit) ... */
+        if (LW >= 4) {
             const bool by2 = wordOff & 2u;
 #pragma unroll
-            for (int i = 0; i < 2 * NW; ++i) w[i] = by2 ? w[i + 2] : w[i];
+            for (int i = 0; i < NL * LW; ++i) w[i] = by2 ? w[i + 2] : w[i];
         }
-        if (NW >= 2) {
+        if (LW >= 2) {
             const bool by1 = wordOff & 1u;
 #pragma unroll
-            for (int i = 0; i < 2 * NW; ++i) w[i] = by1 ? w[i + 1] : w[i];
+            for (int i = 0; i < NL * LW; ++i) w[i] = by1 ? w[i + 1] : w[i];
         }
         /* ... and by bitOff inside the words */
         uint32_t o[NW + 1];
@@ -258,11 +270,19 @@ __device__ __noinline__ void border_unit(const WarpParams<T> &P, const WarpFastA
     const T *s21 = CHROMA ? P.f2uv : P.f2y;
     const size_t pitch = (size_t)P.W * sizeof(T);
     const int mode = P.mode;
-#pragma unroll 1
+    /* every row's samples first (all loads in flight together: one memory round trip per unit, like the interior
+     * path), then the arithmetic */
+    Run ra[ROWS], rb[ROWS];
+#pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        Run a = Run(), b = Run();
-        if (mode != HR_MODE_WARPED_21) a = border_row<UB, is16>(s12 + (size_t)reflect_inner(b12 + r, planeH) * P.W, cx0, d.x1, P.aW, CHROMA);
-        if (mode != HR_MODE_WARPED_12) b = border_row<UB, is16>(s21 + (size_t)reflect_inner(b21 + r, planeH) * P.W, cx0, d.x2, P.aW, CHROMA);
+        ra[r] = Run();
+        rb[r] = Run();
+        if (mode != HR_MODE_WARPED_21) ra[r] = border_row<UB, is16>(s12 + (size_t)reflect_inner(b12 + r, planeH) * P.W, cx0, d.x1, P.aW, CHROMA);
+        if (mode != HR_MODE_WARPED_12) rb[r] = border_row<UB, is16>(s21 + (size_t)reflect_inner(b21 + r, planeH) * P.W, cx0, d.x2, P.aW, CHROMA);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const Run a = ra[r], b = rb[r];
         Run o;
         if (mode == HR_MODE_WARPED_12) o = a;
         else if (mode == HR_MODE_WARPED_21) o = b;
@@ -350,7 +370,7 @@ __device__ __forceinline__ void warp_unit(const WarpParams<T> &P, const WarpFast
     auto rows = [&](auto varTag) {
         constexpr int VAR = decltype(varTag)::value;
         Run ra[ROWS], rb[ROWS];
-        RunSource<UB, is16> A12, A21;
+        RunSource<UB, warp_load_bytes(UB), is16> A12, A21;
         if (VAR != 0 || mode == 0) {
             A12.set(s12, (long long)b12 * P.W + a12, pitch, CHROMA && (d.x1 & 1));
 #pragma unroll
@@ -379,22 +399,52 @@ __device__ __forceinline__ void warp_unit(const WarpParams<T> &P, const WarpFast
     }
 }
 
-/* grid: x = column blocks of 32 units, y = groups of 4 row groups (row groups of the luma plane first, then of the
- * chroma plane), z = output frame of the batch.
+/* grid: x = CTAs (edge columns first, see the kernel), z = output frame of the batch; row groups of the luma plane
+ * first, then of the chroma plane.
  * HR_WARP_MINBLOCKS 128-thread CTAs per SM: the kernel is latency-bound at 4K and above, resident warps are what hides
  * its three dependent round trips (flow word -> flipped flow word -> samples). */
-#ifndef HR_WARP_MINBLOCKS
-#define HR_WARP_MINBLOCKS 12
+/* rows per unit and CTAs per SM by unit size in bytes (tools/diag_warp.py sweeps them through tools/build_variant.py) */
+#ifndef HR_WARP_ROWS4
+#define HR_WARP_ROWS4 4
 #endif
-#ifndef HR_WARP_MINBLOCKS_WIDE
-#define HR_WARP_MINBLOCKS_WIDE 8
+#ifndef HR_WARP_ROWS8
+#define HR_WARP_ROWS8 4
 #endif
-template <typename T, int ROWS, int UW>
-__global__ void __launch_bounds__(128, (UW * sizeof(T) >= 16 ? HR_WARP_MINBLOCKS_WIDE : HR_WARP_MINBLOCKS))
+#ifndef HR_WARP_ROWS16
+#define HR_WARP_ROWS16 4
+#endif
+#ifndef HR_WARP_MB4
+#define HR_WARP_MB4 12
+#endif
+#ifndef HR_WARP_MB8
+#define HR_WARP_MB8 12
+#endif
+#ifndef HR_WARP_MB16
+#define HR_WARP_MB16 8
+#endif
+__host__ __device__ constexpr int warp_rows(int unitBytes) { return unitBytes >= 16 ? HR_WARP_ROWS16 : (unitBytes >= 8 ? HR_WARP_ROWS8 : HR_WARP_ROWS4); }
+__host__ __device__ constexpr int warp_min_blocks(int unitBytes) { return unitBytes >= 16 ? HR_WARP_MB16 : (unitBytes >= 8 ? HR_WARP_MB8 : HR_WARP_MB4); }
+template <typename T, int UW>
+__global__ void __launch_bounds__(128, warp_min_blocks(UW * (int)sizeof(T)))
     warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A, const __grid_constant__ WarpBatch B) {
-    const int cx0 = (blockIdx.x * 32 + threadIdx.x) * UW;
-    const int rg = blockIdx.y * 4 + threadIdx.y;
-    if (cx0 >= P.aW) return;
+    constexpr int ROWS = warp_rows(UW * (int)sizeof(T));
+    /* The first and the last unit column are where displaced runs leave the picture (every row has one on each side,
+     * and a single such unit would drag its whole warp through the reflected path): they get CTAs of their own — the
+     * first A.edgeBlocks, lane = (row group, side), so that a warp holds 32 of them. The other columns follow, 32 units
+     * x 4 row groups per CTA. */
+    int ux, rg;
+    if ((int)blockIdx.x < A.edgeBlocks) {
+        const int e = blockIdx.x * 128 + threadIdx.y * 32 + threadIdx.x;
+        rg = e >> 1;
+        ux = (e & 1) ? A.unitsX - 1 : 0;
+    } else {
+        const int b = blockIdx.x - A.edgeBlocks;
+        const int by = b / A.coreBlocksX;
+        ux = 1 + (b - by * A.coreBlocksX) * 32 + threadIdx.x;
+        if (ux >= A.unitsX - 1) return;
+        rg = by * 4 + threadIdx.y;
+    }
+    const int cx0 = ux * UW;
     /* blend scalars and output planes of this output frame; P.t12 / P.t21 / P.outY / P.outUV are not used here */
     const int z = blockIdx.z;
     if (rg < A.lumaGroups) {

@@ -37,7 +37,7 @@ for name in names:
     w, h, pf = CASES[name]
     bps = 2 if pf else 1
     tdt = torch.uint16 if pf else torch.uint8
-    c = synth.MovingTextureClip(w, h, pixfmt=pf) if h <= 2160 else None
+    c = synth.MovingTextureClip(w, h, pixfmt=pf)
     g = hr.HrCuda(h, w, w, pf)
     g.set_stream(stream.cuda_stream)
     if c is None:      # 8K: a cheap pair (noise shifted by a few pixels), the warp's time does not depend on the picture
