@@ -1122,7 +1122,7 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
             }
             dim3 block(32, 4);
             A.unitsX = (ctx->aW + uw - 1) / uw;
-            A.edgeBlocks = (2 * groups + 127) / 128;
+            A.edgeBlocks = (2 * groups * ROWS + 127) / 128; /* the two edge columns as single-row units */
             A.coreBlocksX = A.unitsX > 2 ? (A.unitsX - 2 + 31) / 32 : 0;
             dim3 grid(A.edgeBlocks + A.coreBlocksX * ((groups + 3) / 4), 1, B.n);
             if (uw == 4) warp_fast_kernel<T, 4><<<grid, block, 0, st>>>(P, A, B);
@@ -1260,8 +1260,20 @@ extern "C" int hr_warp_batch(HrContext *ctx, int nWarps, const float *blendingSc
     if (nWarps == 0) return 0;
     if (bind_device(ctx)) return 1;
     if (!ctx->pipeline && ctx->sPack && pipe_join(ctx)) return 1; /* leftovers of an earlier pipelined phase */
-    return ctx->bps == 1 ? launch_warp<uint8_t>(ctx, nWarps, blendingScalars, outY, outUV, frameOutputMode, blackLevel, whiteLevel, 1)
-                         : launch_warp<uint16_t>(ctx, nWarps, blendingScalars, outY, outUV, frameOutputMode, blackLevel, whiteLevel, 1);
+    /* developer knob HR_WARP_SPLIT=k: at most k outputs per launch (each launch on the next warp stream) */
+    static int split = -1;
+    if (split < 0) {
+        const char *e = getenv("HR_WARP_SPLIT");
+        split = e ? atoi(e) : 0;
+    }
+    const int per = split > 0 ? split : nWarps;
+    for (int i = 0; i < nWarps; i += per) {
+        const int n = nWarps - i < per ? nWarps - i : per;
+        if (ctx->bps == 1 ? launch_warp<uint8_t>(ctx, n, blendingScalars + i, outY + i, outUV + i, frameOutputMode, blackLevel, whiteLevel, 1)
+                          : launch_warp<uint16_t>(ctx, n, blendingScalars + i, outY + i, outUV + i, frameOutputMode, blackLevel, whiteLevel, 1))
+            return 1;
+    }
+    return 0;
 }
 
 /* nSteps consecutive source frames in one call (hr_step_device in a loop): warps of step i use

@@ -428,25 +428,32 @@ template <typename T, int UW>
 __global__ void __launch_bounds__(128, warp_min_blocks(UW * (int)sizeof(T)))
     warp_fast_kernel(const __grid_constant__ WarpParams<T> P, const __grid_constant__ WarpFastArgs A, const __grid_constant__ WarpBatch B) {
     constexpr int ROWS = warp_rows(UW * (int)sizeof(T));
-    /* The first and the last unit column are where displaced runs leave the picture (every row has one on each side,
-     * and a single such unit would drag its whole warp through the reflected path): they get CTAs of their own — the
-     * first A.edgeBlocks, lane = (row group, side), so that a warp holds 32 of them. The other columns follow, 32 units
-     * x 4 row groups per CTA. */
-    int ux, rg;
+    /* The first and the last unit column always touch the picture's border (an undisplaced column 0 reads column 1,
+     * hr_warp.cuh reflect_inner): their units take the reflected path, which is several times longer than the interior
+     * one, and a single such unit would drag its whole warp through it. They get CTAs of their own — the first
+     * A.edgeBlocks — as single-row units, lane = (row, side), so that the long path is spread over ROWS times as many
+     * threads and is not what the launch waits for. The other columns follow, 32 units x 4 row groups per CTA. */
+    const int z = blockIdx.z;
     if ((int)blockIdx.x < A.edgeBlocks) {
         const int e = blockIdx.x * 128 + threadIdx.y * 32 + threadIdx.x;
-        rg = e >> 1;
-        ux = (e & 1) ? A.unitsX - 1 : 0;
-    } else {
-        const int b = blockIdx.x - A.edgeBlocks;
-        const int by = b / A.coreBlocksX;
-        ux = 1 + (b - by * A.coreBlocksX) * 32 + threadIdx.x;
-        if (ux >= A.unitsX - 1) return;
-        rg = by * 4 + threadIdx.y;
+        const int row = e >> 1;                       /* row of the launch: luma rows first, then chroma rows */
+        const int cx0 = (e & 1) ? (A.unitsX - 1) * UW : 0;
+        const int lumaRows = A.lumaGroups * ROWS;
+        if (row < lumaRows) {
+            const int cy0 = A.lumaG0 * ROWS + row;
+            if (cy0 < P.H) warp_unit<T, 1, UW, false>(P, A, B, z, (T *)B.outY[z], cx0, cy0);
+        } else if (row - lumaRows < A.chromaGN * ROWS) {
+            const int cy0 = A.chromaG0 * ROWS + row - lumaRows;
+            if (cy0 < (P.H >> 1)) warp_unit<T, 1, UW, true>(P, A, B, z, (T *)B.outUV[z], cx0, cy0);
+        }
+        return;
     }
+    const int b = blockIdx.x - A.edgeBlocks;
+    const int by = b / A.coreBlocksX;
+    const int ux = 1 + (b - by * A.coreBlocksX) * 32 + threadIdx.x;
+    if (ux >= A.unitsX - 1) return;
+    const int rg = by * 4 + threadIdx.y;
     const int cx0 = ux * UW;
-    /* blend scalars and output planes of this output frame; P.t12 / P.t21 / P.outY / P.outUV are not used here */
-    const int z = blockIdx.z;
     if (rg < A.lumaGroups) {
         warp_unit<T, ROWS, UW, false>(P, A, B, z, (T *)B.outY[z], cx0, (A.lumaG0 + rg) * ROWS);
     } else if (rg - A.lumaGroups < A.chromaGN) {
