@@ -142,6 +142,16 @@ int hr_warp_batch(HrContext *ctx, int nWarps, const float *blendingScalars, int 
  * planes; `seconds` (may be NULL) receives warp-start -> download-end (= warpCalcTime). */
 int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds);
 
+/* Zero-copy hand-off (frames that arrive as IMGFMT_CUDA, video/img_format.h:274, and leave as such):
+ * hr_update_frame_device(borrow = 1) takes the decoder's device planes, hr_set_output_device + hr_warp write into the
+ * device image that travels on, hr_finish waits until everything enqueued is complete and reports the time since the
+ * start of the most recent hr_warp (the warpCalcTime of a frame that is never downloaded, HR/opticalFlowCalc.c:117-122).
+ * hr_debug_host_transfer_bytes: bytes the interface calls have moved across PCIe in this process so far (uploads of
+ * hr_update_frame / hr_band_upload, downloads of hr_download / hr_band_download) — a zero-copy integration leaves both
+ * counters where they were. */
+int hr_finish(HrContext *ctx, double *seconds);
+int hr_debug_host_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
+
 /* Device-side view of the output frame (zero-copy hand-off to a CUDA VO; N2). Valid until the
  * next hr_warp on this context; ordered on the context's stream. */
 int hr_get_output_device(HrContext *ctx, void **dYPlane, void **dUvPlane);

@@ -61,6 +61,8 @@ ABI = {
     "hr_warp": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]),
     "hr_warp_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "hr_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "hr_debug_host_transfer_bytes": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_band_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -138,6 +140,13 @@ def debug_rcp_table(n=1024):
     if load_library().hr_debug_rcp_table(_ptr(out), n):
         raise HrError(load_library().hr_last_error(None).decode())
     return out
+
+
+def host_transfer_bytes():
+    """(host->device, device->host) bytes moved by the interface calls in this process so far."""
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    load_library().hr_debug_host_transfer_bytes(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def debug_int_peak(device=-1):
@@ -249,6 +258,11 @@ class HrCuda:
         sec = C.c_double(0.0)
         self._chk(self.lib.hr_download(self.h, _ptr(y), _ptr(uv), C.byref(sec)))
         return y, uv, sec.value
+
+    def finish(self):
+        sec = C.c_double(0.0)
+        self._chk(self.lib.hr_finish(self.h, C.byref(sec)))
+        return sec.value
 
     def output_device_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()

@@ -121,6 +121,9 @@ struct HrContext {
 };
 
 static char g_createErr[256];
+/* bytes that crossed the host <-> device boundary on behalf of the six interface calls (not the parity taps):
+ * hr_debug_host_transfer_bytes; what a zero-copy integration must leave untouched */
+static unsigned long long g_h2dBytes, g_d2hBytes;
 
 static int fail(HrContext *ctx, const char *fmt, ...) {
     char *dst = ctx ? ctx->err : g_createErr;
@@ -749,6 +752,7 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
         CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
     }
+    g_h2dBytes += ylen + uvlen;
     ctx->fy[1] = dst;
     ctx->fuv[1] = dst + ylen;
     ctx->fslot[1] = slot;
@@ -1179,7 +1183,7 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
     if (mode < 0 || mode > 6) return fail(ctx, "hr_warp: unknown output mode %d", mode);
     if (bind_device(ctx)) return 1;
     if (!ctx->pipeline && ctx->sPack && pipe_join(ctx)) return 1; /* leftovers of an earlier pipelined phase */
-    if (!pipe_on(ctx) || ctx->outY == ctx->outBuf) CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
+    CU(cudaEventRecord(ctx->evWarpStart, ctx->stream));
     const int internal = ctx->outY == ctx->outBuf;
     if (internal) {
         /* history for hr_download's guess of the next blending scalar (vf_HopperRender.c:371-374: t advances by a
@@ -1304,6 +1308,7 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
         CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(uvPlane, ctx->outUV, uvlen, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    g_d2hBytes += ylen + uvlen;
     CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
     if (warp_ahead(ctx)) return 1;
     CU(cudaEventSynchronize(ctx->evDlEnd));
@@ -1456,6 +1461,7 @@ extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvB
     const cudaMemcpyKind kind = sourceIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CU(cudaMemcpyAsync(dst + (size_t)r0 * rowBytes, yBand, (size_t)(r1 - r0) * rowBytes, kind, ctx->stream));
     CU(cudaMemcpyAsync(dst + ylen + (size_t)(r0 >> 1) * rowBytes, uvBand, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes, kind, ctx->stream));
+    if (!sourceIsDevice) g_h2dBytes += (size_t)(r1 - r0) * rowBytes + (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes;
     band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 0, n + 1);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -1509,12 +1515,39 @@ extern "C" int hr_band_download(HrContext *ctx, void *yBand, void *uvBand, doubl
     CU(cudaMemcpyAsync(yBand, (const unsigned char *)ctx->outY + (size_t)r0 * rowBytes, (size_t)(r1 - r0) * rowBytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(uvBand, (const unsigned char *)ctx->outUV + (size_t)(r0 >> 1) * rowBytes, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes, cudaMemcpyDeviceToHost,
                        ctx->stream));
+    g_d2hBytes += (size_t)(r1 - r0) * rowBytes + (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes;
     CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
     CU(cudaEventSynchronize(ctx->evDlEnd));
     if (seconds) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
             cudaGetLastError();
+            ms = 0.f;
+        }
+        *seconds = (double)ms * 1e-3;
+    }
+    return 0;
+}
+
+extern "C" int hr_debug_host_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h) {
+    if (h2d) *h2d = g_h2dBytes;
+    if (d2h) *d2h = g_d2hBytes;
+    return 0;
+}
+
+/* Everything enqueued so far is complete when this returns (outputs in caller-owned device planes included);
+ * seconds: device time from the start of the most recent hr_warp to now (= warpCalcTime of a frame that is not
+ * downloaded, opticalFlowCalc.c:117-122). */
+extern "C" int hr_finish(HrContext *ctx, double *seconds) {
+    if (!ctx) return 1;
+    if (bind_device(ctx)) return 1;
+    if (pipe_join(ctx)) return 1;
+    CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evDlEnd));
+    if (seconds) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
+            cudaGetLastError(); /* no warp was recorded yet */
             ms = 0.f;
         }
         *seconds = (double)ms * 1e-3;

@@ -49,6 +49,31 @@ bool warpFrames(struct OpticalFlowCalc *ofc, const float blendingScalar, const i
     return 0;
 }
 
+/* ---- device-resident frames (no reference counterpart) ---- */
+bool updateFrameDevice(struct OpticalFlowCalc *ofc, unsigned char **devicePlanes) {
+    if (!ofc->isInitialized) return 1;
+    CHECK_ERROR(hr_update_frame_device((HrContext *)ofc->impl, devicePlanes[0], devicePlanes[1], 1));
+    return 0;
+}
+
+bool warpFramesToDevice(struct OpticalFlowCalc *ofc, const float blendingScalar, const int frameOutputMode, unsigned char **devicePlanes) {
+    if (!ofc->isInitialized) return 1;
+    HrContext *ctx = (HrContext *)ofc->impl;
+    CHECK_ERROR(hr_set_output_device(ctx, devicePlanes[0], devicePlanes[1]));
+    const int failed = hr_warp(ctx, blendingScalar, frameOutputMode, ofc->outputBlackLevel, ofc->outputWhiteLevel);
+    hr_set_output_device(ctx, NULL, NULL);
+    CHECK_ERROR(failed);
+    return 0;
+}
+
+bool finishFrames(struct OpticalFlowCalc *ofc) {
+    if (!ofc->isInitialized) return 1;
+    double seconds = 0.0;
+    CHECK_ERROR(hr_finish((HrContext *)ofc->impl, &seconds));
+    ofc->warpCalcTime = seconds;
+    return 0;
+}
+
 /* reference :236-253 (the struct itself belongs to the filter) */
 void freeOFC(struct OpticalFlowCalc *ofc) {
     if (ofc->impl) hr_destroy((HrContext *)ofc->impl);

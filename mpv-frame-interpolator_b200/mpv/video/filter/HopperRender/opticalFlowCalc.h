@@ -46,4 +46,15 @@ bool downloadFrame(struct OpticalFlowCalc *ofc, unsigned char **outputPlanes);
 bool calculateOpticalFlow(struct OpticalFlowCalc *ofc);
 bool warpFrames(struct OpticalFlowCalc *ofc, const float blendingScalar, const int frameOutputMode);
 
+/* Frames that live in device memory (IMGFMT_CUDA in and out, video/img_format.h:274; no reference counterpart — the
+ * reference moves every frame through host memory, reference :98-100, :112-114). Same convention: 0 = success.
+ * devicePlanes[0] = Y, [1] = interleaved UV, CUDA device pointers with the stride given at init.
+ *   updateFrameDevice   the new source frame is used in place: the caller keeps it alive and unchanged until two further
+ *                       updateFrame* calls have been made (the filter holds a reference to the last two source images)
+ *   warpFramesToDevice  warpFrames into a device image (not the source images of the pair); enqueue-only
+ *   finishFrames        waits until every frame warped so far is complete; sets warpCalcTime like downloadFrame does */
+bool updateFrameDevice(struct OpticalFlowCalc *ofc, unsigned char **devicePlanes);
+bool warpFramesToDevice(struct OpticalFlowCalc *ofc, const float blendingScalar, const int frameOutputMode, unsigned char **devicePlanes);
+bool finishFrames(struct OpticalFlowCalc *ofc);
+
 #endif /* OPTICALFLOWCALC_H */

@@ -104,6 +104,26 @@ def main():
             subprocess.run([CC, "-shared", "-o", str(OUT / "libhr_filter_sim_p010.so"), o1, o2, o3,
                             "-L", str(csrc), "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../mpv-frame-interpolator_b200/csrc", "-lm", "-lpthread"], check=True)
         print("build_ref: built", OUT / "libhr_filter_sim_p010.so", "(the same, P010)")
+        # 5. the filter with this repository's patch series applied (patches/*.patch: P010 negotiation, the headless
+        #    control channel, IMGFMT_CUDA in and out). The patches are applied to a scratch copy of the reference's
+        #    source that lives only while this step runs; the harness gets the CUDA runtime for its device images.
+        patches = sorted((root / "patches").glob("*.patch"))
+        cudart = next((d for d in ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib") if (pathlib.Path(d) / "libcudart.so").exists()), None)
+        if patches and cudart:
+            with tempfile.TemporaryDirectory(dir=str(OUT)) as td:
+                work = pathlib.Path(td) / "video" / "filter" / "HopperRender"
+                work.mkdir(parents=True)
+                (work / "vf_HopperRender.c").write_bytes((REF / "vf_HopperRender.c").read_bytes())
+                for pt in patches:
+                    subprocess.run(["patch", "-p1", "-s", "-d", td, "-i", str(pt)], check=True)
+                cmd = [CC, "-O2", "-std=gnu11", "-w", "-fPIC", "-shared", "-DHR_SIM_CUDA", "-include", str(pkg_hr / "opticalFlowCalc.h"),
+                       "-I", str(pkg_hr), "-I", str(HERE / "mpv_shim"), "-I", str(root / "include"),
+                       "-o", str(OUT / "libhr_filter_sim_patched.so"),
+                       str(work / "vf_HopperRender.c"), str(HERE / "filter_host_sim.c"), str(pkg_hr / "opticalFlowCalc.c"), str(pkg_hr / "hrControl.c"),
+                       "-L", str(csrc), "-lhopperrender_cuda", "-Wl,-rpath,$ORIGIN/../../mpv-frame-interpolator_b200/csrc",
+                       "-L", cudart, "-lcudart", "-Wl,-rpath," + cudart, "-lm", "-lpthread"]
+                subprocess.run(cmd, check=True)
+            print("build_ref: built", OUT / "libhr_filter_sim_patched.so", "(reference filter + patches/%s)" % ", ".join(p.name for p in patches))
     else:
         print("build_ref: libhopperrender_cuda.so not built yet — filter host sim skipped")
     return 0

@@ -22,12 +22,25 @@ void talloc_free(void *p) { free(p); }
 #endif
 int hr_sim_bytes_per_sample(void) { return HR_SIM_BPS; }
 
-static struct mp_image *image_alloc(int w, int h) {
+/* device memory for the IMGFMT_CUDA images of the zero-copy build (HR_SIM_CUDA: linked against libcudart) */
+#ifdef HR_SIM_CUDA
+extern int cudaMalloc(void **p, size_t n);
+extern int cudaFree(void *p);
+extern int cudaMemset(void *p, int v, size_t n);
+#else
+static int cudaMalloc(void **p, size_t n) { (void)n; *p = NULL; return 1; }
+static int cudaFree(void *p) { (void)p; return 0; }
+static int cudaMemset(void *p, int v, size_t n) { (void)p; (void)v; (void)n; return 1; }
+#endif
+
+static int fmt_bps(int fmt) { return (fmt == IMGFMT_P010 || HR_SIM_BPS == 2) ? 2 : 1; }
+
+static struct mp_image *image_alloc(int w, int h, int fmt) {
     struct mp_image *img = calloc(1, sizeof(*img));
-    const int stride = (w * HR_SIM_BPS + 63) & ~63; /* mpv aligns strides to 64 bytes (video/mp_image.h:35) */
+    const int stride = (w * fmt_bps(fmt) + 63) & ~63; /* mpv aligns strides to 64 bytes (video/mp_image.h:35) */
     img->w = w;
     img->h = h;
-    img->imgfmt = IMGFMT_NV12;
+    img->imgfmt = fmt;
     img->storage = malloc((size_t)stride * h * 3 / 2 + 64);
     img->planes[0] = img->storage;
     img->planes[1] = img->storage + (size_t)stride * h;
@@ -47,6 +60,7 @@ void mp_image_unrefp(struct mp_image **p) {
     if (!img) return;
     if (--*img->refcount == 0) {
         free(img->storage);
+        if (img->deviceStorage) cudaFree(img->deviceStorage);
         free(img->refcount);
     }
     free(img);
@@ -65,9 +79,82 @@ struct mp_image_pool *mp_image_pool_new(void *tparent) {
 }
 struct mp_image *mp_image_pool_get(struct mp_image_pool *pool, int fmt, int w, int h) {
     (void)pool;
-    (void)fmt;
-    return image_alloc(w, h);
+    return image_alloc(w, h, fmt);
 }
+
+/* ---- the slice of libavutil / mpv hardware-frame plumbing the IMGFMT_CUDA patch uses --------------------------- */
+static struct AVBufferRef g_deviceRef;          /* "the CUDA device": one per process here                 */
+struct SimFramesCtx {
+    struct AVBufferRef ref;                      /* ref.data -> ctx                                         */
+    AVHWFramesContext ctx;
+};
+static struct SimFramesCtx g_inputFrames;        /* the frames context the harness's input images claim      */
+AVFrame *av_frame_alloc(void) { return calloc(1, sizeof(AVFrame)); }
+void av_frame_free(AVFrame **frame) {
+    if (frame && *frame) free(*frame);
+    if (frame) *frame = NULL;
+}
+void av_buffer_unref(struct AVBufferRef **buf) {
+    if (buf && *buf && *buf != &g_inputFrames.ref) free(*buf); /* a SimFramesCtx starts with its ref */
+    if (buf) *buf = NULL;
+}
+bool mp_update_av_hw_frames_pool(struct AVBufferRef **hw_frames_ctx, struct AVBufferRef *hw_device_ctx, int imgfmt, int sw_imgfmt, int w, int h,
+                                 bool disable_multiplane) {
+    (void)disable_multiplane;
+    if (imgfmt != IMGFMT_CUDA || !hw_device_ctx || w < 1 || h < 1) return false;
+    if (*hw_frames_ctx) {
+        AVHWFramesContext *c = (void *)(*hw_frames_ctx)->data;
+        if (c->device_ref != hw_device_ctx || c->sw_format != sw_imgfmt || c->width != w || c->height != h) av_buffer_unref(hw_frames_ctx);
+    }
+    if (!*hw_frames_ctx) {
+        struct SimFramesCtx *n = calloc(1, sizeof(*n));
+        n->ref.data = (unsigned char *)&n->ctx;
+        n->ctx.device_ref = hw_device_ctx;
+        n->ctx.sw_format = sw_imgfmt;
+        n->ctx.width = w;
+        n->ctx.height = h;
+        *hw_frames_ctx = &n->ref;
+    }
+    return true;
+}
+static int g_deviceImagesAllocated;
+/* libavutil's CUDA frames: one allocation, the chroma plane behind the luma plane, pitch aligned to 256 bytes */
+int av_hwframe_get_buffer(struct AVBufferRef *hwframe_ctx, AVFrame *frame, int flags) {
+    (void)flags;
+    AVHWFramesContext *c = (void *)hwframe_ctx->data;
+    const int bps = c->sw_format == IMGFMT_P010 ? 2 : 1;
+    const int pitch = (c->width * bps + 255) & ~255;
+    void *d = NULL;
+    const size_t n = (size_t)pitch * c->height * 3 / 2;
+    if (cudaMalloc(&d, n) != 0 || !d) return -1;
+    cudaMemset(d, 0, n);
+    frame->data[0] = d;
+    frame->data[1] = (unsigned char *)d + (size_t)pitch * c->height;
+    frame->linesize[0] = frame->linesize[1] = pitch;
+    frame->width = c->width;
+    frame->height = c->height;
+    frame->hw_frames_ctx = hwframe_ctx;
+    ++g_deviceImagesAllocated;
+    return 0;
+}
+struct mp_image *mp_image_from_av_frame(AVFrame *src) {
+    AVHWFramesContext *c = (void *)src->hw_frames_ctx->data;
+    struct mp_image *img = calloc(1, sizeof(*img));
+    img->w = src->width;
+    img->h = src->height;
+    img->imgfmt = IMGFMT_CUDA;
+    img->params.hw_subfmt = c->sw_format;
+    img->hwctx = src->hw_frames_ctx;
+    img->planes[0] = src->data[0];
+    img->planes[1] = src->data[1];
+    img->stride[0] = src->linesize[0];
+    img->stride[1] = src->linesize[1];
+    img->deviceStorage = src->data[0];
+    img->refcount = malloc(sizeof(int));
+    *img->refcount = 1;
+    return img;
+}
+int hr_sim_device_images_allocated(void) { return g_deviceImagesAllocated; }
 void mp_image_pool_clear(struct mp_image_pool *pool) { (void)pool; }
 
 bool mp_frame_is_signaling(struct mp_frame frame) { return frame.type == MP_FRAME_EOF; }
@@ -187,13 +274,7 @@ const char *hr_sim_filter_name(void) { return vf_HopperRender.desc.name; }
 
 /* feed one NV12 (P010 build: P010) source frame (tightly packed planes of w x h samples) and run the filter until it stalls;
  * returns the number of output frames waiting, or -1 if the filter marked itself failed */
-int hr_sim_push(struct mp_filter_sim *s, const unsigned char *y, const unsigned char *uv, int w, int h, double pts, double nominalFps) {
-    struct mp_image *img = image_alloc(w, h);
-    const size_t rowBytes = (size_t)w * HR_SIM_BPS;
-    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * rowBytes, rowBytes);
-    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * rowBytes, rowBytes);
-    img->pts = pts;
-    img->nominal_fps = nominalFps;
+static int sim_run(struct mp_filter_sim *s, struct mp_image *img) {
     s->in.slot = MAKE_FRAME(MP_FRAME_VIDEO, img);
     s->in.has = true;
     do { /* filters/filter.c:211-263: run process() while somebody reports progress */
@@ -202,12 +283,75 @@ int hr_sim_push(struct mp_filter_sim *s, const unsigned char *y, const unsigned 
     } while (s->progress && !s->failed);
     return s->failed ? -1 : s->n_out;
 }
+/* the same for a frame that lives in device memory (IMGFMT_CUDA, as a CUDA decoder delivers it): dY / dUV are device
+ * pointers the caller keeps valid while the filter holds the frame (two source frames), pitch in bytes */
+int hr_sim_push_device(struct mp_filter_sim *s, void *dY, void *dUV, int w, int h, int pitchBytes, int swFormat, double pts, double nominalFps) {
+    struct mp_image *img = calloc(1, sizeof(*img));
+    g_inputFrames.ref.data = (unsigned char *)&g_inputFrames.ctx;
+    g_inputFrames.ctx.device_ref = &g_deviceRef;
+    g_inputFrames.ctx.sw_format = swFormat;
+    g_inputFrames.ctx.width = w;
+    g_inputFrames.ctx.height = h;
+    img->w = w;
+    img->h = h;
+    img->imgfmt = IMGFMT_CUDA;
+    img->params.hw_subfmt = swFormat;
+    img->hwctx = &g_inputFrames.ref;
+    img->planes[0] = dY;
+    img->planes[1] = dUV;
+    img->stride[0] = img->stride[1] = pitchBytes;
+    img->refcount = malloc(sizeof(int));
+    *img->refcount = 1;
+    img->pts = pts;
+    img->nominal_fps = nominalFps;
+    return sim_run(s, img);
+}
+/* oldest waiting output frame as it is: format, device (or host) plane pointers, pitch. The frame stays alive until the
+ * next call of this function or hr_sim_destroy. Returns 0, or 1 when none is waiting. */
+int hr_sim_pop_image(struct mp_filter_sim *s, int *imgfmt, int *subfmt, void **p0, void **p1, int *pitch, double *pts) {
+    static struct mp_image *held;
+    if (held) mp_image_unrefp(&held);
+    if (!s || s->n_out == 0) return 1;
+    struct mp_image *img = s->outputs[0];
+    memmove(s->outputs, s->outputs + 1, sizeof(s->outputs[0]) * (size_t)(--s->n_out));
+    if (imgfmt) *imgfmt = img->imgfmt;
+    if (subfmt) *subfmt = img->params.hw_subfmt;
+    if (p0) *p0 = img->planes[0];
+    if (p1) *p1 = img->planes[1];
+    if (pitch) *pitch = img->stride[0];
+    if (pts) *pts = img->pts;
+    held = img;
+    return 0;
+}
+void hr_sim_command_text(struct mp_filter_sim *s, const char *cmd, const char *arg) {
+    struct mp_filter_command c = {.type = MP_FILTER_COMMAND_TEXT, .cmd = cmd, .arg = arg, .speed = 1.0};
+    s->f->info->command(s->f, &c);
+}
+/* host frame of an explicit format (the patched filter negotiates NV12 or P010 by the image's format) */
+int hr_sim_push_fmt(struct mp_filter_sim *s, const unsigned char *y, const unsigned char *uv, int w, int h, int fmt, double pts, double nominalFps) {
+    struct mp_image *img = image_alloc(w, h, fmt);
+    const size_t rowBytes = (size_t)w * fmt_bps(fmt);
+    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * rowBytes, rowBytes);
+    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * rowBytes, rowBytes);
+    img->pts = pts;
+    img->nominal_fps = nominalFps;
+    return sim_run(s, img);
+}
+int hr_sim_push(struct mp_filter_sim *s, const unsigned char *y, const unsigned char *uv, int w, int h, double pts, double nominalFps) {
+    struct mp_image *img = image_alloc(w, h, HR_SIM_BPS == 2 ? IMGFMT_P010 : IMGFMT_NV12);
+    const size_t rowBytes = (size_t)w * HR_SIM_BPS;
+    for (int r = 0; r < h; ++r) memcpy(img->planes[0] + (size_t)r * img->stride[0], y + (size_t)r * rowBytes, rowBytes);
+    for (int r = 0; r < h / 2; ++r) memcpy(img->planes[1] + (size_t)r * img->stride[1], uv + (size_t)r * rowBytes, rowBytes);
+    img->pts = pts;
+    img->nominal_fps = nominalFps;
+    return sim_run(s, img);
+}
 /* oldest waiting output frame -> tightly packed planes; returns 0, or 1 when none is waiting */
 int hr_sim_pop(struct mp_filter_sim *s, unsigned char *y, unsigned char *uv, double *pts, int *stride) {
     if (s->n_out == 0) return 1;
     struct mp_image *img = s->outputs[0];
     memmove(s->outputs, s->outputs + 1, sizeof(s->outputs[0]) * (size_t)(--s->n_out));
-    const size_t rowBytes = (size_t)img->w * HR_SIM_BPS;
+    const size_t rowBytes = (size_t)img->w * fmt_bps(img->imgfmt);
     for (int r = 0; r < img->h; ++r) memcpy(y + (size_t)r * rowBytes, img->planes[0] + (size_t)r * img->stride[0], rowBytes);
     for (int r = 0; r < img->h / 2; ++r) memcpy(uv + (size_t)r * rowBytes, img->planes[1] + (size_t)r * img->stride[1], rowBytes);
     if (pts) *pts = img->pts;
@@ -216,7 +360,7 @@ int hr_sim_pop(struct mp_filter_sim *s, unsigned char *y, unsigned char *uv, dou
     return 0;
 }
 void hr_sim_command_speed(struct mp_filter_sim *s, double speed) {
-    struct mp_filter_command c = {MP_FILTER_COMMAND_TEXT, speed};
+    struct mp_filter_command c = {.type = MP_FILTER_COMMAND_TEXT, .speed = speed};
     s->f->info->command(s->f, &c);
 }
 void hr_sim_reset(struct mp_filter_sim *s) { s->f->info->reset(s->f); }

@@ -37,16 +37,44 @@ void talloc_free(void *p);
 
 /* ---- images ------------------------------------------------------------------------------------ */
 #define IMGFMT_NV12 1
+#define IMGFMT_P010 2
+#define IMGFMT_CUDA 3 /* planes[] are CUDA device pointers, params.hw_subfmt the layout (video/img_format.h:274) */
+struct AVBufferRef {
+    unsigned char *data;
+};
+typedef struct AVHWFramesContext { /* libavutil/hwcontext.h: the fields the patched filter reads */
+    struct AVBufferRef *device_ref;
+    int sw_format, width, height;
+} AVHWFramesContext;
+typedef struct AVFrame {
+    unsigned char *data[4];
+    int linesize[4];
+    int width, height;
+    struct AVBufferRef *hw_frames_ctx;
+} AVFrame;
+struct mp_image_params {
+    int hw_subfmt;
+};
 struct mp_image {
     int w, h;
     int imgfmt;
+    struct mp_image_params params;
+    struct AVBufferRef *hwctx; /* IMGFMT_CUDA: the frames context the image belongs to */
     unsigned char *planes[4];
     int stride[4];
     double pts;
     double nominal_fps;
     int *refcount;          /* shared between references                      */
-    unsigned char *storage; /* freed with the last reference                  */
+    unsigned char *storage; /* freed with the last reference (host images)    */
+    void *deviceStorage;    /* cudaFree()d with the last reference            */
 };
+AVFrame *av_frame_alloc(void);
+void av_frame_free(AVFrame **frame);
+int av_hwframe_get_buffer(struct AVBufferRef *hwframe_ctx, AVFrame *frame, int flags);
+void av_buffer_unref(struct AVBufferRef **buf);
+struct mp_image *mp_image_from_av_frame(AVFrame *src);
+bool mp_update_av_hw_frames_pool(struct AVBufferRef **hw_frames_ctx, struct AVBufferRef *hw_device_ctx, int imgfmt, int sw_imgfmt, int w, int h,
+                                 bool disable_multiplane); /* video/mp_image_pool.h:37 */
 struct mp_image *mp_image_new_ref(struct mp_image *img);
 void mp_image_unrefp(struct mp_image **img);
 void mp_image_copy_attributes(struct mp_image *dst, struct mp_image *src);
@@ -69,9 +97,12 @@ enum mp_pin_dir { MP_PIN_INVALID = 0, MP_PIN_IN, MP_PIN_OUT };
 struct mp_pin;
 struct mp_filter;
 enum mp_filter_command_type { MP_FILTER_COMMAND_NONE = 0, MP_FILTER_COMMAND_TEXT };
-struct mp_filter_command {
+struct mp_filter_command { /* filters/filter.h:377-392 */
     enum mp_filter_command_type type;
+    const char *target, *cmd, *arg;
+    void *res;
     double speed;
+    bool is_active;
 };
 struct mp_filter_info {
     const char *name;

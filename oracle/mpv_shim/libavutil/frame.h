@@ -1,0 +1,2 @@
+/* shim: see ../hr_mpv_shim.h */
+#include "../hr_mpv_shim.h"
