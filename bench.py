@@ -332,7 +332,7 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
     rows = None
     if banded:
         rows = env.sharding.band_rows(h, world, g.info.resScalar)
-        hr.connect_bands_distributed(g, dist, rows)
+        hr.connect_bands_distributed(g, dist, rows, max_radius=max(radius, 5))
         r0, r1 = rows[rank]
         nring = max(8, min(96, nring * world))      # a rank keeps only its band of every ring frame
     with torch.cuda.stream(stream):
@@ -495,7 +495,7 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
             if hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt, device=local):
                 raise SystemExit("initOpticalFlowCalc failed")
             ofc.opticalFlowSearchRadius = radius
-            hr.connect_bands_distributed(ofc.impl, dist, rows)
+            hr.connect_bands_distributed(ofc.impl, dist, rows, max_radius=max(radius, 5))
 
             def step_host(i):                               # a rank moves only its band over PCIe
                 ofc.impl.band_upload(*hring[i % nbase])

@@ -160,29 +160,45 @@ int hr_get_output_device(HrContext *ctx, void **dYPlane, void **dUvPlane);
 int hr_set_output_device(HrContext *ctx, void *dYPlane, void *dUvPlane);
 
 /* ---- spatial bands (no reference counterpart: the reference drives one device,
- * HR/opticalFlowCalc.c:279-305). N contexts, one per GPU, created for the FULL frame geometry; context
- * `rank` owns the rows [row0[rank], row1[rank]) of every frame: it uploads, warps and downloads only those
- * rows, and pulls the other bands from its peers' frame slots over NVLink P2P, so that every GPU holds
- * the whole frame pair for the flow search (replicated, bit-identical on every GPU). Bands must tile
- * the frame in order; all but the last end on a multiple of 2^(resScalar+1) rows.
- * Call order per source frame, on every rank: hr_band_upload ... then hr_band_gather (a driver of
- * several ranks in one process calls upload on all of them before the first gather); then
- * hr_calc_flow / hr_warp (warps the band only) / hr_band_download as usual. */
+ * HR/opticalFlowCalc.c:279-305). N contexts, one per GPU, created for the FULL frame geometry; context `rank` owns the
+ * rows [row0[rank], row1[rank]) of every frame — a whole number of lattice tile rows (32 << resScalar frame rows; the
+ * last band ends with the frame). Per source frame every GPU
+ *   - uploads only its band (hr_band_upload),
+ *   - fetches only its HALO from the neighbouring bands' frame slots over NVLink P2P (hr_band_gather): the rows its
+ *     search and its warp can reach beyond the band, i.e. the largest accumulated offset of the configured maximum search
+ *     radius (+-32 rows at radius 5, -512/+392 at 16, HR/Kernels/calcDeltaSumsKernel.cl:68-72), and packs what it holds,
+ *   - searches ONLY ITS OWN lattice tiles (hr_calc_flow): what tiles of different GPUs owe one another — the tile totals
+ *     of windows that span tiles, the window-table entries at a band's edge, the blurred flow — is stored straight into
+ *     the peers' memory by the search kernel itself (epoch-tagged 64-bit words in an "exchange arena" with the same layout
+ *     on every GPU; consumers poll their own memory only), so the flow is bit-identical to the single-GPU one and whole on
+ *     every GPU when the launch ends,
+ *   - warps and downloads only its band (hr_warp, hr_band_download).
+ * No NCCL, no host synchronisation on the data path: hand-offs between GPUs are device-side (mailbox counters written and
+ * polled by one-thread kernels in stream order; tagged words inside the search). Every rank issues the same sequence of
+ * calls; a driver of several ranks in one process calls hr_band_upload on all of them before the first hr_band_gather, and
+ * hr_calc_flow on all of them before it waits for any. The searches of a group wait for one another ON THE DEVICE: the
+ * contexts of a group must sit on different GPUs (several waiting kernels on one GPU are not guaranteed to run at the
+ * same time); a group of one band is allowed anywhere. The pipelined mode is off while bands are configured. */
 #define HR_MAX_BANDS 16
 #define HR_IPC_HANDLE_BYTES 64
 int hr_band_configure(HrContext *ctx, int rank, int world, const int *row0, const int *row1);
-/* what a peer must map: frame slot 0, frame slot 1, mailbox — as pointers (same process) ... */
-int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **mailbox);
+/* largest search radius the group will use (sizes the halo; default 16 = MAX_SEARCH_RADIUS, HR/config.h:7); the same
+ * on every rank, before the first frame */
+int hr_band_set_max_radius(HrContext *ctx, int searchRadius);
+/* what a peer must map: frame slot 0, frame slot 1, exchange arena — as pointers (same process) ... */
+int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **arena);
 /* ... or as three CUDA IPC handles (another process) */
 int hr_band_export_ipc(HrContext *ctx, unsigned char *handles /* 3 * HR_IPC_HANDLE_BYTES */);
-int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **mailbox);
+int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **arena);
 /* peerDevice >= 0: same-process peer on that device (peer access is enabled); < 0: pointers from IPC */
-int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *mailbox);
+int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *arena);
 /* updateFrame, banded, in two phases (see above). yBand / uvBand: first luma / chroma row of the band. */
 int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvBand, int sourceIsDevice);
 int hr_band_gather(HrContext *ctx, int blocking);
 /* downloadFrame of the band's rows only */
 int hr_band_download(HrContext *ctx, void *yBand, void *uvBand, double *seconds);
+/* rows [*lo, *hi) of every frame this rank holds (band + halo), bytes fetched from peers over NVLink so far */
+int hr_band_get_halo(const HrContext *ctx, int *lo, int *hi, unsigned long long *p2pBytes);
 
 /* ---- parity taps (tests only; nothing on the playback path calls them). Blocking.
  * raw / blurred: int16 [2][lowHeight][lowWidth], X plane then Y plane = offsetArray /

@@ -66,6 +66,8 @@ ABI = {
     "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_band_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hr_band_set_max_radius": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_band_get_halo": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)]),
     "hr_band_local_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_band_export_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hr_band_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -325,6 +327,15 @@ class HrCuda:
         self._chk(self.lib.hr_band_configure(self.h, rank, world, r0, r1))
         self.band = (rank, world, list(rows))
 
+    def band_set_max_radius(self, radius):
+        self._chk(self.lib.hr_band_set_max_radius(self.h, int(radius)))
+
+    def band_halo(self):
+        """(first row, end row) of every frame this rank holds, bytes fetched from peers over NVLink so far."""
+        lo, hi, n = C.c_int(), C.c_int(), C.c_ulonglong()
+        self._chk(self.lib.hr_band_get_halo(self.h, C.byref(lo), C.byref(hi), C.byref(n)))
+        return lo.value, hi.value, n.value
+
     def band_local_pointers(self):
         a, b, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._chk(self.lib.hr_band_local_pointers(self.h, C.byref(a), C.byref(b), C.byref(m)))
@@ -357,20 +368,25 @@ class HrCuda:
 
 
 class BandGroup:
-    """One frame stream split into spatial bands over several contexts IN ONE PROCESS (one per entry of
-    `devices`; the same device may appear more than once, e.g. to exercise the protocol on one GPU).
-    Presents the six calls of the optical-flow-calc interface for whole frames: updateFrame uploads every
-    band to its own GPU and gathers the rest by P2P, the flow runs replicated, warp + download work band
-    by band and write straight into the caller's full-size planes. SURVEY.md §8e."""
+    """One frame stream split into spatial bands over several contexts IN ONE PROCESS, one per entry of `devices`
+    (different GPUs: the searches of the group wait for one another on the device, include/hopperrender_cuda.h).
+    Presents the six calls of the optical-flow-calc interface for whole frames: updateFrame uploads every band to its
+    own GPU and fetches the halos by P2P, every GPU searches its own lattice tiles (the flow ends up whole and
+    bit-identical on all of them), warp + download work band by band and write straight into the caller's full-size
+    planes. SURVEY.md §8e."""
 
-    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=PIXFMT_NV12, devices=(0, 1)):
+    def __init__(self, frameHeight, frameWidth, actualWidth=None, pixfmt=PIXFMT_NV12, devices=(0, 1), max_radius=None):
         from . import sharding
+        if len(set(devices)) != len(devices):
+            raise ValueError("a band group needs one GPU per band (the searches wait for one another on the device)")
         self.H, self.W = frameHeight, frameWidth
         self.world = len(devices)
         self.ctx = [HrCuda(frameHeight, frameWidth, actualWidth, pixfmt, d) for d in devices]
         self.rows = sharding.band_rows(frameHeight, self.world, self.ctx[0].info.resScalar)
         for r, c in enumerate(self.ctx):
             c.band_configure(r, self.world, self.rows)
+            if max_radius is not None:
+                c.band_set_max_radius(max_radius)
         ptrs = [c.band_local_pointers() for c in self.ctx]
         for r, c in enumerate(self.ctx):
             for p in range(self.world):
@@ -416,12 +432,14 @@ class BandGroup:
         return y, uv
 
 
-def connect_bands_distributed(ctx, dist, rows):
+def connect_bands_distributed(ctx, dist, rows, max_radius=None):
     """One process per GPU (torchrun): configure `ctx` as band `rank` and map every peer's frame slots and
-    mailbox through CUDA IPC handles exchanged once, at set-up, over the process group (control plane
-    only; the frames themselves move by P2P copies)."""
+    exchange arena through CUDA IPC handles exchanged once, at set-up, over the process group (control plane
+    only; halos move by P2P copies, the searches store into one another's arenas)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     ctx.band_configure(rank, world, rows)
+    if max_radius is not None:
+        ctx.band_set_max_radius(max_radius)
     handles = [None] * world
     dist.all_gather_object(handles, ctx.band_export_ipc())
     for p in range(world):

@@ -32,6 +32,22 @@
 #define HR_FIRST_NEIGHBOR_ITERATION 4 /* calcDeltaSumsKernel.cl:1 */
 #define HR_TIMELINE_SLOTS 128
 
+/* Spatial bands: the lattice tiles are split by tile rows over `world` GPUs, every GPU searches its own
+ * tiles only. What tiles hand to one another across GPUs — tile totals of the windows that span tiles, window-table
+ * entries at a band's edge, the flow itself — is stored straight into the peers' copies over NVLink: all of it lives in
+ * one "exchange arena" per GPU with the same layout everywhere, so the address of a word in peer g's arena is the local
+ * address plus peerDelta[g] (0 for the GPU itself). Consumers only ever poll their own memory. */
+#define HR_MAX_BANDS 16
+struct BandLink {
+    int world, rank;                       /* world <= 1: no bands                                                  */
+    int tile0;                             /* first lattice tile of this GPU (tiles tile0 .. tile0 + gridDim.x - 1)  */
+    int tileRow0, tileRow1;                /* its tile rows                                                          */
+    int up, down;                          /* GPUs that own the tile row above / below the band (-1: none)           */
+    long long peerDelta[HR_MAX_BANDS];     /* byte distance from a local arena address to the same word at GPU g     */
+    unsigned long long *ready, *done;      /* local [HR_MAX_BANDS]: epoch GPU g has entered / finished writing        */
+    unsigned int *exitCount;               /* local: CTAs of this launch that have stored all their results           */
+};
+
 struct FlowParams {
     const uint32_t *p1;      /* packed previous frame (frame1): all phase planes                 */
     const void *f2y, *f2uv;  /* newest frame (frame2) as it arrived, NV12 / P010: read at the lattice points only, so
@@ -53,6 +69,7 @@ struct FlowParams {
     uint32_t *blurXY;        /* the same, one word per lattice point: x | y << 16 (read by the warp)  */
     uint8_t *trace;          /* optional [steps][lh][lw] winning layer per point, or NULL         */
     long long *timeline;     /* optional [ctas][HR_TIMELINE_SLOTS] clock64 stamps of thread 0, or NULL */
+    BandLink band;
 };
 
 template <typename T>
@@ -106,6 +123,22 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsig
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+/* the same word at another GPU (peer-mapped memory, NVLink) */
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T *at_peer(T *local, long long delta) {
+    return reinterpret_cast<T *>(reinterpret_cast<char *>(local) + delta);
+}
 
 /* ---- tile-to-tile hand-off without barriers ------------------------------------------------------
  * Every word that one CTA produces for another (window-table entries, per-tile window sums) is a
@@ -117,6 +150,11 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
  * level, so polling cannot deadlock. */
 __device__ __forceinline__ void put_tagged(unsigned long long *p, uint32_t epoch, uint32_t payload) {
     st_relaxed_u64(p, ((unsigned long long)epoch << 32) | payload);
+}
+/* ... and into the arena of every GPU of a band group (the own one included: delta 0) */
+__device__ __forceinline__ void put_tagged_all(const BandLink &B, unsigned long long *p, uint32_t epoch, uint32_t payload) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | payload;
+    for (int g = 0; g < B.world; ++g) st_relaxed_sys_u64(at_peer(p, B.peerDelta[g]), v);
 }
 __device__ __forceinline__ uint32_t get_tagged(const unsigned long long *p, uint32_t epoch) {
     unsigned long long v = ld_relaxed_u64(p);

@@ -63,9 +63,21 @@ struct HrContext {
     int bandRow0[HR_MAX_BANDS], bandRow1[HR_MAX_BANDS];
     unsigned char *peerSlot[HR_MAX_BANDS][2];       /* the peers' two frame slots, mapped into this process   */
     unsigned long long *peerMail[HR_MAX_BANDS];     /* the peers' mailboxes: [0] uploaded, [1] consumed        */
-    unsigned long long *mail;                       /* own mailbox (device memory)                             */
+    unsigned char *peerArena[HR_MAX_BANDS];         /* the peers' exchange arenas                              */
+    unsigned long long *mail;                       /* own mailbox (inside the arena)                          */
     unsigned long long bandFrames;                  /* frames uploaded so far                                  */
     int bandPending;                                /* hr_band_upload done, hr_band_gather outstanding        */
+    int banded;                                     /* bands configured (also with a single band)              */
+    int bandMaxRadius;                              /* largest search radius the halo is sized for             */
+    int haloLo, haloHi;                             /* rows of every frame this GPU holds: band + halo         */
+    unsigned long long bandP2pBytes;                /* bytes fetched from peers' frame slots so far             */
+    /* exchange arena: everything the searches of the band group store into one another, one allocation with the same
+     * layout on every GPU (hr_common.cuh BandLink) */
+    unsigned char *arena;
+    size_t arenaBytes, aT, aPartial, aOff, aBlur, aBlurXY, aReady, aDone, aExit, aMail;
+    unsigned long long *plainT, *plainPartial;      /* what the context used before the bands were configured  */
+    int16_t *plainOff, *plainBlur;
+    uint32_t *plainBlurXY;
 
     /* pipelined mode (hr_set_pipeline): independent work of consecutive frame pairs overlaps on internal streams —
      * pack(k) || search(k) (the search reads frame 2 as it arrived), the warps of one pair on HR_WARP_STREAMS
@@ -231,6 +243,13 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaDeviceSynchronize();
     /* ctx->blur / blurXY / off / T / partial alias entry [x] of their rings; entry [0] is freed below through them */
     pipeline_release(ctx);
+    if (ctx->banded) { /* the flow arrays live in the arena while bands are configured: back to the context's own */
+        ctx->T = ctx->plainT;
+        ctx->partial = ctx->plainPartial;
+        ctx->off = ctx->plainOff;
+        ctx->blur = ctx->plainBlur;
+        ctx->blurXY = ctx->plainBlurXY;
+    }
     /* (a context whose creation failed half-way has no ring yet: keep what was allocated directly) */
     if (ctx->blurB[0]) ctx->blur = ctx->blurB[0];
     if (ctx->blurXYB[0]) ctx->blurXY = ctx->blurXYB[0];
@@ -252,7 +271,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
         cudaFree(ctx->colours[b]);
         if (ctx->evColour[b]) cudaEventDestroy(ctx->evColour[b]);
     }
-    cudaFree(ctx->mail);
+    cudaFree(ctx->arena);
     cudaFree(ctx->timeline);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
     if (ctx->evFlowEnd) cudaEventDestroy(ctx->evFlowEnd);
@@ -580,18 +599,20 @@ template <typename T>
 static void launch_pack_t(HrContext *ctx, cudaStream_t st) {
     const T *y = (const T *)ctx->fy[1], *uv = (const T *)ctx->fuv[1];
     const bool vec = ctx->s <= 4 && ctx->W % 16 == 0 && (((uintptr_t)y | (uintptr_t)uv) % 16 == 0);
+    /* bands: only the rows this GPU holds (band + halo, even bounds) */
+    const int rowLo = ctx->banded ? ctx->haloLo : 0, rowHi = ctx->banded ? ctx->haloHi : ctx->H;
     if (vec) {
-        dim3 block(128), grid((ctx->W / 16 + 127) / 128, (ctx->H + 1) / 2);
+        dim3 block(128), grid((ctx->W / 16 + 127) / 128, (rowHi - rowLo + 1) / 2);
         switch (ctx->s) {
-#define HR_PCASE(S_) case S_: pack_frame16_kernel<T, S_><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->planePitch, ctx->planeSize); break;
+#define HR_PCASE(S_) case S_: pack_frame16_kernel<T, S_><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, rowHi, ctx->planePitch, ctx->planeSize, rowLo >> 1); break;
             HR_PCASE(0) HR_PCASE(1) HR_PCASE(2) HR_PCASE(3) HR_PCASE(4)
 #undef HR_PCASE
         }
     } else {
         const int bx = ctx->s <= 3 ? 128 : 64; /* s <= 4 (hr_create): at most 64 x 16 threads */
         dim3 block(bx, 1 << ctx->s);
-        dim3 grid((ctx->lw + bx - 1) / bx, ctx->H);
-        pack_frame_kernel<T><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize);
+        dim3 grid((ctx->lw + bx - 1) / bx, rowHi - rowLo);
+        pack_frame_kernel<T><<<grid, block, 0, st>>>(y, uv, ctx->packed[1], ctx->W, ctx->H, ctx->s, ctx->lw, ctx->planePitch, ctx->planeSize, rowLo);
     }
 }
 static int launch_pack(HrContext *ctx) {
@@ -638,7 +659,7 @@ static void rotate_slots(HrContext *ctx, int *freeSlot) {
 }
 
 /* ---- pipelined mode ----------------------------------------------------------------------------------- */
-static int pipe_on(const HrContext *ctx) { return ctx->pipeline && ctx->bandWorld <= 1; }
+static int pipe_on(const HrContext *ctx) { return ctx->pipeline && !ctx->banded; }
 
 /* make `st` wait for every warp that reads flow buffer b */
 static int wait_warps(HrContext *ctx, cudaStream_t st, int b) {
@@ -858,6 +879,36 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     P.blurXY = ctx->blurXYB[fb];
     P.trace = ctx->traceOn ? ctx->trace : NULL;
     P.timeline = ctx->timelineOn ? ctx->timeline : NULL;
+    int grid = ctx->grid;
+    if (ctx->banded) {
+        /* this GPU's tile rows only; tables, totals and the flow live in the exchange arena (same layout everywhere) */
+        const int tileRows = HR_TILE << ctx->s;
+        const int r0 = ctx->bandRow0[ctx->bandRank], r1 = ctx->bandRow1[ctx->bandRank];
+        BandLink &B = P.band;
+        B.world = ctx->bandWorld;
+        B.rank = ctx->bandRank;
+        B.tileRow0 = r0 / tileRows;
+        B.tileRow1 = (r1 + tileRows - 1) / tileRows;
+        B.tile0 = B.tileRow0 * ctx->tilesX;
+        B.up = ctx->bandRank > 0 ? ctx->bandRank - 1 : -1;
+        B.down = ctx->bandRank + 1 < ctx->bandWorld ? ctx->bandRank + 1 : -1;
+        for (int g = 0; g < ctx->bandWorld; ++g) {
+            if (!ctx->peerArena[g]) return fail(ctx, "hr_calc_flow: band peer %d is not connected", g);
+            B.peerDelta[g] = (long long)((intptr_t)ctx->peerArena[g] - (intptr_t)ctx->arena);
+        }
+        B.ready = (unsigned long long *)(ctx->arena + ctx->aReady);
+        B.done = (unsigned long long *)(ctx->arena + ctx->aDone);
+        B.exitCount = (unsigned int *)(ctx->arena + ctx->aExit);
+        P.T = (unsigned long long *)(ctx->arena + ctx->aT);
+        P.partial = (unsigned long long *)(ctx->arena + ctx->aPartial);
+        P.off = (int16_t *)(ctx->arena + ctx->aOff);
+        P.blur = (int16_t *)(ctx->arena + ctx->aBlur);
+        P.blurXY = (uint32_t *)(ctx->arena + ctx->aBlurXY);
+        P.trace = NULL;
+        P.timeline = NULL;
+        grid = (B.tileRow1 - B.tileRow0) * ctx->tilesX;
+        if (grid < 1 || grid > ctx->smCount) return fail(ctx, "hr_calc_flow: a band of %d tiles does not fit the GPU", grid);
+    }
     void *args[] = {&P};
     if (pl) {
         /* after: the newest frame (evIn, recorded by the update), the packed copy of the previous frame, the warps
@@ -873,8 +924,8 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         if (pipe_join(ctx)) return 1;
     }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], st));
-    const void *kfn = search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn);
-    CU(cudaLaunchCooperativeKernel(kfn, dim3(ctx->grid), dim3(HR_THREADS), args, 0, st));
+    const void *kfn = ctx->banded ? (searchRadius == 5 ? (const void *)flow_search_band_kernel<5> : (const void *)flow_search_band_kernel<0>) : search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn);
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HR_THREADS), args, 0, st));
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], st));
         ctx->haveSearchT = 1;
@@ -882,12 +933,14 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     ctx->launches++;
     ctx->flowCur = fb;
     ctx->flowSerial[fb] = ++ctx->flowStamp;
-    ctx->blur = ctx->blurB[fb];
-    ctx->blurXY = ctx->blurXYB[fb];
-    ctx->lane = lane;
-    ctx->off = ctx->offL[lane];
-    ctx->T = ctx->TL[lane];
-    ctx->partial = ctx->partialL[lane];
+    if (!ctx->banded) {
+        ctx->blur = ctx->blurB[fb];
+        ctx->blurXY = ctx->blurXYB[fb];
+        ctx->lane = lane;
+        ctx->off = ctx->offL[lane];
+        ctx->T = ctx->TL[lane];
+        ctx->partial = ctx->partialL[lane];
+    }
     if (ctx->sPack) {
         CU(cudaEventRecord(ctx->evSearch[fb], st));
         ctx->haveSearch[fb] = 1;
@@ -903,6 +956,8 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
         return fail(ctx, "hr_calc_flow: search radius %d outside [%d, %d]", searchRadius, HR_MIN_SEARCH_RADIUS, HR_MAX_SEARCH_RADIUS);
     if (deltaScalar < 0 || deltaScalar > 31 || neighborBiasScalar < 0 || neighborBiasScalar > 31)
         return fail(ctx, "hr_calc_flow: scalar out of range");
+    if (ctx->banded && searchRadius > ctx->bandMaxRadius)
+        return fail(ctx, "hr_calc_flow: search radius %d needs a larger halo than the bands were configured for (hr_band_set_max_radius: %d)", searchRadius, ctx->bandMaxRadius);
     if (bind_device(ctx)) return 1;
     const int pl = pipe_on(ctx);
     ctx->specWarp.valid = 0; /* a new flow: whatever was warped ahead is void */
@@ -1011,7 +1066,7 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
     P.black = black;
     P.white = white;
     int r0 = 0, r1 = ctx->H;
-    if (ctx->bandWorld > 1) {
+    if (ctx->banded) {
         r0 = ctx->bandRow0[ctx->bandRank];
         r1 = ctx->bandRow1[ctx->bandRank];
     }
@@ -1346,11 +1401,27 @@ __global__ void band_wait_kernel(const unsigned long long *p, unsigned long long
     } while (v < target);
 }
 
+/* rows [lo, hi) of every frame that rank r needs besides its own band: what its search (frame-1 samples of its tiles
+ * at the largest accumulated offset) and its warp (displaced source rows) can reach, even bounds, inside the frame */
+static void band_reach(const HrContext *ctx, int r, int *lo, int *hi) {
+    const int R = ctx->bandMaxRadius;
+    const int neg = (R / 2) * (R / 2) * ctx->iters, pos = (R - 1 - R / 2) * (R - 1 - R / 2) * ctx->iters; /* calcDeltaSumsKernel.cl:68-72, one shift per level */
+    const int reach = (neg > pos ? neg : pos) + 2;
+    int a = ctx->bandRow0[r] - reach, b = ctx->bandRow1[r] + reach;
+    a = a < 0 ? 0 : a & ~1;
+    b = b > ctx->H ? ctx->H : (b + 1) & ~1;
+    if (b > ctx->H) b = ctx->H;
+    *lo = a;
+    *hi = b;
+}
+static size_t arena_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
 extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int *row0, const int *row1) {
     if (!ctx || !row0 || !row1) return 1;
     if (world < 1 || world > HR_MAX_BANDS || rank < 0 || rank >= world) return fail(ctx, "hr_band_configure: rank %d / world %d out of range (max %d bands)", rank, world, HR_MAX_BANDS);
     if (bind_device(ctx)) return 1;
-    const int unit = 1 << (ctx->s + 1);
+    /* a band is a whole number of lattice tile rows (32 lattice rows = 32 << s frame rows): the search is split by tiles */
+    const int unit = HR_TILE << ctx->s;
     int expect = 0;
     for (int r = 0; r < world; ++r) {
         if (row0[r] != expect || row1[r] <= row0[r] || (r + 1 < world && row1[r] % unit != 0))
@@ -1360,40 +1431,93 @@ extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int 
         ctx->bandRow1[r] = row1[r];
     }
     if (expect != ctx->H) return fail(ctx, "hr_band_configure: the bands cover %d rows, the frame has %d", expect, ctx->H);
-    /* a (re)configuration restarts the frame count: every rank of the group reconfigures together, the mailbox
-     * counters start from zero again once nothing of the old stream is in flight */
+    if ((row1[rank] - row0[rank] + unit - 1) / unit * ctx->tilesX > ctx->smCount)
+        return fail(ctx, "hr_band_configure: band %d has more lattice tiles than the GPU has SMs", rank);
+    /* a (re)configuration restarts the frame count: every rank of the group reconfigures together, counters and tags
+     * start from zero again once nothing of the old stream is in flight */
     if (sync_all(ctx)) return 1;
-    if (!ctx->mail) CU(cudaMalloc(&ctx->mail, 256));
-    CU(cudaMemset(ctx->mail, 0, 256));
+    if (ctx->pipeline) {
+        ctx->pipeline = 0;
+        ctx->specWarp.valid = ctx->specFlow.valid = 0;
+    }
+    if (!ctx->arena) {
+        const size_t ln = (size_t)ctx->lw * ctx->lh;
+        size_t o = 0;
+        ctx->aT = o;        o = arena_align(o + (size_t)(ctx->tWords ? ctx->tWords : 32) * 8);
+        ctx->aPartial = o;  o = arena_align(o + (size_t)(ctx->bigWords ? ctx->bigWords : 32) * 8);
+        ctx->aOff = o;      o = arena_align(o + 2 * ln * sizeof(int16_t));
+        ctx->aBlur = o;     o = arena_align(o + 2 * ln * sizeof(int16_t));
+        ctx->aBlurXY = o;   o = arena_align(o + ln * sizeof(uint32_t));
+        ctx->aReady = o;    o = arena_align(o + HR_MAX_BANDS * 8);
+        ctx->aDone = o;     o = arena_align(o + HR_MAX_BANDS * 8);
+        ctx->aExit = o;     o = arena_align(o + 8);
+        ctx->aMail = o;     o = arena_align(o + 256);
+        ctx->arenaBytes = o;
+        CU(cudaMalloc(&ctx->arena, o));
+        ctx->deviceBytes += o;
+        ctx->plainT = ctx->T;
+        ctx->plainPartial = ctx->partial;
+        ctx->plainOff = ctx->off;
+        ctx->plainBlur = ctx->blur;
+        ctx->plainBlurXY = ctx->blurXY;
+    }
+    CU(cudaMemset(ctx->arena, 0, ctx->arenaBytes));
     CU(cudaDeviceSynchronize());
+    ctx->epoch = 0; /* the group counts its searches together */
+    ctx->T = (unsigned long long *)(ctx->arena + ctx->aT);
+    ctx->partial = (unsigned long long *)(ctx->arena + ctx->aPartial);
+    ctx->off = (int16_t *)(ctx->arena + ctx->aOff);
+    ctx->blur = (int16_t *)(ctx->arena + ctx->aBlur);
+    ctx->blurXY = (uint32_t *)(ctx->arena + ctx->aBlurXY);
+    ctx->mail = (unsigned long long *)(ctx->arena + ctx->aMail);
+    ctx->flowCur = 0;
+    ctx->flowSerial[0] = ++ctx->flowStamp;
+    ctx->banded = 1;
     ctx->bandWorld = world;
     ctx->bandRank = rank;
     ctx->bandFrames = 0;
     ctx->bandPending = 0;
+    if (ctx->bandMaxRadius < HR_MIN_SEARCH_RADIUS) ctx->bandMaxRadius = 16; /* MAX_SEARCH_RADIUS, config.h:7 */
+    band_reach(ctx, rank, &ctx->haloLo, &ctx->haloHi);
     for (int r = 0; r < HR_MAX_BANDS; ++r) {
         ctx->peerSlot[r][0] = ctx->peerSlot[r][1] = NULL;
         ctx->peerMail[r] = NULL;
+        ctx->peerArena[r] = NULL;
     }
     ctx->peerSlot[rank][0] = ctx->frameBuf[0];
     ctx->peerSlot[rank][1] = ctx->frameBuf[1];
+    ctx->peerArena[rank] = ctx->arena;
     ctx->peerMail[rank] = ctx->mail;
     return 0;
 }
 
-/* The three device allocations a peer needs to see: frame slot 0, frame slot 1, mailbox. */
-extern "C" int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **mailbox) {
-    if (!ctx || !ctx->mail) return 1;
+/* Largest search radius the group will use: it sizes the halo (rows of the neighbouring bands every GPU holds).
+ * Default 16 = MAX_SEARCH_RADIUS (config.h:7): -512 / +392 rows; radius 5: +-32 rows. Same value on every rank,
+ * before the first frame. */
+extern "C" int hr_band_set_max_radius(HrContext *ctx, int searchRadius) {
+    if (!ctx) return 1;
+    if (!ctx->banded) return fail(ctx, "hr_band_set_max_radius: configure the bands first");
+    if (searchRadius < HR_MIN_SEARCH_RADIUS || searchRadius > HR_MAX_SEARCH_RADIUS) return fail(ctx, "hr_band_set_max_radius: radius %d out of range", searchRadius);
+    if (ctx->bandFrames) return fail(ctx, "hr_band_set_max_radius: the stream has started");
+    ctx->bandMaxRadius = searchRadius;
+    band_reach(ctx, ctx->bandRank, &ctx->haloLo, &ctx->haloHi);
+    return 0;
+}
+
+/* The three device allocations a peer needs to see: frame slot 0, frame slot 1, exchange arena. */
+extern "C" int hr_band_local_pointers(HrContext *ctx, void **slot0, void **slot1, void **arena) {
+    if (!ctx || !ctx->arena) return 1;
     if (slot0) *slot0 = ctx->frameBuf[0];
     if (slot1) *slot1 = ctx->frameBuf[1];
-    if (mailbox) *mailbox = ctx->mail;
+    if (arena) *arena = ctx->arena;
     return 0;
 }
 extern "C" int hr_band_export_ipc(HrContext *ctx, unsigned char *handles /* 3 x HR_IPC_HANDLE_BYTES */) {
     if (!ctx || !handles) return 1;
-    if (!ctx->mail) return fail(ctx, "hr_band_export_ipc: configure the bands first");
+    if (!ctx->arena) return fail(ctx, "hr_band_export_ipc: configure the bands first");
     if (bind_device(ctx)) return 1;
     static_assert(sizeof(cudaIpcMemHandle_t) == HR_IPC_HANDLE_BYTES, "IPC handle size");
-    void *ptrs[3] = {ctx->frameBuf[0], ctx->frameBuf[1], ctx->mail};
+    void *ptrs[3] = {ctx->frameBuf[0], ctx->frameBuf[1], ctx->arena};
     for (int i = 0; i < 3; ++i) {
         cudaIpcMemHandle_t h;
         CU(cudaIpcGetMemHandle(&h, ptrs[i]));
@@ -1401,10 +1525,10 @@ extern "C" int hr_band_export_ipc(HrContext *ctx, unsigned char *handles /* 3 x 
     }
     return 0;
 }
-extern "C" int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **mailbox) {
-    if (!ctx || !handles || !slot0 || !slot1 || !mailbox) return 1;
+extern "C" int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, void **slot0, void **slot1, void **arena) {
+    if (!ctx || !handles || !slot0 || !slot1 || !arena) return 1;
     if (bind_device(ctx)) return 1;
-    void **outs[3] = {slot0, slot1, mailbox};
+    void **outs[3] = {slot0, slot1, arena};
     for (int i = 0; i < 3; ++i) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + i * HR_IPC_HANDLE_BYTES, HR_IPC_HANDLE_BYTES);
@@ -1414,10 +1538,10 @@ extern "C" int hr_band_open_ipc(HrContext *ctx, const unsigned char *handles, vo
 }
 /* pointers must be valid in this process and on this device (same process: enable peer access first —
  * done here when peerDevice >= 0; another process: hr_band_open_ipc) */
-extern "C" int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *mailbox) {
+extern "C" int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, void *slot0, void *slot1, void *arena) {
     if (!ctx) return 1;
     if (peerRank < 0 || peerRank >= ctx->bandWorld || peerRank == ctx->bandRank) return fail(ctx, "hr_band_connect: bad peer rank %d", peerRank);
-    if (!slot0 || !slot1 || !mailbox) return fail(ctx, "hr_band_connect: NULL pointer");
+    if (!slot0 || !slot1 || !arena) return fail(ctx, "hr_band_connect: NULL pointer");
     if (bind_device(ctx)) return 1;
     if (peerDevice >= 0 && peerDevice != ctx->device) {
         int can = 0;
@@ -1429,8 +1553,17 @@ extern "C" int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, voi
     }
     ctx->peerSlot[peerRank][0] = (unsigned char *)slot0;
     ctx->peerSlot[peerRank][1] = (unsigned char *)slot1;
-    ctx->peerMail[peerRank] = (unsigned long long *)mailbox;
+    ctx->peerArena[peerRank] = (unsigned char *)arena;
+    ctx->peerMail[peerRank] = (unsigned long long *)((unsigned char *)arena + ctx->aMail);
     return 0;
+}
+
+/* does rank a hold rows of rank b's band in its halo (= does a read b's frame slots)? */
+static int band_reads(const HrContext *ctx, int a, int b) {
+    if (a == b) return 0;
+    int lo, hi;
+    band_reach(ctx, a, &lo, &hi);
+    return lo < ctx->bandRow1[b] && hi > ctx->bandRow0[b];
 }
 
 /* Phase 1 of a banded updateFrame: upload (or copy from device memory) the rows of this context's band
@@ -1438,7 +1571,7 @@ extern "C" int hr_band_connect(HrContext *ctx, int peerRank, int peerDevice, voi
  * row. Enqueue-only for device sources; host sources are copied asynchronously (pinned memory advised). */
 extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvBand, int sourceIsDevice) {
     if (!ctx) return 1;
-    if (ctx->bandWorld < 1 || !ctx->mail) return fail(ctx, "hr_band_upload: bands are not configured");
+    if (!ctx->banded) return fail(ctx, "hr_band_upload: bands are not configured");
     if (ctx->bandPending) return fail(ctx, "hr_band_upload: the previous frame was not gathered (hr_band_gather)");
     if (!yBand || !uvBand) return fail(ctx, "hr_band_upload: NULL plane");
     for (int r = 0; r < ctx->bandWorld; ++r)
@@ -1450,8 +1583,8 @@ extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvB
     const unsigned long long n = ctx->bandFrames; /* this is frame n; frame n-2 lived in the same slot */
     if (n >= 2) {
         for (int r = 0; r < ctx->bandWorld; ++r) {
-            if (r == ctx->bandRank) continue;
-            band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 1, n - 1); /* peer r has gathered frame n-2 */
+            if (!band_reads(ctx, r, ctx->bandRank)) continue;
+            band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 1, n - 1); /* peer r has fetched its halo of frame n-2 */
             ctx->launches++;
         }
     }
@@ -1462,8 +1595,10 @@ extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvB
     CU(cudaMemcpyAsync(dst + (size_t)r0 * rowBytes, yBand, (size_t)(r1 - r0) * rowBytes, kind, ctx->stream));
     CU(cudaMemcpyAsync(dst + ylen + (size_t)(r0 >> 1) * rowBytes, uvBand, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes, kind, ctx->stream));
     if (!sourceIsDevice) g_h2dBytes += (size_t)(r1 - r0) * rowBytes + (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes;
-    band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 0, n + 1);
-    ctx->launches++;
+    if (ctx->bandWorld > 1) {
+        band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 0, n + 1);
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     ctx->fy[1] = dst;
     ctx->fuv[1] = dst + ylen;
@@ -1472,9 +1607,9 @@ extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvB
     return 0;
 }
 
-/* Phase 2: pull the other bands of the new frame from the peers (P2P copies, each after the peer's upload
- * has been signalled), tell the peers, pack the frame for the search. blocking != 0: waits for the stream
- * like updateFrame does. */
+/* Phase 2: fetch the halo — the rows of the neighbouring bands within reach of this band's search and warp — from the
+ * owners' frame slots over NVLink (P2P copies, each after the owner's upload has been signalled), tell the peers, pack
+ * the rows held here for the search. blocking != 0: waits for the stream like updateFrame does. */
 extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
     if (!ctx) return 1;
     if (!ctx->bandPending) return fail(ctx, "hr_band_gather: no upload outstanding");
@@ -1484,17 +1619,22 @@ extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
     unsigned char *dst = ctx->frameBuf[slot];
     const size_t rowBytes = (size_t)ctx->W * ctx->bps, ylen = (size_t)ctx->H * rowBytes;
     for (int k = 1; k < ctx->bandWorld; ++k) {
-        const int r = (ctx->bandRank + k) % ctx->bandWorld; /* staggered, so that not everybody reads rank 0 first */
+        const int r = (ctx->bandRank + k) % ctx->bandWorld;
+        if (!band_reads(ctx, ctx->bandRank, r)) continue;
         band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 0, n + 1);
         ctx->launches++;
         const unsigned char *src = ctx->peerSlot[r][slot];
-        const int r0 = ctx->bandRow0[r], r1 = ctx->bandRow1[r];
-        CU(cudaMemcpyAsync(dst + (size_t)r0 * rowBytes, src + (size_t)r0 * rowBytes, (size_t)(r1 - r0) * rowBytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(dst + ylen + (size_t)(r0 >> 1) * rowBytes, src + ylen + (size_t)(r0 >> 1) * rowBytes, (size_t)((r1 >> 1) - (r0 >> 1)) * rowBytes,
+        const int a = ctx->bandRow0[r] > ctx->haloLo ? ctx->bandRow0[r] : ctx->haloLo;
+        const int b = ctx->bandRow1[r] < ctx->haloHi ? ctx->bandRow1[r] : ctx->haloHi;
+        CU(cudaMemcpyAsync(dst + (size_t)a * rowBytes, src + (size_t)a * rowBytes, (size_t)(b - a) * rowBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dst + ylen + (size_t)(a >> 1) * rowBytes, src + ylen + (size_t)(a >> 1) * rowBytes, (size_t)((b >> 1) - (a >> 1)) * rowBytes,
                            cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->bandP2pBytes += (size_t)(b - a) * rowBytes + (size_t)((b >> 1) - (a >> 1)) * rowBytes;
     }
-    band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 1, n + 1);
-    ctx->launches++;
+    if (ctx->bandWorld > 1) {
+        band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 1, n + 1);
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     if (launch_pack(ctx)) return 1;
     ctx->framesSeen++;
@@ -1504,10 +1644,18 @@ extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
     return 0;
 }
 
+extern "C" int hr_band_get_halo(const HrContext *ctx, int *lo, int *hi, unsigned long long *p2pBytes) {
+    if (!ctx || !ctx->banded) return 1;
+    if (lo) *lo = ctx->haloLo;
+    if (hi) *hi = ctx->haloHi;
+    if (p2pBytes) *p2pBytes = ctx->bandP2pBytes;
+    return 0;
+}
+
 /* downloadFrame for a band: only this context's rows, to host pointers of the band's first rows */
 extern "C" int hr_band_download(HrContext *ctx, void *yBand, void *uvBand, double *seconds) {
     if (!ctx) return 1;
-    if (ctx->bandWorld < 1) return fail(ctx, "hr_band_download: bands are not configured");
+    if (!ctx->banded) return fail(ctx, "hr_band_download: bands are not configured");
     if (!yBand || !uvBand) return fail(ctx, "hr_band_download: NULL plane");
     if (bind_device(ctx)) return 1;
     const size_t rowBytes = (size_t)ctx->W * ctx->bps;

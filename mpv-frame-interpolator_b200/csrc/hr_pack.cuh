@@ -60,9 +60,9 @@ __device__ __forceinline__ void store_words<1>(uint32_t *dst, const uint32_t (&w
  * aligned planes; pack_frame_kernel below handles everything else. */
 template <typename T, int S>
 __global__ void __launch_bounds__(128) pack_frame16_kernel(const T *__restrict__ yPlane, const T *__restrict__ uvPlane, uint32_t *__restrict__ packed,
-                                                            int W, int H, int planePitch, int planeSize) {
+                                                            int W, int H, int planePitch, int planeSize, int crow0) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int crow = blockIdx.y; /* chroma row = pair of luma rows */
+    const int crow = crow0 + blockIdx.y; /* chroma row = pair of luma rows; crow0: first one of the rows to pack */
     if (x0 >= W) return;
     constexpr int M = (1 << S) - 1, N = 16 >> S;
     const uint4 uv = load16_top8(uvPlane + (size_t)crow * W + x0);
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(128) pack_frame16_kernel(const T *__restrict__
 /* any geometry: one word per thread */
 template <typename T>
 __global__ void pack_frame_kernel(const T *__restrict__ yPlane, const T *__restrict__ uvPlane, uint32_t *__restrict__ packed,
-                                  int W, int H, int s, int lw, int planePitch, int planeSize) {
-    const int row = blockIdx.y;
+                                  int W, int H, int s, int lw, int planePitch, int planeSize, int row0) {
+    const int row = row0 + blockIdx.y;
     const int lx = blockIdx.x * blockDim.x + threadIdx.x;
     const int px = threadIdx.y;
     const int x = (lx << s) | px;

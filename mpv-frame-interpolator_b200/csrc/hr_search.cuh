@@ -175,7 +175,7 @@ __device__ __forceinline__ void trace_store(const FlowParams &P, const Thr &t, i
  * window larger than a tile; the real size is `ws`). AXIS 0: the layers move x, 1: y.
  * Packed word of full-resolution sample (x,y): plane ((y&m)<<s | (x&m)), row y>>s, column x>>s.
  * For WS = 64 the step only publishes the tile's totals; big_finish() scores them. */
-template <int RT, int WS, int AXIS>
+template <int RT, int WS, int AXIS, bool BANDS = false>
 __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &sh, Thr &t, int it, int ws, int lane, int warp, long long *fine = nullptr) {
     /* DBG instantiations only (fine == nullptr folds away elsewhere): clock stamps of thread 0 inside the step */
 #define FST(k) if (fine) { asm volatile("" ::: "memory"); fine[k] = clock64(); asm volatile("" ::: "memory"); }
@@ -331,7 +331,9 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
                 uint32_t tt = 0;
 #pragma unroll
                 for (int w = 0; w < HR_NWARPS; ++w) tt += sh.warpTot[w][lane];
-                put_tagged(P.partial + P.bigOff[step] + t.tile * HR_RMAX + lane, P.epoch, tt);
+                unsigned long long *slot = P.partial + P.bigOff[step] + t.tile * HR_RMAX + lane;
+                if (BANDS) put_tagged_all(P.band, slot, P.epoch, tt); /* the window's tiles live on several GPUs */
+                else put_tagged(slot, P.epoch, tt);
             }
             __syncthreads(); /* warpTot is reused by big_finish */
             return;
@@ -360,7 +362,15 @@ __device__ __forceinline__ void search_step(const FlowParams &P, SearchShared &s
     /* publish this level's windows (neighbours of the next level / blur) */
     if (AXIS == 1 && t.m0 && (t.px & (WS - 1)) == 0 && (t.py & (WS - 1)) == 0) {
         const int lgw = 31 - __clz(WS), nwx = (P.lw + WS - 1) >> lgw;
-        put_tagged(P.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw), P.epoch, (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16));
+        unsigned long long *slot = P.T + P.tOff[it] + (t.py >> lgw) * nwx + (t.px >> lgw);
+        const uint32_t word = (uint32_t)(uint16_t)t.ox | ((uint32_t)(uint16_t)t.oy << 16);
+        put_tagged(slot, P.epoch, word);
+        if (BANDS) {
+            /* the tiles across a band's edge read this level's windows (neighbour bias of the next level, blur halo) */
+            const int tileRow = t.ty0 / HR_TILE;
+            if (tileRow == P.band.tileRow0 && P.band.up >= 0) st_relaxed_sys_u64(at_peer(slot, P.band.peerDelta[P.band.up]), ((unsigned long long)P.epoch << 32) | word);
+            if (tileRow == P.band.tileRow1 - 1 && P.band.down >= 0) st_relaxed_sys_u64(at_peer(slot, P.band.peerDelta[P.band.down]), ((unsigned long long)P.epoch << 32) | word);
+        }
     }
 }
 
@@ -422,8 +432,9 @@ __device__ __forceinline__ void big_finish(const FlowParams &P, SearchShared &sh
 #define HR_SEARCH_MAXNREG 88 /* measured (tools/diag_pipeline.py): no spills at R = 5, 24 bytes at R = 16, same serial time as 117 */
 #endif
 #define HR_SEARCH_BOUNDS __maxnreg__(HR_SEARCH_MAXNREG)
-template <int RT, bool MULTI, bool DBG>
+template <int RT, bool MULTI, bool DBG, bool BANDS = false>
 __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
+    static_assert(!(BANDS && MULTI), "a band's tiles always fit the GPU");
     __shared__ SearchShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nCtas = gridDim.x;
@@ -456,8 +467,9 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
         t.v2a = frame2_word(t.cxs, t.cy0s) & t.m0;
         t.v2b = frame2_word(t.cxs, t.cy1s) & t.m1;
     };
+    const int firstTile = BANDS ? P.band.tile0 + (int)blockIdx.x : (int)blockIdx.x;
     if (!MULTI) {
-        thr_place(P, t, blockIdx.x, warp, lane);
+        thr_place(P, t, firstTile, warp, lane);
         load_frame2();
     } else {
         int slot = 0;
@@ -467,10 +479,21 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
             sh.parked[slot][tid] = make_int4(0, 0, (int)t.v2a, (int)t.v2b);
         }
     }
+    if (BANDS && P.band.world > 1) {
+        /* Every GPU of the group announces that it has entered this pair's search — by stream order that also says its
+         * previous search and the warps that read the previous flow are done, so its tables and its flow buffer may be
+         * written — and nobody stores into a peer before that peer has said so. All GPUs are then inside the same launch,
+         * which is what the polling below relies on. */
+        if (blockIdx.x == 0 && tid < P.band.world && tid != P.band.rank)
+            st_release_sys_u64(at_peer(P.band.ready + P.band.rank, P.band.peerDelta[tid]), P.epoch);
+        if (warp == 0 && lane < P.band.world && lane != P.band.rank)
+            while ((uint32_t)ld_acquire_sys_u64(P.band.ready + lane) != P.epoch) {}
+        __syncthreads();
+    }
     /* a CTA that owns several tiles (MULTI) parks the per-thread state of each in shared memory */
     auto for_tiles = [&](auto body) {
         int slot = 0;
-        for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas, ++slot) {
+        for (int tile = firstTile; tile < (BANDS ? firstTile + 1 : P.numTiles); tile += nCtas, ++slot) {
             if (MULTI) {
                 thr_place(P, t, tile, warp, lane);
                 const int4 st = sh.parked[slot][tid];
@@ -489,11 +512,11 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
     auto level = [&](auto wsTag, int it, int ws) {
         constexpr int WS = decltype(wsTag)::value;
         if constexpr (WS > HR_TILE) {
-            for_tiles([&] { search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp); });
+            for_tiles([&] { search_step<RT, WS, 0, BANDS>(P, sh, t, it, ws, lane, warp); });
             HR_STAMP();
             for_tiles([&] { big_finish<RT, 0>(P, sh, t, it, ws, lane, warp, true); });
             HR_STAMP();
-            for_tiles([&] { search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp); });
+            for_tiles([&] { search_step<RT, WS, 1, BANDS>(P, sh, t, it, ws, lane, warp); });
             HR_STAMP();
             for_tiles([&] { big_finish<RT, 1>(P, sh, t, it, ws, lane, warp, MULTI); });
             HR_STAMP();
@@ -503,9 +526,9 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
                 const int fineLevel = it - (P.iters - 3);
                 long long *fine = (DBG && P.timeline && tid == 0 && WS <= 8 && fineLevel >= 0 && fineLevel < 3)
                                       ? P.timeline + blockIdx.x * HR_TIMELINE_SLOTS + 40 + fineLevel * 12 : nullptr;
-                search_step<RT, WS, 0>(P, sh, t, it, ws, lane, warp, fine);
+                search_step<RT, WS, 0, BANDS>(P, sh, t, it, ws, lane, warp, fine);
                 HR_STAMP();
-                search_step<RT, WS, 1>(P, sh, t, it, ws, lane, warp, fine ? fine + 6 : nullptr);
+                search_step<RT, WS, 1, BANDS>(P, sh, t, it, ws, lane, warp, fine ? fine + 6 : nullptr);
                 HR_STAMP();
             });
         }
@@ -522,16 +545,20 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
     HR_STAMP(); /* search done */
 
     /* raw offsets (offsetArray) */
+    const int copies = BANDS ? P.band.world : 1; /* bands: every GPU gets the whole flow */
     for_tiles([&] {
-        if (t.m0) {
-            const size_t idx = (size_t)t.py * P.lw + t.px;
-            P.off[idx] = (int16_t)t.ox;
-            P.off[ln + idx] = (int16_t)t.oy;
-        }
-        if (t.m1) {
-            const size_t idx = (size_t)(t.py + 1) * P.lw + t.px;
-            P.off[idx] = (int16_t)t.ox;
-            P.off[ln + idx] = (int16_t)t.oy;
+        for (int g = 0; g < copies; ++g) {
+            int16_t *off = BANDS ? at_peer(P.off, P.band.peerDelta[g]) : P.off;
+            if (t.m0) {
+                const size_t idx = (size_t)t.py * P.lw + t.px;
+                off[idx] = (int16_t)t.ox;
+                off[ln + idx] = (int16_t)t.oy;
+            }
+            if (t.m1) {
+                const size_t idx = (size_t)(t.py + 1) * P.lw + t.px;
+                off[idx] = (int16_t)t.ox;
+                off[ln + idx] = (int16_t)t.oy;
+            }
         }
     });
 
@@ -544,7 +571,7 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
         int16_t *tX = sh.blur.tX, *tY = sh.blur.tY;
         int *hX = sh.blur.hX, *hY = sh.blur.hY;
         constexpr int NT = HR_THREADS;
-        for (int tile = blockIdx.x; tile < P.numTiles; tile += nCtas) {
+        for (int tile = firstTile; tile < (BANDS ? firstTile + 1 : P.numTiles); tile += nCtas) {
             const int ttx = tile % P.tilesX, tty = tile / P.tilesX;
             const int tx0 = ttx * HR_TILE, ty0 = tty * HR_TILE;
             {
@@ -603,13 +630,34 @@ __device__ __forceinline__ void flow_search_body(const FlowParams &P) {
                     }
                     const size_t idx = (size_t)y * P.lw + x;
                     const int bx = sx / 64, by = sy / 64; /* C division truncates toward zero */
-                    P.blur[idx] = (int16_t)bx;
-                    P.blur[ln + idx] = (int16_t)by;
-                    P.blurXY[idx] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
+                    for (int g = 0; g < copies; ++g) {
+                        int16_t *blur = BANDS ? at_peer(P.blur, P.band.peerDelta[g]) : P.blur;
+                        uint32_t *blurXY = BANDS ? at_peer(P.blurXY, P.band.peerDelta[g]) : P.blurXY;
+                        blur[idx] = (int16_t)bx;
+                        blur[ln + idx] = (int16_t)by;
+                        blurXY[idx] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
+                    }
                 }
             }
             __syncthreads();
         }
+    }
+    if (BANDS && P.band.world > 1) {
+        /* The launch may only end when the whole flow is here: the last CTA of every GPU to have stored its results tells
+         * the peers (after a system-wide fence), and one CTA of every GPU waits for all of them. */
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(P.band.exitCount, 1u);
+            if (prev == gridDim.x - 1) {
+                *P.band.exitCount = 0u; /* for the next launch (stream order) */
+                __threadfence_system();
+                for (int g = 0; g < P.band.world; ++g)
+                    if (g != P.band.rank) st_release_sys_u64(at_peer(P.band.done + P.band.rank, P.band.peerDelta[g]), P.epoch);
+            }
+        }
+        if (blockIdx.x == 0 && warp == 0 && lane < P.band.world && lane != P.band.rank)
+            while ((uint32_t)ld_acquire_sys_u64(P.band.done + lane) != P.epoch) {}
     }
     HR_STAMP(); /* blur done */
     if (DBG && P.timeline && tid == 0) {
@@ -629,6 +677,12 @@ __global__ void HR_SEARCH_BOUNDS flow_search_kernel(const FlowParams P) {
 template <bool MULTI, bool DBG>
 __global__ void __launch_bounds__(HR_THREADS, 1) flow_search_generic_kernel(const FlowParams P) {
     flow_search_body<0, MULTI, DBG>(P);
+}
+/* one band of a frame that is split over several GPUs (BandLink, hr_common.cuh): the default radius unrolled (RT = 5),
+ * any other radius generic (RT = 0) */
+template <int RT>
+__global__ void __launch_bounds__(HR_THREADS, 1) flow_search_band_kernel(const FlowParams P) {
+    flow_search_body<RT, false, false, true>(P);
 }
 
 /* Stand-alone K4 (parity tap hr_blur_flow): direct 64-tap form of blurFlowKernel.cl:80-88. */

@@ -2,9 +2,9 @@
 
 * independent frame pairs / streams (`shard_items`): item i -> rank i mod N; every rank owns its own
   context, stream and pinned buffers; results meet only as counters and times (`reduce_throughput`).
-* 8K spatial bands (`band_rows`, `band_halo`): rows split on multiples of 2^(s+1) full-resolution rows
-  (lattice-row and chroma-row aligned); each rank uploads, warps and downloads only its band; the rows a
-  band's warp can reach outside itself follow from the search radius.
+* 8K spatial bands (`band_rows`, `band_halo`): rows split into whole lattice tile rows (32 << s frame rows); each rank
+  uploads, searches, warps and downloads only its band; the rows its search and warp can reach outside the band
+  (the halo, fetched from the neighbours by NVLink P2P) follow from the search radius.
 
 Pure Python + torch.distributed for the counters (gloo on CPU in the tests, NCCL under torchrun);
 the reference has no counterpart (single device, `HR/opticalFlowCalc.c:279-305`).
@@ -27,22 +27,28 @@ def res_scalar(frame_height, max_calc_res=270):
     return s
 
 
+LATTICE_TILE = 32   # lattice points per tile side of the search kernel (csrc/hr_common.cuh HR_TILE)
+
+
 def band_rows(frame_height, world, s=None):
-    """[(row0, row1)] per rank: contiguous bands, boundaries on multiples of 2^(s+1) rows, sizes as equal
-    as that alignment allows, the last band takes the remainder. Every row belongs to exactly one band."""
+    """[(row0, row1)] per rank: contiguous bands of whole lattice tile rows (32 << s frame rows: the search is split
+    by tiles, and tile rows are lattice-row and chroma-row aligned), sizes as equal as that allows, the last band ends
+    with the frame. Every row belongs to exactly one band."""
     if s is None:
         s = res_scalar(frame_height)
-    unit = 1 << (s + 1)
+    unit = LATTICE_TILE << s
     units = math.ceil(frame_height / unit)
     if world > units:
         raise ValueError("%d bands do not fit %d rows in units of %d" % (world, frame_height, unit))
-    base, extra = divmod(units, world)
-    out, u = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
-        out.append((min(u * unit, frame_height), min((u + n) * unit, frame_height)))
-        u += n
-    return out
+    # boundary r as close to r/world of the frame as whole tile rows allow, at least one tile row per band
+    cuts = [0]
+    for r in range(1, world):
+        c = int(round(r * frame_height / world / unit))
+        c = max(c, cuts[-1] + 1)
+        c = min(c, units - (world - r))
+        cuts.append(c)
+    cuts.append(units)
+    return [(min(a * unit, frame_height), min(b * unit, frame_height)) for a, b in zip(cuts, cuts[1:])]
 
 
 def max_offset(radius, iterations=8):

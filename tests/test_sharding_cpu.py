@@ -26,14 +26,20 @@ def test_bands_cover_the_frame_and_are_aligned(hr):
     for h in (1080, 2160, 4320, 4322, 720):
         s = S.res_scalar(h)
         for world in (1, 2, 4, 8):
+            if world > -(-h // (32 << s)):
+                continue                             # more bands than lattice tile rows
             bands = S.band_rows(h, world)
             assert bands[0][0] == 0 and bands[-1][1] == h
             for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
                 assert a1 == b0 and a0 < a1
             for r0, r1 in bands[:-1]:
-                assert r1 % (1 << (s + 1)) == 0
+                assert r1 % (32 << s) == 0          # whole lattice tile rows: the search is split by tiles
     assert S.res_scalar(4320) == 4 and S.res_scalar(2160) == 3 and S.res_scalar(1080) == 2
-    assert S.band_rows(4320, 8)[0] == (0, 544) and S.band_rows(4320, 8)[-1] == (3808, 4320)
+    assert S.band_rows(4320, 8) == [(512 * k, 512 * (k + 1)) for k in range(7)] + [(3584, 4320)]
+    assert S.band_rows(4320, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4320)]
+    assert S.band_rows(1080, 2) == [(0, 512), (512, 1080)]
+    with pytest.raises(ValueError):
+        S.band_rows(720, 8)                          # 720 lines = 6 tile rows
 
 
 def test_halo_follows_the_search_radius(hr):
@@ -62,7 +68,7 @@ dist.all_gather_object(gathered, mine)
 assert sorted(gathered[0] + gathered[1]) == list(range(9))
 assert outs == 45 and secs == 2.0, (outs, secs)
 bands = S.band_rows(4320, 2)
-assert bands[rank] == ((0, 2176), (2176, 4320))[rank]
+assert bands[rank] == ((0, 2048), (2048, 4320))[rank]
 dist.barrier()
 dist.destroy_process_group()
 print("rank %d ok" % rank)

@@ -6,7 +6,8 @@ sections (default: all): host  - the six calls of the host interface, all output
                          multi - a lattice with more tiles than SMs (search CTAs own several tiles)
                          s4    - resolution scalar 4 (a narrow 8K strip), NV12 and P010
                          pipe  - pipelined mode: hr_steps_device on device planes (two search lanes, warp streams)
-                         bands - two band contexts on one GPU (mailbox kernels, P2P copies)
+                         bands - a band group of one band (band search kernel, row-range pack; groups of several bands need
+                                 one GPU each, see tests/test_gpu_bands.py)
 tools/run_sanitizers.sh runs the three tools and keeps their summaries (profiles/r02_sanitizer_*.txt).
 """
 import ctypes as C
@@ -92,7 +93,7 @@ if "pipe" in sections:
 if "bands" in sections:
     w, h = 1280, 720
     c = synth.MovingTextureClip(w, h)
-    b = hr.BandGroup(h, w, w, 0, (0, 0))
+    b = hr.BandGroup(h, w, w, 0, (0,))
     for k in range(3):
         b.update_frame(*c.frame(k))
         if k:
