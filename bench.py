@@ -592,13 +592,13 @@ def zero_copy_leg(env, g, ring, out_ring, ets, nring, radius, mode):
             "api": "hr_update_frame_device(borrow) / hr_calc_flow(blocking) / hr_set_output_device + hr_warp per output / hr_synchronize per source frame: device planes in and out"}
 
 
-def host_ceiling(env, workload):
+def host_ceiling(env, workload, frac=1.0):
     """What the PCIe legs of one step allow on this rank with no kernel at all: one frame host->device, the step's
     outputs device->host, pinned memory. serial = one copy after the other with a wait each (how the blocking calls
     drive them); duplex = upload and downloads on two streams at once (the bound of any asynchronous host interface)."""
     torch = env.torch
     w, h, pixfmt, sfps, dfps, _ = WORKLOADS[workload]
-    nbytes = int(1.5 * w * h * (2 if pixfmt else 1))
+    nbytes = int(1.5 * w * h * (2 if pixfmt else 1) * frac) & ~255     # a band's share of the frame
     per_step = dfps / sfps
     hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -728,8 +728,11 @@ def run_ours(args):
 
     extras = []
     ceiling = None
-    if not args.no_extra and not banded:
-        ceiling = host_ceiling(env, args.workload)
+    if not args.no_extra:
+        ceiling = host_ceiling(env, args.workload, band_frac)
+        if banded:                   # every rank moves a band of the SAME frames
+            for k in ("serial_frames_per_s", "duplex_frames_per_s"):
+                ceiling[k] /= world
     if world == 1 and not args.no_extra:
         shared = {}
         for name in EXTRA_CONFIGS:

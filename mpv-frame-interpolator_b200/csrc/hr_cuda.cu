@@ -68,6 +68,7 @@ struct HrContext {
     unsigned long long bandFrames;                  /* frames uploaded so far                                  */
     int bandPending;                                /* hr_band_upload done, hr_band_gather outstanding        */
     int banded;                                     /* bands configured (also with a single band)              */
+    int bandSearched;                               /* a search of the group was launched since the last upload */
     int bandMaxRadius;                              /* largest search radius the halo is sized for             */
     int haloLo, haloHi;                             /* rows of every frame this GPU holds: band + halo         */
     unsigned long long bandP2pBytes;                /* bytes fetched from peers' frame slots so far             */
@@ -906,6 +907,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         P.blurXY = (uint32_t *)(ctx->arena + ctx->aBlurXY);
         P.trace = NULL;
         P.timeline = NULL;
+        ctx->bandSearched = 1;
         grid = (B.tileRow1 - B.tileRow0) * ctx->tilesX;
         if (grid < 1 || grid > ctx->smCount) return fail(ctx, "hr_calc_flow: a band of %d tiles does not fit the GPU", grid);
     }
@@ -1416,6 +1418,46 @@ static void band_reach(const HrContext *ctx, int r, int *lo, int *hi) {
 }
 static size_t arena_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
+/* The halo of one frame in ONE launch: wait until every owner has uploaded its band of the frame (mailbox counter),
+ * copy the halo rows out of the owners' frame slots (peer-mapped 128-bit loads over NVLink), and — the last CTA to
+ * finish — tell the peers that this GPU no longer reads their slots of this frame. */
+#define HR_HALO_MAX_SEGS (2 * HR_MAX_BANDS)
+struct HaloJob {
+    int nSeg;
+    const uint4 *src[HR_HALO_MAX_SEGS];
+    uint4 *dst[HR_HALO_MAX_SEGS];
+    unsigned long long units[HR_HALO_MAX_SEGS];           /* 16-byte units of the segment                     */
+    const unsigned long long *uploaded[HR_HALO_MAX_SEGS]; /* the owner's "frames uploaded" counter              */
+    unsigned long long frame;                             /* wait for uploaded >= frame                         */
+    unsigned long long *gathered;                         /* own "frames fetched" counter                       */
+    unsigned int *exitCount;
+};
+__global__ void __launch_bounds__(256) band_halo_kernel(const HaloJob J) {
+    if (threadIdx.x < J.nSeg) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(J.uploaded[threadIdx.x]) : "memory");
+        } while (v < J.frame);
+    }
+    __syncthreads();
+    for (int sgm = 0; sgm < J.nSeg; ++sgm) {
+        const uint4 *src = J.src[sgm];
+        uint4 *dst = J.dst[sgm];
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.units[sgm]; i += (unsigned long long)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(J.exitCount, 1u);
+        if (prev == gridDim.x - 1) {
+            *J.exitCount = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(J.gathered), "l"(J.frame) : "memory");
+        }
+    }
+}
+
 extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int *row0, const int *row1) {
     if (!ctx || !row0 || !row1) return 1;
     if (world < 1 || world > HR_MAX_BANDS || rank < 0 || rank >= world) return fail(ctx, "hr_band_configure: rank %d / world %d out of range (max %d bands)", rank, world, HR_MAX_BANDS);
@@ -1450,7 +1492,7 @@ extern "C" int hr_band_configure(HrContext *ctx, int rank, int world, const int 
         ctx->aBlurXY = o;   o = arena_align(o + ln * sizeof(uint32_t));
         ctx->aReady = o;    o = arena_align(o + HR_MAX_BANDS * 8);
         ctx->aDone = o;     o = arena_align(o + HR_MAX_BANDS * 8);
-        ctx->aExit = o;     o = arena_align(o + 8);
+        ctx->aExit = o;     o = arena_align(o + 16); /* exit counters: search launch, halo launch */
         ctx->aMail = o;     o = arena_align(o + 256);
         ctx->arenaBytes = o;
         CU(cudaMalloc(&ctx->arena, o));
@@ -1581,13 +1623,17 @@ extern "C" int hr_band_upload(HrContext *ctx, const void *yBand, const void *uvB
     int slot;
     rotate_slots(ctx, &slot);
     const unsigned long long n = ctx->bandFrames; /* this is frame n; frame n-2 lived in the same slot */
-    if (n >= 2) {
+    if (n >= 2 && !ctx->bandSearched) {
+        /* The slot about to be overwritten held frame n-2, whose halo rows the neighbours fetched from here. A search of
+         * the group since then already proves that they are done (every GPU enters a pair's search after it has fetched
+         * that pair's halos, and no search ends before all have entered); without one, ask their counters. */
         for (int r = 0; r < ctx->bandWorld; ++r) {
             if (!band_reads(ctx, r, ctx->bandRank)) continue;
             band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 1, n - 1); /* peer r has fetched its halo of frame n-2 */
             ctx->launches++;
         }
     }
+    ctx->bandSearched = 0;
     unsigned char *dst = ctx->frameBuf[slot];
     const size_t rowBytes = (size_t)ctx->W * ctx->bps, ylen = (size_t)ctx->H * rowBytes;
     const int r0 = ctx->bandRow0[ctx->bandRank], r1 = ctx->bandRow1[ctx->bandRank];
@@ -1618,7 +1664,46 @@ extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
     const unsigned long long n = ctx->bandFrames;
     unsigned char *dst = ctx->frameBuf[slot];
     const size_t rowBytes = (size_t)ctx->W * ctx->bps, ylen = (size_t)ctx->H * rowBytes;
-    for (int k = 1; k < ctx->bandWorld; ++k) {
+    /* rows, planes and slots aligned to 16 bytes (every real frame): one launch waits, copies and signals */
+    const int fused = rowBytes % 16 == 0 && ((uintptr_t)dst % 16) == 0 && ylen % 16 == 0 && ctx->bandWorld > 1;
+    if (fused) {
+        HaloJob J;
+        memset(&J, 0, sizeof(J));
+        unsigned long long total = 0;
+        for (int k = 1; k < ctx->bandWorld; ++k) {
+            const int r = (ctx->bandRank + k) % ctx->bandWorld;
+            if (!band_reads(ctx, ctx->bandRank, r)) continue;
+            const unsigned char *src = ctx->peerSlot[r][slot];
+            const int a = ctx->bandRow0[r] > ctx->haloLo ? ctx->bandRow0[r] : ctx->haloLo;
+            const int b = ctx->bandRow1[r] < ctx->haloHi ? ctx->bandRow1[r] : ctx->haloHi;
+            const size_t off[2] = {(size_t)a * rowBytes, ylen + (size_t)(a >> 1) * rowBytes};
+            const size_t len[2] = {(size_t)(b - a) * rowBytes, (size_t)((b >> 1) - (a >> 1)) * rowBytes};
+            for (int pl = 0; pl < 2; ++pl) {
+                if (((uintptr_t)(src + off[pl])) % 16) return fail(ctx, "hr_band_gather: peer slot not aligned");
+                J.src[J.nSeg] = (const uint4 *)(src + off[pl]);
+                J.dst[J.nSeg] = (uint4 *)(dst + off[pl]);
+                J.units[J.nSeg] = len[pl] / 16;
+                J.uploaded[J.nSeg] = ctx->peerMail[r] + 0;
+                total += len[pl];
+                ++J.nSeg;
+            }
+        }
+        J.frame = n + 1;
+        J.gathered = ctx->mail + 1;
+        J.exitCount = (unsigned int *)(ctx->arena + ctx->aExit) + 2;
+        if (J.nSeg) {
+            int ctas = (int)((total / 16 + 255) / 256);
+            if (ctas > 2 * ctx->smCount) ctas = 2 * ctx->smCount;
+            if (ctas < 1) ctas = 1;
+            band_halo_kernel<<<ctas, 256, 0, ctx->stream>>>(J);
+            ctx->launches++;
+            ctx->bandP2pBytes += total;
+        } else {
+            band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 1, n + 1);
+            ctx->launches++;
+        }
+    }
+    for (int k = 1; k < ctx->bandWorld && !fused; ++k) {
         const int r = (ctx->bandRank + k) % ctx->bandWorld;
         if (!band_reads(ctx, ctx->bandRank, r)) continue;
         band_wait_kernel<<<1, 1, 0, ctx->stream>>>(ctx->peerMail[r] + 0, n + 1);
@@ -1631,7 +1716,7 @@ extern "C" int hr_band_gather(HrContext *ctx, int blocking) {
                            cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->bandP2pBytes += (size_t)(b - a) * rowBytes + (size_t)((b >> 1) - (a >> 1)) * rowBytes;
     }
-    if (ctx->bandWorld > 1) {
+    if (ctx->bandWorld > 1 && !fused) {
         band_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->mail + 1, n + 1);
         ctx->launches++;
     }
