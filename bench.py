@@ -182,7 +182,11 @@ def pacing_ts(n_steps, src_fps, disp_fps):
     return [p.next_source_frame() for _ in range(n_steps)]
 
 
-def warp_bytes(w, h, bps, lw, lh):
+def warp_bytes(w, h, bps, lw, lh, mode=2):
+    """Algorithmic bytes of one output frame: both source frames read, one frame written, the flow read. The HSV flow
+    mode reads no chroma (its chroma plane is a per-cell constant) but the colour table as well."""
+    if mode == 3:
+        return 3 * w * h * bps + int(0.5 * w * h * bps) + 8 * lw * lh
     return 3 * int(1.5 * w * h * bps) + 4 * lw * lh
 
 
@@ -406,7 +410,7 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
         g.synchronize()
         # pilot: how long do K steps take? -> repetitions for a region of MIN_REGION_S (the same on every rank)
         _, pilot = timed(lambda: steps_device(W, K), 1)
-        reps = max(1, int(np.ceil(MIN_REGION_S * 1.15 / max(env.max_over_ranks(pilot), 1e-6))))
+        reps = max(1, int(np.ceil(MIN_REGION_S * 1.4 / max(env.max_over_ranks(pilot), 1e-6))))
         env.barrier()
         sampler = ClockSampler(local)
         if rank == 0:
@@ -546,6 +550,10 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
             if full:
                 res["e2e_pageable"] = dict(replay_leg(False), api="the same calls with malloc'd (pageable) planes, as mpv's image pool delivers them")
                 res["e2e_zero_copy"] = zero_copy_leg(env, g, ring, out_ring, ets, nring, radius, mode)
+    if banded:
+        lo, hi, _ = g.band_halo()
+        res["band"] = {"rows": [r0, r1], "held_rows": [lo, hi],
+                       "nvlink_halo_bytes_per_frame": int(((r0 - lo) + (hi - r1)) * w * bps * 1.5)}
     g.close()
     del ring, out_ring
     torch.cuda.empty_cache()
@@ -653,7 +661,7 @@ def kernel_rooflines(env, res, radius):
     per_step = {"pack": kms["pack"], "search": kms["search"], "warp": kms["warp"] * (kcount["warp"] / max(1, kcount["search"]))}
     tot = max(1e-12, sum(per_step.values()))
     opl = res["warp_outputs_per_launch"]
-    wbytes = int(warp_bytes(w, h, bps, lw, lh) * ((r1 - r0) / h))   # a band's launch moves the band's rows
+    wbytes = int(warp_bytes(w, h, bps, lw, lh, res["mode"]) * ((r1 - r0) / h))   # a band's launch moves the band's rows
     alg = {"warp": wbytes * opl, "pack": int(1.5 * w * h * bps) + 4 * w * h}
     tag = ncu_tag(res["workload"])
     roof = {}
@@ -754,6 +762,25 @@ def run_ours(args):
                 blk["e2e"].update(h2d_bytes_per_step=r["frame_bytes"], d2h_bytes_per_step=int(r["frame_bytes"] * edf / esf))
             extras.append(blk)
 
+    bands_block = None
+    if world > 1 and not banded and not args.no_extra and not os.environ.get("HR_BENCH_NO_BANDS"):
+        # the 8K configuration of BASELINE.json on the same N GPUs, every frame split into N spatial bands (strong scaling):
+        # a secondary block of this line, so that a scaling run records it next to the independent-streams figure
+        bname = "8k-p010-24to60"
+        br = measure(env, bname, 40, 5, radius, banded=True, full=False)
+        br["banded"] = True
+        bs = summarize(env, br, radius, 40, 5)
+        halo = env.reduce(br["band"]["nvlink_halo_bytes_per_frame"], 0.0)[0]
+        bceil = host_ceiling(env, bname, (br["rows"][1] - br["rows"][0]) / WORKLOADS[bname][1])
+        if rank == 0:
+            broof, bdom = kernel_rooflines(env, br, radius)
+            bands_block = {"workload": bname, "partition": "%d spatial bands of whole lattice tile rows; halo rows by NVLink P2P, band-sharded search with tile totals / edge windows / flow stored into the peers' arenas" % world,
+                           "scaling": "strong", "value": bs["value"], "unit": "frames/s", "ms_per_step": bs["ms_per_step"], "reps": bs["reps"], "timed_region_s": bs["timed_region_s"],
+                           "e2e": {"value": bs["e2e"]["value"], "unit": "frames/s", "steps": bs["e2e"]["steps"]} if "e2e" in bs else None,
+                           "nvlink_halo_bytes_per_frame_all_gpus": int(halo), "rank0_rows": br["band"]["rows"], "rank0_held_rows": br["band"]["held_rows"],
+                           "host_ceiling": {k: (v / world if k.endswith("frames_per_s") else v) for k, v in bceil.items()},
+                           "kernels_rank0": {k: {"avg_us": v["avg_us"], "frac": v["frac"], "bound": v["bound"]} for k, v in broof.items()}}
+
     if rank == 0:
         roof, dom = kernel_rooflines(env, res, radius)
         line = {
@@ -789,6 +816,8 @@ def run_ours(args):
             line["host_ceiling"] = ceiling
         if extras:
             line["configs_measured"] = extras
+        if bands_block:
+            line["bands_8k"] = bands_block
         if world == 1 and not args.no_extra:
             line["reference_gpu"] = reference_gpu(args)
         if world == 1 and not args.no_cpu_baseline:

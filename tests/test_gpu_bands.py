@@ -61,6 +61,8 @@ def _stream_equals_single(hr, synth, w, h, pixfmt, devices, radii, max_radius):
     (3840, 2160, 1, 2, (5, 5), 5),
     (1280, 720, 0, 3, (5, 6, 5), 6),
     (7680, 4320, 1, 2, (5,), 5),
+    (7680, 4320, 1, 8, (5, 7), 7),       # one lattice tile row per GPU (the last one: the last two)
+    (3840, 2160, 0, 8, (16,), 16),       # halos that span several bands
 ])
 def test_banded_stream_equals_single_context(hr, synth, w, h, pixfmt, world, radii, max_radius):
     nd = _ndev()
