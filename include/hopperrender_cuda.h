@@ -231,6 +231,21 @@ int hr_debug_int_peak(int device, double *evalsPerSecond, double *warpInstrPerCl
 #define HR_TIMELINE_SLOTS 128
 int hr_set_timeline(HrContext *ctx, int enable);
 int hr_get_timeline(HrContext *ctx, long long *stamps, int maxCtas);
+/* With HR_TIMELINE_HOST=1 in the environment the stamps live in mapped host memory and can be read while a launch is
+ * still running (or is not coming back): the same array, copied without any synchronisation. */
+int hr_debug_peek_timeline(HrContext *ctx, long long *stamps, int maxCtas);
+
+/* Developer knob: which generation of the search kernel the following hr_calc_flow launches use. 2 (default):
+ * csrc/hr_search2.cuh for radii 5..16 on lattices of at most one tile per SM outside band groups, csrc/hr_search.cuh
+ * for everything else; 1: csrc/hr_search.cuh always. Both write the same tables, totals and offsets (same bits). */
+int hr_debug_set_search_generation(HrContext *ctx, int generation);
+/* ... and the generation the most recent search launch of the context actually ran (0: none yet). */
+int hr_debug_last_search_generation(const HrContext *ctx);
+/* Generation 2 has a variant that stages the tile's neighbourhood of all 16 phase planes of the packed frame in shared
+ * memory by TMA (resolution scalar 2 — 1080p, 720p —, radius 5..8); on by default where it applies. enable = 0: the
+ * following launches read their samples from global memory. hr_debug_last_search_staged: what the last launch ran. */
+int hr_debug_set_search_staged(HrContext *ctx, int enable);
+int hr_debug_last_search_staged(const HrContext *ctx);
 
 /* Record CUDA events around every kernel launch (off by default; adds two event records per launch). */
 int hr_set_profiling(HrContext *ctx, int enable);

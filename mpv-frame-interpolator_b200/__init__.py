@@ -82,8 +82,13 @@ ABI = {
     "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hr_debug_rcp_table": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_debug_int_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hr_debug_set_search_generation": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_debug_last_search_generation": (C.c_int, [C.c_void_p]),
+    "hr_debug_set_search_staged": (C.c_int, [C.c_void_p, C.c_int]),
+    "hr_debug_last_search_staged": (C.c_int, [C.c_void_p]),
     "hr_set_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hr_debug_peek_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hr_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hr_get_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -300,12 +305,31 @@ class HrCuda:
         self._chk(self.lib.hr_get_step_layers(self.h, step, _ptr(out)))
         return out
 
+    def set_search_generation(self, generation):
+        """Developer knob: 2 = csrc/hr_search2.cuh where it applies (default), 1 = csrc/hr_search.cuh always."""
+        self._chk(self.lib.hr_debug_set_search_generation(self.h, int(generation)))
+
+    def last_search_generation(self):
+        return int(self.lib.hr_debug_last_search_generation(self.h))
+
+    def set_search_staged(self, on=True):
+        """Developer knob: the TMA-staged variant of generation 2 where it applies (default) or never."""
+        self._chk(self.lib.hr_debug_set_search_staged(self.h, 1 if on else 0))
+
+    def last_search_staged(self):
+        return bool(self.lib.hr_debug_last_search_staged(self.h))
+
     def set_timeline(self, on=True):
         self._chk(self.lib.hr_set_timeline(self.h, 1 if on else 0))
 
     def get_timeline(self):
         out = np.zeros((self.info.searchCtas, 128), np.int64)
         self._chk(self.lib.hr_get_timeline(self.h, _ptr(out), self.info.searchCtas))
+        return out
+
+    def peek_timeline(self):
+        out = np.zeros((self.info.searchCtas, 128), np.int64)
+        self._chk(self.lib.hr_debug_peek_timeline(self.h, _ptr(out), self.info.searchCtas))
         return out
 
     def set_profiling(self, on=True):

@@ -11,9 +11,11 @@
 #include "hr_common.cuh"
 #include "hr_pack.cuh"
 #include "hr_search.cuh"
+#include "hr_search2.cuh"
 #include "hr_warp.cuh"
 #include "hr_warp_fast.cuh"
 
+#include <cuda.h> /* CUtensorMap and its encoder, reached through cudaGetDriverEntryPoint: no link against libcuda */
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -53,6 +55,7 @@ struct HrContext {
     uint8_t *trace;
     int traceOn;
     long long *timeline;
+    long long *timelineHost; /* HR_TIMELINE_HOST=1: the stamps live in mapped host memory */
     int timelineOn;
     int useFastWarp;
     int haveRcp8;                  /* MUFU.RCP of the 8-bit level denominators, cached per knob setting     */
@@ -123,6 +126,12 @@ struct HrContext {
     unsigned long long flowStamp;
     float lastT, lastDelta, lastBlack, lastWhite;
     int lastWarpFrames, lastMode, aheadOn;
+    int lastSearchGen; /* generation the most recent search launch ran */
+    int lastSearchStaged; /* ... and whether it was the TMA-staged variant */
+    int stagedOk;      /* tensor maps of the two packed copies exist (resolution scalar 2, driver has the encoder) */
+    int stagedOn;      /* developer knob HR_SEARCH_STAGED=0 / hr_debug_set_search_staged */
+    HrTensorMap tmapPacked[2]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
+    int searchGen; /* 2: hr_search2.cuh where it applies (radius 5..16, one tile per CTA, no bands / timeline), 1: hr_search.cuh always */
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
@@ -273,7 +282,8 @@ extern "C" int hr_destroy(HrContext *ctx) {
         if (ctx->evColour[b]) cudaEventDestroy(ctx->evColour[b]);
     }
     cudaFree(ctx->arena);
-    cudaFree(ctx->timeline);
+    if (ctx->timelineHost) cudaFreeHost(ctx->timelineHost);
+    else cudaFree(ctx->timeline);
     if (ctx->evUpdate) cudaEventDestroy(ctx->evUpdate);
     if (ctx->evFlowEnd) cudaEventDestroy(ctx->evFlowEnd);
     if (ctx->evWarpStart) cudaEventDestroy(ctx->evWarpStart);
@@ -282,6 +292,35 @@ extern "C" int hr_destroy(HrContext *ctx) {
         if (ctx->evK[i]) cudaEventDestroy(ctx->evK[i]);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     free(ctx);
+    return 0;
+}
+
+/* 3-D tensor maps (words of a plane row, plane rows, phase planes) over the two packed copies, boxes of the staged
+ * search (hr_search2.cuh): 60 words x 50 rows x 1 plane, out-of-range parts filled with zeros. */
+static int make_packed_tensor_maps(HrContext *ctx, uint32_t *const physical[2]) {
+    ctx->stagedOk = 0;
+    if (ctx->s != HR_ST_S) return 0;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = NULL;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return 0; /* no encoder: the unstaged kernels serve every launch */
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(HrTensorMap), "tensor map size");
+    for (int i = 0; i < 2; ++i) {
+        const cuuint64_t dims[3] = {(cuuint64_t)ctx->planePitch, (cuuint64_t)ctx->lh, (cuuint64_t)1 << (2 * ctx->s)};
+        const cuuint64_t strides[2] = {(cuuint64_t)ctx->planePitch * 4, (cuuint64_t)ctx->planeSize * 4};
+        const cuuint32_t box[3] = {HR_ST_PW, HR_ST_PH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUtensorMap tm;
+        const CUresult r = ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, physical[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed (%d) for the packed frame", (int)r);
+        memcpy(&ctx->tmapPacked[i], &tm, sizeof(tm));
+    }
+    ctx->stagedOk = 1;
     return 0;
 }
 
@@ -363,6 +402,10 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMemset(ctx->outBuf, 0, ctx->frameBytes));
     CU(cudaMemset(ctx->packed[0], 0, ctx->packedBytes));
     CU(cudaMemset(ctx->packed[1], 0, ctx->packedBytes));
+    {
+        uint32_t *const physical[2] = {ctx->packed[0], ctx->packed[1]}; /* packedId[i] = i at this point */
+        if (make_packed_tensor_maps(ctx, physical)) return 1;
+    }
     CU(cudaMemset(ctx->off, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blur, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blurXY, 0, ln * sizeof(uint32_t)));
@@ -393,6 +436,10 @@ static int create_impl(HrContext *ctx) {
     ctx->useFastWarp = !(g && g[0] == '1');
     const char *ah = getenv("HR_AHEAD");
     ctx->aheadOn = !(ah && ah[0] == '0');
+    const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 2 = hr_search2.cuh where it applies (measured: slower, profiles/r02_search_generations.txt) */
+    ctx->searchGen = (sg && sg[0] == '2') ? 2 : 1;
+    const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
+    ctx->stagedOn = !(ss && ss[0] == '0');
     CU(cudaDeviceSynchronize());
     return 0;
 }
@@ -572,10 +619,41 @@ extern "C" int hr_set_timeline(HrContext *ctx, int enable) {
     if (bind_device(ctx)) return 1;
     if (enable && !ctx->timeline) {
         const size_t n = (size_t)ctx->grid * HR_TIMELINE_SLOTS * sizeof(long long);
-        CU(cudaMalloc(&ctx->timeline, n));
-        CU(cudaMemset(ctx->timeline, 0, n));
+        const char *hostTl = getenv("HR_TIMELINE_HOST"); /* developer knob: stamps in mapped host memory (hr_debug_peek_timeline) */
+        if (hostTl && hostTl[0] == '1') {
+            CU(cudaHostAlloc((void **)&ctx->timelineHost, n, cudaHostAllocMapped));
+            memset(ctx->timelineHost, 0, n);
+            CU(cudaHostGetDevicePointer((void **)&ctx->timeline, ctx->timelineHost, 0));
+        } else {
+            CU(cudaMalloc(&ctx->timeline, n));
+            CU(cudaMemset(ctx->timeline, 0, n));
+        }
     }
     ctx->timelineOn = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int hr_debug_set_search_generation(HrContext *ctx, int generation) {
+    if (!ctx) return 1;
+    if (generation != 1 && generation != 2) return fail(ctx, "hr_debug_set_search_generation: %d is not 1 or 2", generation);
+    ctx->searchGen = generation;
+    return 0;
+}
+
+/* the stamps as they stand right now, without waiting for anything (HR_TIMELINE_HOST=1 only) */
+extern "C" int hr_debug_peek_timeline(HrContext *ctx, long long *stamps, int maxCtas) {
+    if (!ctx) return 1;
+    if (!ctx->timelineHost) return fail(ctx, "hr_debug_peek_timeline: needs HR_TIMELINE_HOST=1 and hr_set_timeline");
+    const int n = maxCtas < ctx->grid ? maxCtas : ctx->grid;
+    memcpy(stamps, ctx->timelineHost, (size_t)n * HR_TIMELINE_SLOTS * sizeof(long long));
+    return 0;
+}
+
+extern "C" int hr_debug_last_search_generation(const HrContext *ctx) { return ctx ? ctx->lastSearchGen : 0; }
+extern "C" int hr_debug_last_search_staged(const HrContext *ctx) { return ctx ? ctx->lastSearchStaged : 0; }
+extern "C" int hr_debug_set_search_staged(HrContext *ctx, int enable) {
+    if (!ctx) return 1;
+    ctx->stagedOn = enable ? 1 : 0;
     return 0;
 }
 
@@ -824,9 +902,52 @@ extern "C" int hr_update_frame_device(HrContext *ctx, const void *dY, const void
 /* The search radius the filter uses drifts between MIN_SEARCH_RADIUS and MAX_SEARCH_RADIUS
  * (config.h:6-7, vf_HopperRender.c:326-345): those radii get a kernel with the layer loop fully
  * unrolled and the layer shifts as immediates; any other radius runs the generic kernel. */
-static const void *search_kernel_for(int R, int multi, int timeline) {
+/* the TMA-staged variant of generation 2 (resolution scalar 2, radius 5..HR_ST_MAX_RADIUS); NULL: none for this radius */
+static const void *staged_kernel_for(int R, int timeline) {
+    const void *k = NULL;
+    if (timeline) k = R == 5 ? (const void *)flow_search2_staged_kernel<5, true> : NULL;
+    else {
+        switch (R) {
+            case 5: k = (const void *)flow_search2_staged_kernel<5>; break;
+            case 6: k = (const void *)flow_search2_staged_kernel<6>; break;
+            case 7: k = (const void *)flow_search2_staged_kernel<7>; break;
+            case 8: k = (const void *)flow_search2_staged_kernel<8>; break;
+            default: break;
+        }
+    }
+    if (k) {
+        static const void *prepared[16];
+        static int nPrepared = 0;
+        int seen = 0;
+        for (int i = 0; i < nPrepared; ++i) seen |= prepared[i] == k;
+        if (!seen) {
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, HR_ST_BYTES) != cudaSuccess) {
+                cudaGetLastError();
+                return NULL;
+            }
+            if (nPrepared < 16) prepared[nPrepared++] = k;
+        }
+    }
+    return k;
+}
+
+static const void *search_kernel_for(int R, int multi, int timeline, int gen, int *used) {
+    *used = 1;
     if (multi) return (const void *)flow_search_generic_kernel<true, false>;
+    if (timeline && gen == 2 && (R == 5 || R == 16)) {
+        *used = 2;
+        return R == 5 ? (const void *)flow_search2_kernel<5, true> : (const void *)flow_search2_kernel<16, true>;
+    }
     if (timeline) return R == 5 ? (const void *)flow_search_kernel<5, false, true> : (const void *)flow_search_generic_kernel<false, true>;
+    if (gen == 2) {
+        switch (R) {
+#define HR_RCASE(r) case r: *used = 2; return (const void *)flow_search2_kernel<r>;
+            HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
+            HR_RCASE(13) HR_RCASE(14) HR_RCASE(15) HR_RCASE(16)
+#undef HR_RCASE
+            default: break;
+        }
+    }
     switch (R) {
 #define HR_RCASE(r) case r: return (const void *)flow_search_kernel<r, false, false>;
         HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
@@ -926,8 +1047,19 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         if (pipe_join(ctx)) return 1;
     }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], st));
-    const void *kfn = ctx->banded ? (searchRadius == 5 ? (const void *)flow_search_band_kernel<5> : (const void *)flow_search_band_kernel<0>) : search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn);
-    CU(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HR_THREADS), args, 0, st));
+    int genUsed = 1;
+    const void *kfn = ctx->banded ? (searchRadius == 5 ? (const void *)flow_search_band_kernel<5> : (const void *)flow_search_band_kernel<0>) : search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn, ctx->searchGen, &genUsed);
+    const void *staged = (!ctx->banded && !ctx->multiTile && ctx->searchGen == 2 && ctx->stagedOk && ctx->stagedOn) ? staged_kernel_for(searchRadius, ctx->timelineOn) : NULL;
+    ctx->lastSearchStaged = staged != NULL;
+    if (staged) {
+        /* the packed copy this launch reads, by its physical buffer */
+        void *sargs[] = {&P, &ctx->tmapPacked[ctx->packedId[0]]};
+        ctx->lastSearchGen = 2;
+        CU(cudaLaunchCooperativeKernel(staged, dim3(grid), dim3(HR_THREADS), sargs, HR_ST_BYTES, st));
+    } else {
+        ctx->lastSearchGen = genUsed;
+        CU(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HR_THREADS), args, 0, st));
+    }
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], st));
         ctx->haveSearchT = 1;
