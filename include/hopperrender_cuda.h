@@ -235,9 +235,10 @@ int hr_get_timeline(HrContext *ctx, long long *stamps, int maxCtas);
  * still running (or is not coming back): the same array, copied without any synchronisation. */
 int hr_debug_peek_timeline(HrContext *ctx, long long *stamps, int maxCtas);
 
-/* Developer knob: which generation of the search kernel the following hr_calc_flow launches use. 2 (default):
- * csrc/hr_search2.cuh for radii 5..16 on lattices of at most one tile per SM outside band groups, csrc/hr_search.cuh
- * for everything else; 1: csrc/hr_search.cuh always. Both write the same tables, totals and offsets (same bits). */
+/* Developer knob: which generation of the search kernel the following hr_calc_flow launches use. 3 (default):
+ * csrc/hr_search3.cuh (four lattice points per thread, two CTAs per SM) for radii 5..16 on lattices of at most one tile
+ * per SM outside band groups, csrc/hr_search.cuh for everything else; 2: csrc/hr_search2.cuh (and its TMA-staged
+ * variant) under the same conditions; 1: csrc/hr_search.cuh always. All write the same tables, totals and offsets. */
 int hr_debug_set_search_generation(HrContext *ctx, int generation);
 /* ... and the generation the most recent search launch of the context actually ran (0: none yet). */
 int hr_debug_last_search_generation(const HrContext *ctx);

@@ -12,6 +12,7 @@
 #include "hr_pack.cuh"
 #include "hr_search.cuh"
 #include "hr_search2.cuh"
+#include "hr_search3.cuh"
 #include "hr_warp.cuh"
 #include "hr_warp_fast.cuh"
 
@@ -131,7 +132,7 @@ struct HrContext {
     int stagedOk;      /* tensor maps of the two packed copies exist (resolution scalar 2, driver has the encoder) */
     int stagedOn;      /* developer knob HR_SEARCH_STAGED=0 / hr_debug_set_search_staged */
     HrTensorMap tmapPacked[2]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
-    int searchGen; /* 2: hr_search2.cuh where it applies (radius 5..16, one tile per CTA, no bands / timeline), 1: hr_search.cuh always */
+    int searchGen; /* 3 (default) / 2: hr_search3.cuh / hr_search2.cuh where they apply (radius 5..16, one tile per CTA, no bands), 1: hr_search.cuh always */
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
@@ -436,8 +437,8 @@ static int create_impl(HrContext *ctx) {
     ctx->useFastWarp = !(g && g[0] == '1');
     const char *ah = getenv("HR_AHEAD");
     ctx->aheadOn = !(ah && ah[0] == '0');
-    const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 2 = hr_search2.cuh where it applies (measured: slower, profiles/r02_search_generations.txt) */
-    ctx->searchGen = (sg && sg[0] == '2') ? 2 : 1;
+    const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 1 / 2 = hr_search.cuh / hr_search2.cuh for every launch they can serve */
+    ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 3;
     const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
     ctx->stagedOn = !(ss && ss[0] == '0');
     CU(cudaDeviceSynchronize());
@@ -635,7 +636,7 @@ extern "C" int hr_set_timeline(HrContext *ctx, int enable) {
 
 extern "C" int hr_debug_set_search_generation(HrContext *ctx, int generation) {
     if (!ctx) return 1;
-    if (generation != 1 && generation != 2) return fail(ctx, "hr_debug_set_search_generation: %d is not 1 or 2", generation);
+    if (generation < 1 || generation > 3) return fail(ctx, "hr_debug_set_search_generation: %d is not 1, 2 or 3", generation);
     ctx->searchGen = generation;
     return 0;
 }
@@ -934,6 +935,17 @@ static const void *staged_kernel_for(int R, int timeline) {
 static const void *search_kernel_for(int R, int multi, int timeline, int gen, int *used) {
     *used = 1;
     if (multi) return (const void *)flow_search_generic_kernel<true, false>;
+    if (gen == 3 && R >= 5 && R <= 16 && !(timeline && R != 5)) {
+        *used = 3;
+        if (timeline) return (const void *)flow_search3_kernel<5, true>;
+        switch (R) {
+#define HR_RCASE(r) case r: return (const void *)flow_search3_kernel<r>;
+            HR_RCASE(5) HR_RCASE(6) HR_RCASE(7) HR_RCASE(8) HR_RCASE(9) HR_RCASE(10) HR_RCASE(11) HR_RCASE(12)
+            HR_RCASE(13) HR_RCASE(14) HR_RCASE(15) HR_RCASE(16)
+#undef HR_RCASE
+            default: break;
+        }
+    }
     if (timeline && gen == 2 && (R == 5 || R == 16)) {
         *used = 2;
         return R == 5 ? (const void *)flow_search2_kernel<5, true> : (const void *)flow_search2_kernel<16, true>;
@@ -1058,7 +1070,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         CU(cudaLaunchCooperativeKernel(staged, dim3(grid), dim3(HR_THREADS), sargs, HR_ST_BYTES, st));
     } else {
         ctx->lastSearchGen = genUsed;
-        CU(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HR_THREADS), args, 0, st));
+        CU(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(genUsed == 3 ? HR3_THREADS : HR_THREADS), args, 0, st));
     }
     if (ctx->profiling) {
         CU(cudaEventRecord(ctx->evK[1], st));

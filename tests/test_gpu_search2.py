@@ -1,4 +1,4 @@
-"""The two generations of the search kernel (csrc/hr_search.cuh, csrc/hr_search2.cuh) against the CPU oracle and
+"""The three generations of the search kernel (csrc/hr_search.cuh, hr_search2.cuh, hr_search3.cuh) against the CPU oracle and
 against one another: raw and blurred offsets, the winning layer of every step, the tables the blur reads — same bits.
 Geometries: 16:9 at every resolution scalar, a ragged lattice (points outside the lattice in the last tile column and
 row), clips whose motion pushes the candidates over the frame border (reflected sample addressing), every radius the
@@ -39,6 +39,7 @@ def test_generations_agree_every_radius(hr, synth, R):
     f1, f2 = c.frame(3), c.frame(4)
     first = _flow(hr, f1, f2, 1080, 1920, 1920, R, 1)
     _same(first, _flow(hr, f1, f2, 1080, 1920, 1920, R, 2, staged=False), "1080p R=%d, samples from global memory" % R)
+    _same(first, _flow(hr, f1, f2, 1080, 1920, 1920, R, 3), "1080p R=%d, four points per thread" % R)
     if R <= 8:
         _same(first, _flow(hr, f1, f2, 1080, 1920, 1920, R, 2, staged=True), "1080p R=%d, samples staged by TMA" % R)
 
@@ -49,23 +50,23 @@ def test_staged_variant_fast_motion(hr, oracle, synth, velocity):
     it (the steps that reach further read global memory): R = 5 and R = 8 against the oracle."""
     c = synth.MovingTextureClip(1920, 1080, velocity=velocity)
     f1, f2 = c.frame(1), c.frame(2)
-    for R in (5, 8):
-        got = _flow(hr, f1, f2, 1080, 1920, 1920, R, 2)
+    for R, gen in ((5, 2), (8, 2), (5, 3), (8, 3)):
+        got = _flow(hr, f1, f2, 1080, 1920, 1920, R, gen)
         o = oracle.Oracle(1080, 1920, 1920, 0)
         o.update_frame(*f1)
         o.update_frame(*f2)
         o.calc_flow(R, 8, 6)
         oraw, oblur = o.get_offsets()
-        assert np.array_equal(got[0], oraw) and np.array_equal(got[1], oblur), "velocity %s R=%d" % (velocity, R)
+        assert np.array_equal(got[0], oraw) and np.array_equal(got[1], oblur), "velocity %s R=%d generation %d" % (velocity, R, gen)
 
 
 @pytest.mark.parametrize("w,h,stride,pixfmt", [(1280, 720, 1280, 0), (854, 480, 896, 0), (480, 270, 480, 0), (1000, 562, 1024, 0),
                                                (3840, 2160, 3840, 1), (2048, 858, 2048, 0), (1918, 1080, 1920, 1)])
-@pytest.mark.parametrize("R", [5, 11, 16])
-def test_generation2_against_oracle(hr, oracle, synth, w, h, stride, pixfmt, R):
+@pytest.mark.parametrize("R,gen", [(5, 2), (11, 2), (16, 2), (5, 3), (8, 3), (11, 3), (16, 3)])
+def test_generation2_against_oracle(hr, oracle, synth, w, h, stride, pixfmt, R, gen):
     c = synth.MovingTextureClip(w, h, stride=stride, pixfmt=pixfmt)
     f1, f2 = c.frame(1), c.frame(2)
-    got = _flow(hr, f1, f2, h, stride, w, R, 2, pixfmt)
+    got = _flow(hr, f1, f2, h, stride, w, R, gen, pixfmt)
     o = oracle.Oracle(h, stride, w, pixfmt)
     o.update_frame(*f1)
     o.update_frame(*f2)
@@ -79,8 +80,8 @@ def test_generation2_noise_wrap_and_scalars(hr, oracle, synth):
     """Full-range noise: large offsets everywhere (every border warp takes the reflected path), window sums that wrap
     in 32 bits with a large deltaScalar, and the extreme bias scalars."""
     f1, f2 = synth.noise_frame(1080, 1920, 21), synth.noise_frame(1080, 1920, 22)
-    for R, dS, nS in ((5, 12, 6), (16, 8, 6), (8, 0, 0), (9, 12, 10), (13, 4, 8)):
-        got = _flow(hr, f1, f2, 1080, 1920, 1920, R, 2, 0, dS, nS)
+    for R, dS, nS, gen in ((5, 12, 6, 2), (16, 8, 6, 2), (8, 0, 0, 2), (9, 12, 10, 2), (13, 4, 8, 2), (5, 12, 6, 3), (8, 0, 0, 3), (7, 4, 8, 3), (16, 8, 6, 3), (13, 4, 8, 3)):
+        got = _flow(hr, f1, f2, 1080, 1920, 1920, R, gen, 0, dS, nS)
         o = oracle.Oracle(1080, 1920, 1920, 0)
         o.update_frame(*f1)
         o.update_frame(*f2)
@@ -98,7 +99,7 @@ def test_generation2_repeats_and_alternates(hr, synth):
     g.update_frame(*c.frame(1))
     ref = None
     for k in range(6):
-        g.set_search_generation(1 + (k & 1))
+        g.set_search_generation(1 + k % 3)
         g.calc_flow(5 if k < 4 else 16)
         cur = g.get_offsets()
         if k in (0, 4):

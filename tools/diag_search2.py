@@ -29,7 +29,7 @@ print("gen %%d%%s R %%2d: search %%6.1f us (min %%6.1f)  sha %%s" %% (g.last_sea
 w, h, pf = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080, 0)
 radii = [int(a) for a in sys.argv[4:]] or [5, 8, 16]
 for R in radii:
-    for gen, staged in ((1, 0), (2, 0), (2, 1)):
+    for gen, staged in ((1, 0), (2, 0), (2, 1), (3, 0)):
         try:
             r = subprocess.run([sys.executable, "-c", CASE % (str(ROOT), w, h, pf, R, gen, staged)], capture_output=True, text=True, timeout=40)
             print((r.stdout.strip() or r.stderr.strip()[-400:]), flush=True)

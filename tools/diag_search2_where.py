@@ -16,7 +16,9 @@ w, h, pf = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.arg
 R = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 c = synth.MovingTextureClip(w, h, pixfmt=pf)
 g = hr.HrCuda(h, w, w, pf)
-g.set_search_generation(2)
+GEN = int(os.environ.get('GEN', '2'))
+g.set_search_generation(GEN)
+g.set_search_staged(os.environ.get('STAGED', '1') == '1')
 g.set_timeline(True)
 g.update_frame(*c.frame(2)); g.update_frame(*c.frame(3))
 for _ in range(3):
