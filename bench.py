@@ -438,6 +438,10 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
     #   search = A / n,  pack = (B - A) / n,  warp = (C - B) / (number of warp launches); outputs per launch recorded
     with torch.cuda.stream(stream):
         nk = min(K, 100)
+        # the timed region above ran pipelined: its searches are launches of the third generation (two of them share the
+        # SMs); time THAT kernel here, one launch after the other (left to itself a lone launch would pick the first)
+        search_gen = 3 if (pipelined and 5 <= radius <= 16) else 1
+        g.set_search_generation(search_gen)
 
         def loop(with_pack, with_warp):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -467,6 +471,8 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
         res["kernel_ms"] = {"search": tA / nk, "pack": max(tB - tA, 0.0) / nk, "warp": max(tC - tB, 0.0) / max(1.0, nlaunch)}
         res["kernel_count"] = {"search": nk, "pack": nk, "warp": nlaunch}
         res["warp_outputs_per_launch"] = nwarps / max(1.0, nlaunch)
+        res["search_generation"] = g.last_search_generation()
+        g.set_search_generation(0)
     g.set_output_device(None, None)
 
     # ---- end-to-end through the reference-facing interface, host buffers -------------------------
@@ -682,14 +688,16 @@ def kernel_rooflines(env, res, radius):
         ach = evals / (kms["search"] * 1e-3)
         n = env.ncu.get((tag, "search"), {}) if radius == 5 else {}
         hbm_alg = 4 * lw * lh + int(1.5 * w * h) + 4 * lw * lh    # frame-2 lattice words + reachable frame-1 samples + flow out
-        blk = {"kernel": "flow_search_kernel<%d>" % radius, "bound": "int_alu", "achieved": ach / 1e9, "peak": peak_evals / 1e9, "unit": "G candidate evaluations/s",
+        gen = res.get("search_generation", 1)
+        blk = {"kernel": ("flow_search3_kernel<%d>" if gen == 3 else "flow_search_kernel<%d>") % radius, "bound": "int_alu", "achieved": ach / 1e9, "peak": peak_evals / 1e9, "unit": "G candidate evaluations/s",
                "frac": ach / peak_evals, "avg_us": kms["search"] * 1e3, "share_of_step": per_step["search"] / tot,
                "algorithmic_evaluations": evals,
                "peak_source": "hr_debug_int_peak, this run: a kernel of nothing but independent VABSDIFF4.U8.ACC chains at full occupancy = %.2f warp instructions per SM clock" % per_clk,
                "traffic": (n.get("dram__bytes_read.sum", 0.0) + n.get("dram__bytes_write.sum", 0.0)) if n else None, "traffic_source": n.get("file"),
                "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (kms["search"] * 1e-3) / 1e9, "frac": hbm_alg / (kms["search"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
                "note": ("one packed SAD per candidate evaluation is all the reference's arithmetic asks for; the launch is bound by 16 strictly dependent "
-                        "steps (tile-to-tile hand-offs, block barriers) and by the instructions around each SAD, not by the SAD pipe")}
+                        "steps (tile-to-tile hand-offs, block barriers) and by the instructions around each SAD, not by the SAD pipe; avg_us is one launch "
+                        "alone — in the pipelined device loop two launches (consecutive frame pairs) share the SMs, see config.flow_ms_per_pair_pipelined")}
         if n.get("smsp__inst_executed.sum"):
             slots = pk.get("sm_max_mhz", 1965.0) * 1e6 * 4 * res["smCount"] * (kms["search"] * 1e-3)
             blk["issue"] = {"warp_instructions_per_launch": n["smsp__inst_executed.sum"], "issue_slots_in_launch": slots, "frac": n["smsp__inst_executed.sum"] / slots,
@@ -793,9 +801,11 @@ def run_ours(args):
                        "cache": "source ring of %d frames (%d MB) and output ring exceed the 126 MB L2" % (res["nring"], res["nring"] * frame_bytes >> 20),
                        "timed_region": "the %d steps repeated %d times inside one CUDA event pair (>= %.1f s)" % (K, summ["reps"], MIN_REGION_S),
                        "flow_ms_per_pair": res["kernel_ms"]["search"],
+                       "flow_ms_per_pair_pipelined": summ["ms_per_step"] if res["pipelined"] else None,   # the search is what bounds the pipelined step
+                       "search_kernel": "generation %d (csrc/hr_search%s.cuh)" % (res.get("search_generation", 1), "3" if res.get("search_generation", 1) == 3 else ""),
                        # every delivered frame is a warp output (vf_HopperRender.c:357-375); the ones with t != 0 alone:
                        "interp_only_frames_per_s": summ["value"] * res["interp_share"],
-                       "device_loop": ("pipelined: pack || search, two search lanes, the warps of a source frame in one launch, search(k+1) || warps(k); %d source frames per C call" % res["chunk"]
+                       "device_loop": ("pipelined: pack || search, two search lanes whose launches share the SMs (two CTAs per SM), the warps of a source frame in one launch, search(k+1) || warps(k); %d source frames per C call" % res["chunk"]
                                        if res["pipelined"] else "serial"),
                        "serial_frames_per_s": (1.0 / res["serial_s_per_output"]) if res["serial_s_per_output"] else None},
             "gpu_launches": summ["gpu_launches"],

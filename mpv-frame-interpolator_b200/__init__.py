@@ -306,7 +306,7 @@ class HrCuda:
         return out
 
     def set_search_generation(self, generation):
-        """Developer knob: 3 = csrc/hr_search3.cuh where it applies (default), 2 = csrc/hr_search2.cuh, 1 = csrc/hr_search.cuh always."""
+        """Developer knob: 0 = chosen per launch (default), 3 / 2 = csrc/hr_search3.cuh / hr_search2.cuh where they apply, 1 = csrc/hr_search.cuh always."""
         self._chk(self.lib.hr_debug_set_search_generation(self.h, int(generation)))
 
     def last_search_generation(self):

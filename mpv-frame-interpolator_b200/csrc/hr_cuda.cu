@@ -132,7 +132,7 @@ struct HrContext {
     int stagedOk;      /* tensor maps of the two packed copies exist (resolution scalar 2, driver has the encoder) */
     int stagedOn;      /* developer knob HR_SEARCH_STAGED=0 / hr_debug_set_search_staged */
     HrTensorMap tmapPacked[2]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
-    int searchGen; /* 3 (default) / 2: hr_search3.cuh / hr_search2.cuh where they apply (radius 5..16, one tile per CTA, no bands), 1: hr_search.cuh always */
+    int searchGen; /* 0 (default): chosen per launch (launch_flow); 3 / 2: hr_search3.cuh / hr_search2.cuh where they apply (radius 5..16, one tile per CTA, no bands), 1: hr_search.cuh always */
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
@@ -437,8 +437,8 @@ static int create_impl(HrContext *ctx) {
     ctx->useFastWarp = !(g && g[0] == '1');
     const char *ah = getenv("HR_AHEAD");
     ctx->aheadOn = !(ah && ah[0] == '0');
-    const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 1 / 2 = hr_search.cuh / hr_search2.cuh for every launch they can serve */
-    ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 3;
+    const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 1 / 2 / 3 = that generation for every launch it can serve */
+    ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 0;
     const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
     ctx->stagedOn = !(ss && ss[0] == '0');
     CU(cudaDeviceSynchronize());
@@ -636,7 +636,7 @@ extern "C" int hr_set_timeline(HrContext *ctx, int enable) {
 
 extern "C" int hr_debug_set_search_generation(HrContext *ctx, int generation) {
     if (!ctx) return 1;
-    if (generation < 1 || generation > 3) return fail(ctx, "hr_debug_set_search_generation: %d is not 1, 2 or 3", generation);
+    if (generation < 0 || generation > 3) return fail(ctx, "hr_debug_set_search_generation: %d is not 0 (chosen per launch), 1, 2 or 3", generation);
     ctx->searchGen = generation;
     return 0;
 }
@@ -1059,9 +1059,20 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         if (pipe_join(ctx)) return 1;
     }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], st));
+    /* Which generation? Alone, a launch of the first generation is the shortest (1080p: 39 vs 42 us at R = 5, 59 vs 69 us
+     * at R = 16); two launches of the third share the SMs (two CTAs per SM), and a stream of pairs goes through 20 %
+     * faster with it. So: the third generation while the previous pair's search is still under way (device-resident
+     * streams enqueue far ahead of the GPU), the first when this launch will have the GPU to itself (the blocking call
+     * sequence of the filter). All generations write the same bits (tests/test_gpu_search2.py). */
+    int gen = ctx->searchGen;
+    if (gen == 0) {
+        gen = 1;
+        if (pl && ctx->haveSearch[ctx->flowCur] && cudaEventQuery(ctx->evSearch[ctx->flowCur]) == cudaErrorNotReady) gen = 3;
+        cudaGetLastError(); /* cudaErrorNotReady is not sticky, but leave nothing behind */
+    }
     int genUsed = 1;
-    const void *kfn = ctx->banded ? (searchRadius == 5 ? (const void *)flow_search_band_kernel<5> : (const void *)flow_search_band_kernel<0>) : search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn, ctx->searchGen, &genUsed);
-    const void *staged = (!ctx->banded && !ctx->multiTile && ctx->searchGen == 2 && ctx->stagedOk && ctx->stagedOn) ? staged_kernel_for(searchRadius, ctx->timelineOn) : NULL;
+    const void *kfn = ctx->banded ? (searchRadius == 5 ? (const void *)flow_search_band_kernel<5> : (const void *)flow_search_band_kernel<0>) : search_kernel_for(searchRadius, ctx->multiTile, ctx->timelineOn, gen, &genUsed);
+    const void *staged = (!ctx->banded && !ctx->multiTile && gen == 2 && ctx->stagedOk && ctx->stagedOn) ? staged_kernel_for(searchRadius, ctx->timelineOn) : NULL;
     ctx->lastSearchStaged = staged != NULL;
     if (staged) {
         /* the packed copy this launch reads, by its physical buffer */

@@ -107,3 +107,26 @@ def test_generation2_repeats_and_alternates(hr, synth):
         else:
             assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]), "launch %d" % k
     g.close()
+
+
+def test_generation_chosen_per_launch(hr, synth):
+    """Default policy: a launch that has the GPU to itself (blocking calls) is the first generation; while the previous
+    pair's search is still under way (pipelined, enqueued back to back) the third. Same offsets either way."""
+    c = synth.MovingTextureClip(1920, 1080)
+    g = hr.HrCuda(1080, 1920, 1920)
+    g.update_frame(*c.frame(0))
+    g.update_frame(*c.frame(1))
+    g.calc_flow(5)
+    assert g.last_search_generation() == 1
+    ref = g.get_offsets()
+    g.set_pipeline(True)
+    seen = set()
+    for _ in range(8):
+        g.calc_flow(5, blocking=False)
+        seen.add(g.last_search_generation())
+    g.synchronize()
+    assert seen <= {1, 3} and 3 in seen, seen
+    cur = g.get_offsets()
+    assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1])
+    g.set_pipeline(False)
+    g.close()
