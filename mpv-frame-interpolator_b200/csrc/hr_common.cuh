@@ -1,24 +1,28 @@
 /*
  * hr_common.cuh — shared declarations of the sm_100a device code of the HopperRender hot path
- * (hr_pack.cuh, hr_search.cuh, hr_warp.cuh).
+ * (hr_pack.cuh, hr_search*.cuh, hr_warp.cuh, hr_warp_fast.cuh).
  *
  * Written from scratch for B200; it is not a translation of the reference's OpenCL kernels
  * (video/filter/HopperRender/Kernels/*.cl) but computes the same results:
  *
- *   pack_frame_kernel      per source frame: NV12/P010 -> phase-planar packed (Y,U,V,0) words, so
+ *   pack_frame16_kernel    per source frame: NV12/P010 -> phase-planar packed (Y,U,V,0) words, so
  *                          that every delta-sum evaluation is ONE coalesced 32-bit load and ONE
  *                          VABSDIFF4.U8.ACC (replaces the three strided byte gathers of
  *                          calcDeltaSumsKernel.cl:96-98).
- *   flow_search_kernel     one persistent cooperative launch for all 2*iterations search steps
+ *   flow_search*_kernel    one persistent cooperative launch for all 2*iterations search steps
  *                          (K1 calcDeltaSumsKernel.cl:34-189 + K2 determineLowestLayerKernel.cl:2-22
  *                          + K3 adjustOffsetArrayKernel.cl:2-18) and the 8x8 flow blur
  *                          (K4 blurFlowKernel.cl:15-89); offsets are kept at window granularity.
- *   warp_blend_kernel      K5 warpFrameKernel.cl:114-182: flip lookup, bidirectional warp, blend,
- *                          levels, output modes; luma and chroma in one launch, 32-bit stores.
+ *                          Three generations with the same tables and results (hr_search.cuh,
+ *                          hr_search2.cuh, hr_search3.cuh), chosen per launch by hr_cuda.cu.
+ *   warp_fast_kernel /     K5 warpFrameKernel.cl:114-182: flip lookup, bidirectional warp, blend,
+ *   warp_generic_kernel    levels, output modes; luma and chroma (and the 2-6 outputs of a frame
+ *                          pair) in one launch, 32 / 64 / 128-bit accesses by resolution scalar.
  *
- * Compiled with -fmad=false: the warp's float arithmetic must round after every operation (the
- * reference's expressions evaluated in IEEE single precision without contraction), which is
- * what the parity tests check bit for bit.
+ * Compiled with -fmad=false: no IMPLICIT contraction. The warp's float arithmetic is the one the
+ * NVIDIA OpenCL compiler emits for the unmodified reference kernel (hr_warp.cuh): its contractions
+ * and MUFU.RCP divisions are written out explicitly, which is what makes 8-bit output bit-identical
+ * to the reference run on the same GPU (tests/test_gpu_vs_reference_opencl.py).
  */
 #pragma once
 #include <cuda_runtime.h>

@@ -27,6 +27,7 @@
 #define HR_WARP_STREAMS 3
 #define HR_FLOW_BUFS 4   /* blurred-flow ring: one being written per search lane, the rest read by warps in flight */
 #define HR_SEARCH_LANES 2
+#define HR_PACK_BUFS 3 /* packed copies in rotation: the one a search reads, the one being built, and a spare — with two, the pack of frame k has to wait for the search of pair k-1 (which still reads the buffer it overwrites) and sits on the search lanes' critical path */
 #define HR_MAX_WARP_EVENTS 8
 
 struct HrContext {
@@ -41,7 +42,9 @@ struct HrContext {
     uint8_t *frameBuf[2];          /* owned frame slots                                        */
     const void *fy[2], *fuv[2];    /* [0] previous (frame1 / sourceFrame12), [1] newest         */
     int fslot[2];                  /* which owned slot each of them uses (-1: borrowed)         */
-    uint32_t *packed[2];           /* packed copies, same order                                 */
+    uint32_t *packed[2];           /* packed copies, same order (two of the HR_PACK_BUFS buffers of packedRing) */
+    uint32_t *packedRing[HR_PACK_BUFS];
+    int packedSpare;               /* ring index of the buffer neither slot uses                  */
     uint8_t *outBuf;
     void *outY, *outUV;            /* current output planes (internal or caller's)              */
     int16_t *off, *blur;
@@ -90,11 +93,11 @@ struct HrContext {
     int pipeline;
     cudaStream_t sPack, sSearch[HR_SEARCH_LANES], sWarp[HR_WARP_STREAMS];
     cudaEvent_t evIn;                          /* main stream: the newest frame's planes are complete          */
-    cudaEvent_t evPack[2];                     /* by packed-buffer identity: its pack kernel is done           */
-    cudaEvent_t packRead[2];                   /* by packed-buffer identity: the search that read it last (not owned) */
+    cudaEvent_t evPack[HR_PACK_BUFS];                     /* by packed-buffer identity: its pack kernel is done           */
+    cudaEvent_t packRead[HR_PACK_BUFS];                   /* by packed-buffer identity: the search that read it last (not owned) */
     cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
     cudaEvent_t evWarp[HR_FLOW_BUFS][HR_MAX_WARP_EVENTS]; /* by flow buffer: the warps reading it              */
-    int nWarpEv[HR_FLOW_BUFS], haveSearch[HR_FLOW_BUFS], havePack[2], packedId[2];
+    int nWarpEv[HR_FLOW_BUFS], haveSearch[HR_FLOW_BUFS], havePack[HR_PACK_BUFS], packedId[2];
     int flowCur;                               /* flow buffer of the most recent search                        */
     int16_t *blurB[HR_FLOW_BUFS];
     uint32_t *blurXYB[HR_FLOW_BUFS];
@@ -131,7 +134,7 @@ struct HrContext {
     int lastSearchStaged; /* ... and whether it was the TMA-staged variant */
     int stagedOk;      /* tensor maps of the two packed copies exist (resolution scalar 2, driver has the encoder) */
     int stagedOn;      /* developer knob HR_SEARCH_STAGED=0 / hr_debug_set_search_staged */
-    HrTensorMap tmapPacked[2]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
+    HrTensorMap tmapPacked[HR_PACK_BUFS]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
     int searchGen; /* 0 (default): chosen per launch (launch_flow); 3 / 2: hr_search3.cuh / hr_search2.cuh where they apply (radius 5..16, one tile per CTA, no bands), 1: hr_search.cuh always */
 
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
@@ -196,7 +199,7 @@ static void pipeline_release(HrContext *ctx) {
     }
     if (ctx->evIn) cudaEventDestroy(ctx->evIn);
     ctx->evIn = NULL;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < HR_PACK_BUFS; ++b) {
         if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
         ctx->evPack[b] = NULL;
         ctx->packRead[b] = NULL;
@@ -269,8 +272,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
     if (ctx->partialL[0]) ctx->partial = ctx->partialL[0];
     cudaFree(ctx->frameBuf[0]);
     cudaFree(ctx->frameBuf[1]);
-    cudaFree(ctx->packed[0]);
-    cudaFree(ctx->packed[1]);
+    for (int b = 0; b < HR_PACK_BUFS; ++b) cudaFree(ctx->packedRing[b]);
     cudaFree(ctx->outBuf);
     cudaFree(ctx->off);
     cudaFree(ctx->blur);
@@ -298,7 +300,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
 
 /* 3-D tensor maps (words of a plane row, plane rows, phase planes) over the two packed copies, boxes of the staged
  * search (hr_search2.cuh): 60 words x 50 rows x 1 plane, out-of-range parts filled with zeros. */
-static int make_packed_tensor_maps(HrContext *ctx, uint32_t *const physical[2]) {
+static int make_packed_tensor_maps(HrContext *ctx, uint32_t *const physical[HR_PACK_BUFS]) {
     ctx->stagedOk = 0;
     if (ctx->s != HR_ST_S) return 0;
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -310,7 +312,7 @@ static int make_packed_tensor_maps(HrContext *ctx, uint32_t *const physical[2]) 
         return 0; /* no encoder: the unstaged kernels serve every launch */
     }
     static_assert(sizeof(CUtensorMap) == sizeof(HrTensorMap), "tensor map size");
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HR_PACK_BUFS; ++i) {
         const cuuint64_t dims[3] = {(cuuint64_t)ctx->planePitch, (cuuint64_t)ctx->lh, (cuuint64_t)1 << (2 * ctx->s)};
         const cuuint64_t strides[2] = {(cuuint64_t)ctx->planePitch * 4, (cuuint64_t)ctx->planeSize * 4};
         const cuuint32_t box[3] = {HR_ST_PW, HR_ST_PH, 1};
@@ -391,8 +393,10 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMalloc(&ctx->frameBuf[0], ctx->frameBytes));
     CU(cudaMalloc(&ctx->frameBuf[1], ctx->frameBytes));
     CU(cudaMalloc(&ctx->outBuf, ctx->frameBytes));
-    CU(cudaMalloc(&ctx->packed[0], ctx->packedBytes));
-    CU(cudaMalloc(&ctx->packed[1], ctx->packedBytes));
+    for (int b = 0; b < HR_PACK_BUFS; ++b) CU(cudaMalloc(&ctx->packedRing[b], ctx->packedBytes));
+    ctx->packed[0] = ctx->packedRing[0];
+    ctx->packed[1] = ctx->packedRing[1];
+    ctx->packedSpare = 2;
     CU(cudaMalloc(&ctx->off, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blurXY, ln * sizeof(uint32_t)));
@@ -401,12 +405,8 @@ static int create_impl(HrContext *ctx) {
     CU(cudaMemset(ctx->frameBuf[0], 0, ctx->frameBytes));
     CU(cudaMemset(ctx->frameBuf[1], 0, ctx->frameBytes));
     CU(cudaMemset(ctx->outBuf, 0, ctx->frameBytes));
-    CU(cudaMemset(ctx->packed[0], 0, ctx->packedBytes));
-    CU(cudaMemset(ctx->packed[1], 0, ctx->packedBytes));
-    {
-        uint32_t *const physical[2] = {ctx->packed[0], ctx->packed[1]}; /* packedId[i] = i at this point */
-        if (make_packed_tensor_maps(ctx, physical)) return 1;
-    }
+    for (int b = 0; b < HR_PACK_BUFS; ++b) CU(cudaMemset(ctx->packedRing[b], 0, ctx->packedBytes));
+    if (make_packed_tensor_maps(ctx, ctx->packedRing)) return 1;
     CU(cudaMemset(ctx->off, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blur, 0, 2 * ln * sizeof(int16_t)));
     CU(cudaMemset(ctx->blurXY, 0, ln * sizeof(uint32_t)));
@@ -420,7 +420,7 @@ static int create_impl(HrContext *ctx) {
     ctx->partialL[0] = ctx->partial;
     ctx->packedId[0] = 0;
     ctx->packedId[1] = 1;
-    ctx->deviceBytes = 3 * ctx->frameBytes + 2 * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 8 + 516;
+    ctx->deviceBytes = 3 * ctx->frameBytes + HR_PACK_BUFS * ctx->packedBytes + 4 * ln * sizeof(int16_t) + (size_t)(words + bwords) * 8 + 516;
     for (int i = 0; i < 2; ++i) {
         ctx->fy[i] = ctx->frameBuf[i];
         ctx->fuv[i] = ctx->frameBuf[i] + (size_t)ctx->H * ctx->W * ctx->bps;
@@ -730,12 +730,14 @@ static void rotate_slots(HrContext *ctx, int *freeSlot) {
     ctx->fy[0] = ctx->fy[1];
     ctx->fuv[0] = ctx->fuv[1];
     ctx->fslot[0] = ctx->fslot[1];
-    uint32_t *t = ctx->packed[0];
-    ctx->packed[0] = ctx->packed[1];
-    ctx->packed[1] = t;
+    /* the copy just built becomes the one the next search reads; the next frame is packed into the spare buffer, and
+     * the buffer the last search read becomes the spare */
     const int id = ctx->packedId[0];
     ctx->packedId[0] = ctx->packedId[1];
-    ctx->packedId[1] = id;
+    ctx->packedId[1] = ctx->packedSpare;
+    ctx->packedSpare = id;
+    ctx->packed[0] = ctx->packedRing[ctx->packedId[0]];
+    ctx->packed[1] = ctx->packedRing[ctx->packedId[1]];
 }
 
 /* ---- pipelined mode ----------------------------------------------------------------------------------- */
@@ -749,7 +751,7 @@ static int wait_warps(HrContext *ctx, cudaStream_t st, int b) {
 /* order the main stream after everything in flight on the internal streams (no host wait) */
 static int pipe_join(HrContext *ctx) {
     if (!ctx->sPack) return 0;
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < HR_PACK_BUFS; ++b)
         if (ctx->havePack[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evPack[b], 0));
     for (int b = 0; b < HR_FLOW_BUFS; ++b) {
         if (ctx->haveSearch[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evSearch[b], 0));
@@ -772,7 +774,7 @@ static int pipeline_alloc(HrContext *ctx) {
     CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
     for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
     CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
+    for (int b = 0; b < HR_PACK_BUFS; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
     for (int b = 0; b < HR_FLOW_BUFS; ++b) {
         CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
         for (int i = 0; i < HR_MAX_WARP_EVENTS; ++i) CU(cudaEventCreateWithFlags(&ctx->evWarp[b][i], cudaEventDisableTiming));
