@@ -93,6 +93,9 @@ struct HrContext {
     int pipeline;
     cudaStream_t sPack, sSearch[HR_SEARCH_LANES], sWarp[HR_WARP_STREAMS];
     cudaEvent_t evIn;                          /* main stream: the newest frame's planes are complete          */
+    cudaEvent_t evLattice;                     /* main stream: the rows of the newest frame the search reads (its lattice rows) are there */
+    int latticeFirst;                          /* this frame was uploaded lattice rows first: the search waits for evLattice, not evIn */
+    int splitUpload;                           /* developer knob HR_SPLIT_UPLOAD=0: one transfer per frame, always */
     cudaEvent_t evPack[HR_PACK_BUFS];                     /* by packed-buffer identity: its pack kernel is done           */
     cudaEvent_t packRead[HR_PACK_BUFS];                   /* by packed-buffer identity: the search that read it last (not owned) */
     cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
@@ -199,6 +202,8 @@ static void pipeline_release(HrContext *ctx) {
     }
     if (ctx->evIn) cudaEventDestroy(ctx->evIn);
     ctx->evIn = NULL;
+    if (ctx->evLattice) cudaEventDestroy(ctx->evLattice);
+    ctx->evLattice = NULL;
     for (int b = 0; b < HR_PACK_BUFS; ++b) {
         if (ctx->evPack[b]) cudaEventDestroy(ctx->evPack[b]);
         ctx->evPack[b] = NULL;
@@ -439,6 +444,8 @@ static int create_impl(HrContext *ctx) {
     ctx->aheadOn = !(ah && ah[0] == '0');
     const char *sg = getenv("HR_SEARCH_GEN"); /* developer knob: 1 / 2 / 3 = that generation for every launch it can serve */
     ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 0;
+    const char *su = getenv("HR_SPLIT_UPLOAD"); /* developer knob: 0 = never upload a frame lattice rows first */
+    ctx->splitUpload = !(su && su[0] == '0');
     const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
     ctx->stagedOn = !(ss && ss[0] == '0');
     CU(cudaDeviceSynchronize());
@@ -774,6 +781,7 @@ static int pipeline_alloc(HrContext *ctx) {
     CU(cudaStreamCreateWithPriority(&ctx->sPack, cudaStreamNonBlocking, lo));
     for (int i = 0; i < HR_WARP_STREAMS; ++i) CU(cudaStreamCreateWithPriority(&ctx->sWarp[i], cudaStreamNonBlocking, lo));
     CU(cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evLattice, cudaEventDisableTiming));
     for (int b = 0; b < HR_PACK_BUFS; ++b) CU(cudaEventCreateWithFlags(&ctx->evPack[b], cudaEventDisableTiming));
     for (int b = 0; b < HR_FLOW_BUFS; ++b) {
         CU(cudaEventCreateWithFlags(&ctx->evSearch[b], cudaEventDisableTiming));
@@ -848,28 +856,64 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     rotate_slots(ctx, &slot);
     uint8_t *dst = ctx->frameBuf[slot];
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
-    if ((const uint8_t *)uvPlane == (const uint8_t *)yPlane + ylen) {
-        /* planes of one allocation, back to back (mpv's image pool lays NV12 out like this): one transfer */
-        CU(cudaMemcpyAsync(dst, yPlane, ylen + uvlen, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    g_h2dBytes += ylen + uvlen;
     ctx->fy[1] = dst;
     ctx->fuv[1] = dst + ylen;
     ctx->fslot[1] = slot;
-    if (launch_pack(ctx)) return 1;
     ctx->framesSeen++;
     ctx->specWarp.valid = ctx->specFlow.valid = 0;
-    if (pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn) {
-        /* the search the filter asks for next, with the knobs it used last time: under way while this call waits
-         * for the upload and the caller gets round to calculateOpticalFlow */
+    ctx->latticeFirst = 0;
+    /* the search the filter asks for next, with the knobs it used last time: under way while this call waits for the
+     * upload and the caller gets round to calculateOpticalFlow */
+    const int ahead = pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn;
+    if (ahead && ctx->splitUpload && ctx->s >= 1) {
+        /* The search reads the newest frame at its lattice points only: every 2^s-th luma row and the chroma rows under
+         * them, a quarter to a third of the bytes at 1080p. Those rows go first (pitched copies), the search starts
+         * behind them and runs while the other rows are still crossing PCIe; pack and warp wait for the whole frame. */
+        const size_t rowBytes = (size_t)ctx->W * ctx->bps;
+        const uint8_t *src[2] = {(const uint8_t *)yPlane, (const uint8_t *)uvPlane};
+        uint8_t *dpl[2] = {dst, dst + ylen};
+        const int rows[2] = {ctx->H, ctx->H / 2}, stride[2] = {1 << ctx->s, (1 << ctx->s) / 2 > 1 ? (1 << ctx->s) / 2 : 1};
+        for (int pl = 0; pl < 2; ++pl) { /* first row of every group of `stride` rows */
+            const int groups = (rows[pl] + stride[pl] - 1) / stride[pl];
+            CU(cudaMemcpy2DAsync(dpl[pl], stride[pl] * rowBytes, src[pl], stride[pl] * rowBytes, rowBytes, groups, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(cudaEventRecord(ctx->evLattice, ctx->stream));
+        ctx->latticeFirst = 1;
         cudaStream_t st;
         if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
         CU(cudaEventRecord(ctx->evFlowEnd, st));
         ctx->specFlow = ctx->lastFlow;
         ctx->specFlow.frames = ctx->framesSeen;
+        for (int pl = 0; pl < 2; ++pl) { /* the other rows of every full group, then what is left of a partial last group */
+            const int full = rows[pl] / stride[pl], tail = rows[pl] - full * stride[pl];
+            if (stride[pl] > 1 && full > 0)
+                CU(cudaMemcpy2DAsync(dpl[pl] + rowBytes, stride[pl] * rowBytes, src[pl] + rowBytes, stride[pl] * rowBytes, (stride[pl] - 1) * rowBytes, full,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+            if (tail > 1) {
+                const size_t o = ((size_t)full * stride[pl] + 1) * rowBytes;
+                CU(cudaMemcpyAsync(dpl[pl] + o, src[pl] + o, (size_t)(tail - 1) * rowBytes, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        g_h2dBytes += ylen + uvlen;
+        if (launch_pack(ctx)) return 1; /* records evIn behind the last row */
+        ctx->latticeFirst = 0;          /* later launches for this frame (other knobs) wait for all of it */
+    } else {
+        if ((const uint8_t *)uvPlane == (const uint8_t *)yPlane + ylen) {
+            /* planes of one allocation, back to back (mpv's image pool lays NV12 out like this): one transfer */
+            CU(cudaMemcpyAsync(dst, yPlane, ylen + uvlen, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CU(cudaMemcpyAsync(dst, yPlane, ylen, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(dst + ylen, uvPlane, uvlen, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        g_h2dBytes += ylen + uvlen;
+        if (launch_pack(ctx)) return 1;
+        if (ahead) {
+            cudaStream_t st;
+            if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
+            CU(cudaEventRecord(ctx->evFlowEnd, st));
+            ctx->specFlow = ctx->lastFlow;
+            ctx->specFlow.frames = ctx->framesSeen;
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
     return 0;
@@ -1050,7 +1094,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     if (pl) {
         /* after: the newest frame (evIn, recorded by the update), the packed copy of the previous frame, the warps
          * that read the flow buffer about to be overwritten (those of the pair before the previous one) */
-        CU(cudaStreamWaitEvent(st, ctx->evIn, 0));
+        CU(cudaStreamWaitEvent(st, ctx->latticeFirst ? ctx->evLattice : ctx->evIn, 0));
         if (ctx->havePack[ctx->packedId[0]]) CU(cudaStreamWaitEvent(st, ctx->evPack[ctx->packedId[0]], 0));
         if (wait_warps(ctx, st, fb)) return 1;
         ctx->nWarpEv[fb] = 0;
