@@ -217,3 +217,34 @@ def test_many_frames_per_call(hr, synth):
         assert torch.equal(oa[i][0], ob[i][0]) and torch.equal(oa[i][1], ob[i][1]), "output %d" % i
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("w,h,stride,pixfmt", [(1000, 562, 1024, 0), (854, 480, 896, 0), (1918, 1080, 1920, 1), (3840, 2160, 3840, 0), (7680, 4320, 7680, 1)])
+def test_lattice_rows_first_upload(hr, synth, w, h, stride, pixfmt):
+    """updateFrame through the host layer uploads the rows the search reads first (pitched copies) and the rest behind
+    them while the search runs: ragged heights (a partial last row group), resolution scalars 1 to 4, NV12 and P010, the
+    frame in device memory and everything computed from it equal to a plain context's."""
+    clip = synth.MovingTextureClip(w, h, stride=stride, pixfmt=pixfmt)
+    dt = np.uint16 if pixfmt else np.uint8
+    plain = hr.HrCuda(h, stride, w, pixfmt)
+    ofc = hr.OpticalFlowCalc()
+    assert not hr.initOpticalFlowCalc(ofc, h, stride, w, pixfmt)
+    for k in range(4):
+        f = clip.frame(k)
+        plain.update_frame(*f)
+        assert not hr.updateFrame(ofc, list(f))
+        if k == 0:
+            continue
+        plain.calc_flow(5, 8, 6)
+        assert not hr.calculateOpticalFlow(ofc)
+        a, b = ofc.impl.get_offsets(), plain.get_offsets()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "flow of pair %d" % k
+        for t in (0.3, 0.7):
+            plain.warp(t, 2)
+            py, puv, _ = plain.download()
+            gy, guv = np.zeros((h, stride), dt), np.zeros((h // 2, stride), dt)
+            assert not hr.warpFrames(ofc, t, 2)
+            assert not hr.downloadFrame(ofc, [gy, guv])
+            assert np.array_equal(gy, py) and np.array_equal(guv, puv), "pair %d t=%g" % (k, t)
+    hr.freeOFC(ofc)
+    plain.close()
