@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Static SASS opcode histogram per kernel of the in-tree CUDA library: python profiles/sass_histogram.py > profiles/r02_sass_histogram.txt
 (cuobjdump -sass; what proves which instructions the kernels are made of: VABSDIFF4 / REDUX in the search, packed fp32
-FFMA2 / FADD2 / FMUL2 and 64/128-bit LDG / STG in the warp and pack kernels; no UTMALDG / UBLKCP (TMA), no tensor ops)."""
+FFMA2 / FADD2 / FMUL2 and 64/128-bit LDG / STG in the warp and pack kernels; UTMALDG + SYNCS (TMA on an mbarrier) in the
+staged variant of the second-generation search only; no tensor ops anywhere)."""
 import collections
 import pathlib
 import re
@@ -36,3 +37,6 @@ for blk in re.split(r"\n\s*Function : ", txt)[1:]:
             line = "  "
         line += item + "  "
     print(line)
+    note = ["%s %d" % (k, v) for k, v in sorted(ops.items()) if k.split(".")[0] in ("UTMALDG", "SYNCS", "VABSDIFF4", "REDUX", "CREDUX", "UBLKCP") or k in ("LDG.128", "STG.128")]
+    if note:
+        print("  of note: " + "  ".join(note))
