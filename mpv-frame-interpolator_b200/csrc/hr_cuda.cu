@@ -867,8 +867,10 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     const int ahead = pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn;
     if (ahead && ctx->splitUpload && ctx->s >= 1) {
         /* The search reads the newest frame at its lattice points only: every 2^s-th luma row and the chroma rows under
-         * them, a quarter to a third of the bytes at 1080p. Those rows go first (pitched copies), the search starts
-         * behind them and runs while the other rows are still crossing PCIe; pack and warp wait for the whole frame. */
+         * them, a third of the bytes at 1080p. Those rows go first (pitched copies), the search starts behind them and
+         * runs while the other rows are still crossing PCIe; pack and warp wait for the whole frame. (Measured against
+         * "lattice luma rows + the whole chroma plane first", one pitched copy fewer: the search then starts 12 us later
+         * and the caller waits for it: update + flow 107 us instead of 98 us at 1080p.) */
         const size_t rowBytes = (size_t)ctx->W * ctx->bps;
         const uint8_t *src[2] = {(const uint8_t *)yPlane, (const uint8_t *)uvPlane};
         uint8_t *dpl[2] = {dst, dst + ylen};
