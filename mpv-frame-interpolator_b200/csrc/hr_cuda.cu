@@ -25,9 +25,17 @@
 
 #define MAX_CALC_RES 270 /* video/filter/HopperRender/config.h:2 */
 #define HR_WARP_STREAMS 3
-#define HR_FLOW_BUFS 4   /* blurred-flow ring: one being written per search lane, the rest read by warps in flight */
+#ifndef HR_FLOW_BUFS
+#define HR_FLOW_BUFS 4
+#endif
+/* HR_FLOW_BUFS: blurred-flow ring: one being written per search lane, the rest read by warps in flight */
+#ifndef HR_SEARCH_LANES
 #define HR_SEARCH_LANES 2
-#define HR_PACK_BUFS 3 /* packed copies in rotation: the one a search reads, the one being built, and a spare — with two, the pack of frame k has to wait for the search of pair k-1 (which still reads the buffer it overwrites) and sits on the search lanes' critical path */
+#endif
+#ifndef HR_PACK_BUFS
+#define HR_PACK_BUFS 3
+#endif
+/* HR_PACK_BUFS: packed copies in rotation: the one a search reads, the one being built, and a spare — with two, the pack of frame k has to wait for the search of pair k-1 (which still reads the buffer it overwrites) and sits on the search lanes' critical path */
 #define HR_MAX_WARP_EVENTS 8
 
 struct HrContext {
@@ -44,7 +52,7 @@ struct HrContext {
     int fslot[2];                  /* which owned slot each of them uses (-1: borrowed)         */
     uint32_t *packed[2];           /* packed copies, same order (two of the HR_PACK_BUFS buffers of packedRing) */
     uint32_t *packedRing[HR_PACK_BUFS];
-    int packedSpare;               /* ring index of the buffer neither slot uses                  */
+    int packedSpare[HR_PACK_BUFS - 2]; /* ring indices of the buffers neither slot uses, the one to reuse next first */
     uint8_t *outBuf;
     void *outY, *outUV;            /* current output planes (internal or caller's)              */
     int16_t *off, *blur;
@@ -401,7 +409,7 @@ static int create_impl(HrContext *ctx) {
     for (int b = 0; b < HR_PACK_BUFS; ++b) CU(cudaMalloc(&ctx->packedRing[b], ctx->packedBytes));
     ctx->packed[0] = ctx->packedRing[0];
     ctx->packed[1] = ctx->packedRing[1];
-    ctx->packedSpare = 2;
+    for (int i = 0; i < HR_PACK_BUFS - 2; ++i) ctx->packedSpare[i] = 2 + i;
     CU(cudaMalloc(&ctx->off, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blur, 2 * ln * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->blurXY, ln * sizeof(uint32_t)));
@@ -741,8 +749,9 @@ static void rotate_slots(HrContext *ctx, int *freeSlot) {
      * the buffer the last search read becomes the spare */
     const int id = ctx->packedId[0];
     ctx->packedId[0] = ctx->packedId[1];
-    ctx->packedId[1] = ctx->packedSpare;
-    ctx->packedSpare = id;
+    ctx->packedId[1] = ctx->packedSpare[0];
+    for (int i = 0; i + 1 < HR_PACK_BUFS - 2; ++i) ctx->packedSpare[i] = ctx->packedSpare[i + 1];
+    ctx->packedSpare[HR_PACK_BUFS - 3] = id;
     ctx->packed[0] = ctx->packedRing[ctx->packedId[0]];
     ctx->packed[1] = ctx->packedRing[ctx->packedId[1]];
 }

@@ -27,6 +27,9 @@
 
 #define HR3_THREADS 256
 #define HR3_NWARPS 8
+#ifndef HR3_CTAS_PER_SM
+#define HR3_CTAS_PER_SM 2 /* register cap 128; 3 (cap 80: no spills up to radius 8) was measured and gains nothing */
+#endif
 
 struct Search3Shared {
     uint32_t warpTot[2][HR3_NWARPS][HR_RMAX]; /* per-warp block totals of a step, by step parity               */
@@ -42,7 +45,7 @@ struct Search3Shared {
  * search lanes of hr_cuda.cu) then run side by side on the same SMs, each filling the issue slots the other leaves
  * empty while it waits — which the first generation could not do (512 threads x 88 registers: one CTA per SM). */
 template <int RT, bool DBG = false>
-__global__ void __launch_bounds__(HR3_THREADS, 2) flow_search3_kernel(const __grid_constant__ FlowParams P) {
+__global__ void __launch_bounds__(HR3_THREADS, HR3_CTAS_PER_SM) flow_search3_kernel(const __grid_constant__ FlowParams P) {
     static_assert(RT >= 2 && RT <= HR_RMAX, "search radius");
     constexpr int ZC = RT < HR_ZCHUNK ? RT : HR_ZCHUNK; /* layers in flight at once: 4 * ZC loads per thread */
     __shared__ Search3Shared sh;
