@@ -805,7 +805,7 @@ def run_ours(args):
                        "search_kernel": "generation %d (csrc/hr_search%s.cuh)" % (res.get("search_generation", 1), "3" if res.get("search_generation", 1) == 3 else ""),
                        # every delivered frame is a warp output (vf_HopperRender.c:357-375); the ones with t != 0 alone:
                        "interp_only_frames_per_s": summ["value"] * res["interp_share"],
-                       "device_loop": ("pipelined: pack || search, two search lanes whose launches share the SMs (two CTAs per SM), the warps of a source frame in one launch, search(k+1) || warps(k); %d source frames per C call" % res["chunk"]
+                       "device_loop": ("pipelined: pack || search, three search lanes whose launches share the SMs (three CTAs per SM), the warps of a source frame in one launch, search(k+1) || warps(k); %d source frames per C call" % res["chunk"]
                                        if res["pipelined"] else "serial"),
                        "serial_frames_per_s": (1.0 / res["serial_s_per_output"]) if res["serial_s_per_output"] else None},
             "gpu_launches": summ["gpu_launches"],

@@ -236,8 +236,8 @@ int hr_get_timeline(HrContext *ctx, long long *stamps, int maxCtas);
 int hr_debug_peek_timeline(HrContext *ctx, long long *stamps, int maxCtas);
 
 /* Developer knob: which generation of the search kernel the following hr_calc_flow launches use. 0 (default): chosen
- * per launch — csrc/hr_search3.cuh (four lattice points per thread, two CTAs per SM) while the search of the previous
- * pair is still running (pipelined, device-resident streams: two launches share the SMs), csrc/hr_search.cuh when the
+ * per launch — csrc/hr_search3.cuh (four lattice points per thread, three CTAs per SM) while the search of the previous
+ * pair is still running (pipelined, device-resident streams: up to three launches share the SMs), csrc/hr_search.cuh when the
  * launch has the GPU to itself (shortest single launch); 3 / 2: csrc/hr_search3.cuh / csrc/hr_search2.cuh (and its
  * TMA-staged variant) for radii 5..16 on lattices of at most one tile per SM outside band groups, csrc/hr_search.cuh
  * for everything else; 1: csrc/hr_search.cuh always. All write the same tables, totals and offsets (same bits). */

@@ -25,17 +25,22 @@
 
 #define MAX_CALC_RES 270 /* video/filter/HopperRender/config.h:2 */
 #define HR_WARP_STREAMS 3
-#ifndef HR_FLOW_BUFS
-#define HR_FLOW_BUFS 4
-#endif
-/* HR_FLOW_BUFS: blurred-flow ring: one being written per search lane, the rest read by warps in flight */
+/* Three search lanes (measured against two, same box: 29.3 -> 25.7 us per source frame at 1080p R = 5, 48.7 -> 45.5 at
+ * R = 16, 24.5 -> 18.5 at 720p; nothing at 4K / 8K where the warps are the step): three launches of the third search
+ * generation share the SMs at three CTAs each (HR3_CTAS_PER_SM). The rings follow from the lanes: */
 #ifndef HR_SEARCH_LANES
-#define HR_SEARCH_LANES 2
+#define HR_SEARCH_LANES 3
 #endif
+#ifndef HR_FLOW_BUFS
+#define HR_FLOW_BUFS (2 * HR_SEARCH_LANES)
+#endif
+/* HR_FLOW_BUFS: blurred-flow ring: one being written per search lane, the rest read by warps in flight; a multiple of
+ * the lanes, so that a buffer is rewritten on the lane that wrote it last */
 #ifndef HR_PACK_BUFS
-#define HR_PACK_BUFS 3
+#define HR_PACK_BUFS (HR_SEARCH_LANES + 1)
 #endif
-/* HR_PACK_BUFS: packed copies in rotation: the one a search reads, the one being built, and a spare — with two, the pack of frame k has to wait for the search of pair k-1 (which still reads the buffer it overwrites) and sits on the search lanes' critical path */
+/* HR_PACK_BUFS: packed copies in rotation: one per search in flight and the one being built — with fewer, the pack of
+ * frame k has to wait for a search that still reads the buffer it overwrites and sits on the lanes' critical path */
 #define HR_MAX_WARP_EVENTS 8
 
 struct HrContext {
@@ -112,9 +117,9 @@ struct HrContext {
     int flowCur;                               /* flow buffer of the most recent search                        */
     int16_t *blurB[HR_FLOW_BUFS];
     uint32_t *blurXYB[HR_FLOW_BUFS];
-    /* two search lanes: consecutive pairs are independent (the offsets start from zero for every pair,
-     * opticalFlowCalc.c:153), so the search of pair k+1 is launched on the other lane — its own stream, window
-     * tables, tile totals and raw-offset array — and fills the launch gaps and hand-off waits of the search of pair k */
+    /* search lanes: consecutive pairs are independent (the offsets start from zero for every pair,
+     * opticalFlowCalc.c:153), so the search of pair k+1 is launched on the next lane — its own stream, window
+     * tables, tile totals and raw-offset array — and fills the launch gaps and hand-off waits of the searches before it */
     int lane;                                  /* lane of the most recent search                               */
     int16_t *offL[HR_SEARCH_LANES];
     unsigned long long *TL[HR_SEARCH_LANES], *partialL[HR_SEARCH_LANES];
@@ -1060,7 +1065,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     /* pipelined: into the flow buffer the warps of the previous pair are not reading */
     const int pl = pipe_on(ctx);
     const int fb = pl ? (ctx->flowCur + 1) % HR_FLOW_BUFS : ctx->flowCur;
-    /* the other search lane — unless a tap wants to look at this launch's tables afterwards */
+    /* the next search lane — unless a tap wants to look at this launch's tables afterwards */
     const int lane = (pl && !ctx->traceOn && !ctx->timelineOn) ? (ctx->lane + 1) % HR_SEARCH_LANES : ctx->lane;
     cudaStream_t st = pl ? ctx->sSearch[lane] : ctx->stream;
     P.T = ctx->TL[lane];
@@ -1109,16 +1114,17 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
         if (ctx->havePack[ctx->packedId[0]]) CU(cudaStreamWaitEvent(st, ctx->evPack[ctx->packedId[0]], 0));
         if (wait_warps(ctx, st, fb)) return 1;
         ctx->nWarpEv[fb] = 0;
-        /* the flow buffer was last written by a search four pairs back: on this lane (stream order) or on the
-         * other one, whose event the warps above waited for already */
+        /* the flow buffer was last written HR_FLOW_BUFS pairs back: on this lane when the ring is a multiple of the
+         * lanes (stream order); in any case after that search, even when no warp ever read its flow */
+        if (ctx->haveSearch[fb]) CU(cudaStreamWaitEvent(st, ctx->evSearch[fb], 0));
     } else if (ctx->sPack) {
         /* the pipeline was used earlier: order this launch after what is left of it */
         if (pipe_join(ctx)) return 1;
     }
     if (ctx->profiling) CU(cudaEventRecord(ctx->evK[0], st));
     /* Which generation? Alone, a launch of the first generation is the shortest (1080p: 39 vs 42 us at R = 5, 59 vs 69 us
-     * at R = 16); two launches of the third share the SMs (two CTAs per SM), and a stream of pairs goes through 20 %
-     * faster with it. So: the third generation while the previous pair's search is still under way (device-resident
+     * at R = 16); launches of the third share the SMs (three CTAs per SM, one per search lane), and a stream of pairs
+     * goes through 35 % faster with it. So: the third generation while the previous pair's search is still under way (device-resident
      * streams enqueue far ahead of the GPU), the first when this launch will have the GPU to itself (the blocking call
      * sequence of the filter). All generations write the same bits (tests/test_gpu_search2.py). */
     int gen = ctx->searchGen;

@@ -13,9 +13,11 @@
  *     side), windows 16 and up one REDUX per layer (lane z keeps layer z) and the shared-memory exchange of
  *     generation 2 between 2 / 8 warps;
  *   - twenty loads in flight per thread at R = 5, at most 32 (eight layers at a time) for the larger radii;
- *   - 256 threads x <= 128 registers: TWO CTAs fit an SM, so the searches of two consecutive frame pairs (pipelined
- *     mode, two search lanes) run side by side on the same SMs — measured 39.0 -> 31.5 us per source frame at 1080p
- *     R = 5, where one launch alone is no faster than the first generation (41.6 vs 39.9 us).
+ *   - 256 threads x <= 80 registers: THREE CTAs fit an SM, so the searches of three consecutive frame pairs (pipelined
+ *     mode, three search lanes) run side by side on the same SMs — measured 39.0 -> 31.5 us per source frame at 1080p
+ *     R = 5 with two lanes at two CTAs per SM (cap 128), 25.7 us with three at three, where one launch alone is no
+ *     faster than the first generation (41.6 vs 39.9 us). At 80 registers radii up to 11 keep everything in registers,
+ *     12..16 spill 4 to 40 bytes per thread (ptxas -v) and still gain (R = 16: 48.7 -> 45.5 us).
  * Tables, tile totals, outputs: the same words at the same places as hr_search.cuh — interchangeable launch by launch.
  *
  * Reference semantics: video/filter/HopperRender/Kernels/calcDeltaSumsKernel.cl:34-189,
@@ -28,7 +30,7 @@
 #define HR3_THREADS 256
 #define HR3_NWARPS 8
 #ifndef HR3_CTAS_PER_SM
-#define HR3_CTAS_PER_SM 2 /* register cap 128; 3 (cap 80: no spills up to radius 8) was measured and gains nothing */
+#define HR3_CTAS_PER_SM 3 /* register cap 80, one CTA per search lane of hr_cuda.cu (2: cap 128, the two-lane build) */
 #endif
 
 struct Search3Shared {
@@ -41,9 +43,9 @@ struct Search3Shared {
 };
 
 /* DBG: the stamps of hr_search2.cuh (slot 0, 1 + 4 * step + k, 100, 101, 126, 127). */
-/* Two CTAs per SM (at most 128 registers): in pipelined mode the searches of two consecutive frame pairs (the two
- * search lanes of hr_cuda.cu) then run side by side on the same SMs, each filling the issue slots the other leaves
- * empty while it waits — which the first generation could not do (512 threads x 88 registers: one CTA per SM). */
+/* Several CTAs per SM: in pipelined mode the searches of consecutive frame pairs (the search lanes of hr_cuda.cu)
+ * then run side by side on the same SMs, each filling the issue slots the others leave
+ * empty while they wait — which the first generation could not do (512 threads x 88 registers: one CTA per SM). */
 template <int RT, bool DBG = false>
 __global__ void __launch_bounds__(HR3_THREADS, HR3_CTAS_PER_SM) flow_search3_kernel(const __grid_constant__ FlowParams P) {
     static_assert(RT >= 2 && RT <= HR_RMAX, "search radius");
