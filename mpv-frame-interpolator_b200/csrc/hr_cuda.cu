@@ -13,6 +13,7 @@
 #include "hr_search.cuh"
 #include "hr_search2.cuh"
 #include "hr_search3.cuh"
+#include "hr_staging.h"
 #include "hr_warp.cuh"
 #include "hr_warp_fast.cuh"
 
@@ -153,6 +154,15 @@ struct HrContext {
     HrTensorMap tmapPacked[HR_PACK_BUFS]; /* [physical packed buffer]: 3-D view (words, rows, phase planes) for the staged search */
     int searchGen; /* 0 (default): chosen per launch (launch_flow); 3 / 2: hr_search3.cuh / hr_search2.cuh where they apply (radius 5..16, one tile per CTA, no bands), 1: hr_search.cuh always */
 
+    /* pageable host planes (hr_staging.h): a ring of pinned chunks and the threads that fill / drain it */
+    HrCopyCrew *crew;
+    int stageThreads;
+    size_t stageChunk;
+    uint8_t *stage;
+    cudaEvent_t evStage[HR_STAGE_SLOTS]; /* the copy engine is done with the slot */
+    int stageBusy[HR_STAGE_SLOTS];
+    unsigned stageNext;
+
     cudaEvent_t evUpdate, evFlowEnd, evWarpStart, evDlEnd;
     cudaEvent_t evK[6]; /* search start/end, warp start/end, pack start/end */
     int profiling;
@@ -192,6 +202,7 @@ static int sync_all(HrContext *ctx);
 static void pipeline_release(HrContext *ctx);
 static int pipe_join(HrContext *ctx);
 static int pipe_on(const HrContext *ctx);
+static void stage_release(HrContext *ctx);
 static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, cudaStream_t *stOut);
 
 extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
@@ -273,6 +284,7 @@ extern "C" int hr_destroy(HrContext *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
+    stage_release(ctx);
     /* ctx->blur / blurXY / off / T / partial alias entry [x] of their rings; entry [0] is freed below through them */
     pipeline_release(ctx);
     if (ctx->banded) { /* the flow arrays live in the arena while bands are configured: back to the context's own */
@@ -459,6 +471,11 @@ static int create_impl(HrContext *ctx) {
     ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 0;
     const char *su = getenv("HR_SPLIT_UPLOAD"); /* developer knob: 0 = never upload a frame lattice rows first */
     ctx->splitUpload = !(su && su[0] == '0');
+    const char *stt = getenv("HR_STAGE_THREADS"), *stc = getenv("HR_STAGE_CHUNK_KB"); /* hr_staging.h */
+    ctx->stageThreads = stt ? atoi(stt) : 4;
+    if (ctx->stageThreads > 16) ctx->stageThreads = 16;
+    const int chunkKb = stc ? atoi(stc) : 512;
+    ctx->stageChunk = (size_t)(chunkKb < 64 ? 64 : chunkKb > 16384 ? 16384 : chunkKb) << 10;
     const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
     ctx->stagedOn = !(ss && ss[0] == '0');
     CU(cudaDeviceSynchronize());
@@ -860,6 +877,94 @@ extern "C" int hr_pipeline_join(HrContext *ctx) {
     return pipe_join(ctx);
 }
 
+/* ---- pageable host planes through the pinned ring (hr_staging.h) ---- */
+static int host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+/* 1: the ring is there (built on first use), 0: staging is switched off, -1: error */
+static int stage_ready(HrContext *ctx) {
+    if (ctx->stageThreads < 2) return 0;
+    if (ctx->stage) return 1;
+    if (cudaHostAlloc((void **)&ctx->stage, HR_STAGE_SLOTS * ctx->stageChunk, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->stage = NULL;
+        ctx->stageThreads = 0; /* no pinned memory to be had: the driver's own path from here on */
+        return 0;
+    }
+    for (int i = 0; i < HR_STAGE_SLOTS; ++i) {
+        if (cudaEventCreateWithFlags(&ctx->evStage[i], cudaEventDisableTiming) != cudaSuccess) return fail(ctx, "staging ring: %s", cudaGetErrorString(cudaGetLastError())), -1;
+        ctx->stageBusy[i] = 0;
+    }
+    ctx->crew = new HrCopyCrew(ctx->stageThreads);
+    return 1;
+}
+static void stage_release(HrContext *ctx) {
+    delete ctx->crew;
+    ctx->crew = NULL;
+    for (int i = 0; i < HR_STAGE_SLOTS; ++i) {
+        if (ctx->evStage[i]) cudaEventDestroy(ctx->evStage[i]);
+        ctx->evStage[i] = NULL;
+    }
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = NULL;
+}
+/* host -> device: the crew fills chunk c + 1 while the copy engine moves chunk c; everything is enqueued on return */
+static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t bytes) {
+    const size_t ch = ctx->stageChunk;
+    for (size_t o = 0; o < bytes; o += ch) {
+        const size_t len = bytes - o < ch ? bytes - o : ch;
+        const int slot = ctx->stageNext++ % HR_STAGE_SLOTS;
+        if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
+        ctx->crew->copy(ctx->stage + slot * ch, hSrc + o, len);
+        CU(cudaMemcpyAsync(dDst + o, ctx->stage + slot * ch, len, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
+        ctx->stageBusy[slot] = 1;
+    }
+    return 0;
+}
+/* device -> host in two halves, so that the caller can put work between them: the first chunks are handed to the copy
+ * engine, ... */
+static int staged_d2h_begin(HrContext *ctx, const uint8_t *dSrc, size_t bytes, unsigned *base) {
+    const size_t ch = ctx->stageChunk;
+    const size_t nch = (bytes + ch - 1) / ch;
+    *base = ctx->stageNext;
+    for (size_t k = 0; k < nch && k < HR_STAGE_SLOTS; ++k) {
+        const int slot = (*base + k) % HR_STAGE_SLOTS;
+        if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
+        const size_t o = k * ch, len = bytes - o < ch ? bytes - o : ch;
+        CU(cudaMemcpyAsync(ctx->stage + slot * ch, dSrc + o, len, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
+        ctx->stageBusy[slot] = 1;
+    }
+    ctx->stageNext += (unsigned)nch;
+    return 0;
+}
+/* ... and drained in order by the crew, every emptied slot going back to the copy engine; complete on return */
+static int staged_d2h_end(HrContext *ctx, uint8_t *hDst, const uint8_t *dSrc, size_t bytes, unsigned base) {
+    const size_t ch = ctx->stageChunk;
+    const size_t nch = (bytes + ch - 1) / ch;
+    for (size_t c = 0; c < nch; ++c) {
+        const int slot = (base + c) % HR_STAGE_SLOTS;
+        const size_t o = c * ch, len = bytes - o < ch ? bytes - o : ch;
+        CU(cudaEventSynchronize(ctx->evStage[slot]));
+        ctx->crew->copy(hDst + o, ctx->stage + slot * ch, len);
+        ctx->stageBusy[slot] = 0;
+        const size_t k = c + HR_STAGE_SLOTS;
+        if (k < nch) {
+            const size_t o2 = k * ch, len2 = bytes - o2 < ch ? bytes - o2 : ch;
+            CU(cudaMemcpyAsync(ctx->stage + slot * ch, dSrc + o2, len2, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
+            ctx->stageBusy[slot] = 1;
+        }
+    }
+    return 0;
+}
+
 extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *uvPlane) {
     if (!ctx) return 1;
     if (!yPlane || !uvPlane) return fail(ctx, "hr_update_frame: NULL plane");
@@ -879,7 +984,29 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     /* the search the filter asks for next, with the knobs it used last time: under way while this call waits for the
      * upload and the caller gets round to calculateOpticalFlow */
     const int ahead = pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn;
-    if (ahead && ctx->splitUpload && ctx->s >= 1) {
+    /* pageable planes (what mpv's pool and the decoder hand the filter) go through the pinned ring */
+    int staged = 0;
+    if (ctx->stageThreads >= 2 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
+        staged = stage_ready(ctx);
+        if (staged < 0) return 1;
+    }
+    if (staged) {
+        if ((const uint8_t *)uvPlane == (const uint8_t *)yPlane + ylen) {
+            if (staged_h2d(ctx, dst, (const uint8_t *)yPlane, ylen + uvlen)) return 1;
+        } else {
+            if (staged_h2d(ctx, dst, (const uint8_t *)yPlane, ylen)) return 1;
+            if (staged_h2d(ctx, dst + ylen, (const uint8_t *)uvPlane, uvlen)) return 1;
+        }
+        g_h2dBytes += ylen + uvlen;
+        if (launch_pack(ctx)) return 1;
+        if (ahead) {
+            cudaStream_t st;
+            if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
+            CU(cudaEventRecord(ctx->evFlowEnd, st));
+            ctx->specFlow = ctx->lastFlow;
+            ctx->specFlow.frames = ctx->framesSeen;
+        }
+    } else if (ahead && ctx->splitUpload && ctx->s >= 1) {
         /* The search reads the newest frame at its lattice points only: every 2^s-th luma row and the chroma rows under
          * them, a third of the bytes at 1080p. Those rows go first (pitched copies), the search starts behind them and
          * runs while the other rows are still crossing PCIe; pack and warp wait for the whole frame. (Measured against
@@ -1577,6 +1704,37 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
     if (!yPlane || !uvPlane) return fail(ctx, "hr_download: NULL plane");
     if (bind_device(ctx)) return 1;
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
+    int staged = 0;
+    if (ctx->stageThreads >= 2 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
+        staged = stage_ready(ctx);
+        if (staged < 0) return 1;
+    }
+    if (staged) {
+        /* pageable planes: device -> pinned ring by the copy engine, ring -> the caller's planes by the crew; the
+         * next frame is warped ahead while the crew copies */
+        const int oneRun = (uint8_t *)uvPlane == (uint8_t *)yPlane + ylen && (uint8_t *)ctx->outUV == (uint8_t *)ctx->outY + ylen;
+        unsigned base = 0;
+        if (staged_d2h_begin(ctx, (const uint8_t *)ctx->outY, oneRun ? ylen + uvlen : ylen, &base)) return 1;
+        if (oneRun && ylen + uvlen <= HR_STAGE_SLOTS * ctx->stageChunk && warp_ahead(ctx)) return 1; /* the whole frame is with the copy engine already */
+        if (staged_d2h_end(ctx, (uint8_t *)yPlane, (const uint8_t *)ctx->outY, oneRun ? ylen + uvlen : ylen, base)) return 1;
+        if (!oneRun) {
+            if (staged_d2h_begin(ctx, (const uint8_t *)ctx->outUV, uvlen, &base)) return 1;
+            if (staged_d2h_end(ctx, (uint8_t *)uvPlane, (const uint8_t *)ctx->outUV, uvlen, base)) return 1;
+        }
+        g_d2hBytes += ylen + uvlen;
+        CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));
+        if (warp_ahead(ctx)) return 1; /* no-op when it was started above */
+        CU(cudaEventSynchronize(ctx->evDlEnd));
+        if (seconds) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->evWarpStart, ctx->evDlEnd) != cudaSuccess) {
+                cudaGetLastError();
+                ms = 0.f;
+            }
+            *seconds = (double)ms * 1e-3;
+        }
+        return 0;
+    }
     if ((uint8_t *)uvPlane == (uint8_t *)yPlane + ylen && (uint8_t *)ctx->outUV == (uint8_t *)ctx->outY + ylen) {
         CU(cudaMemcpyAsync(yPlane, ctx->outY, ylen + uvlen, cudaMemcpyDeviceToHost, ctx->stream)); /* back-to-back planes: one transfer */
     } else {

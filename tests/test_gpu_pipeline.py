@@ -248,3 +248,60 @@ def test_lattice_rows_first_upload(hr, synth, w, h, stride, pixfmt):
             assert np.array_equal(gy, py) and np.array_equal(guv, puv), "pair %d t=%g" % (k, t)
     hr.freeOFC(ofc)
     plain.close()
+
+
+@pytest.mark.parametrize("w,h,pixfmt,chunk_kb,threads", [(1920, 1080, 0, 512, 4), (1920, 1080, 0, 64, 3), (3840, 2160, 1, 512, 4), (1280, 720, 1, 64, 2), (1920, 1080, 0, 512, 0)])
+def test_pageable_planes_through_the_staging_ring(hr, synth, monkeypatch, w, h, pixfmt, chunk_kb, threads):
+    """Pageable planes go through the pinned ring of csrc/hr_staging.h (copying threads + copy engine, chunk by chunk;
+    small chunks make a frame go round the eight slots several times), pinned planes straight to the copy engine, and
+    with HR_STAGE_THREADS=0 pageable planes are left to the driver: the same frames come back on every road, whether
+    the two planes are one allocation or two."""
+    import torch
+
+    monkeypatch.setenv("HR_STAGE_CHUNK_KB", str(chunk_kb))
+    monkeypatch.setenv("HR_STAGE_THREADS", str(threads))
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    npdt = np.uint16 if pixfmt else np.uint8
+    tdt = torch.uint16 if pixfmt else torch.uint8
+    frames = [clip.frame(k) for k in range(4)]
+    ts = [[0.0, 0.4, 0.8], [0.2, 0.6], [0.0, 0.4, 0.8]]
+
+    def run(kind):
+        def host_pair(src=None):
+            if kind == "pinned":
+                y, uv = torch.zeros((h, w), dtype=tdt).pin_memory(), torch.zeros((h // 2, w), dtype=tdt).pin_memory()
+                if src is not None:
+                    y.numpy().view(npdt)[:] = src[0]
+                    uv.numpy().view(npdt)[:] = src[1]
+                return [y, uv]
+            if kind == "one_allocation":      # UV plane right behind the Y plane, as mpv's pool lays NV12 out
+                both = np.zeros((h + h // 2, w), npdt)
+                y, uv = both[:h], both[h:]
+            else:
+                y, uv = np.zeros((h, w), npdt), np.zeros((h // 2, w), npdt)
+            if src is not None:
+                y[:] = src[0]
+                uv[:] = src[1]
+            return [y, uv]
+
+        ofc = hr.OpticalFlowCalc()
+        assert not hr.initOpticalFlowCalc(ofc, h, w, w, pixfmt)
+        got = []
+        src = [host_pair(f) for f in frames]
+        assert not hr.updateFrame(ofc, src[0])
+        for k in range(3):
+            assert not hr.updateFrame(ofc, src[k + 1])
+            assert not hr.calculateOpticalFlow(ofc)
+            for t in ts[k]:
+                out = host_pair()
+                assert not hr.warpFrames(ofc, t, 2)
+                assert not hr.downloadFrame(ofc, out)
+                got.append([np.array(p.numpy().view(npdt) if hasattr(p, "numpy") else p) for p in out])
+        hr.freeOFC(ofc)
+        return got
+
+    want = run("pinned")
+    for kind in ("two_allocations", "one_allocation"):
+        got = run(kind)
+        for i, (a, b) in enumerate(zip(want, got)):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (kind, i)
