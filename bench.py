@@ -657,8 +657,9 @@ def host_ceiling(env, workload, frac=1.0):
     return out
 
 
-def kernel_rooflines(env, res, radius):
-    """Per-kernel roofline blocks from the by-difference kernel times of `res`."""
+def kernel_rooflines(env, res, radius, step_ms=None):
+    """Per-kernel roofline blocks from the by-difference kernel times of `res`; step_ms: the pipelined device loop's time per
+    source frame (all kernels overlapped), for the issue-slot share of the whole step."""
     pk = env.peaks
     w, h, pixfmt, _, _, _ = WORKLOADS[res["workload"]]
     bps, lw, lh = res["bps"], res["lw"], res["lh"]
@@ -697,12 +698,21 @@ def kernel_rooflines(env, res, radius):
                "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (kms["search"] * 1e-3) / 1e9, "frac": hbm_alg / (kms["search"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
                "note": ("one packed SAD per candidate evaluation is all the reference's arithmetic asks for; the launch is bound by 16 strictly dependent "
                         "steps (tile-to-tile hand-offs, block barriers) and by the instructions around each SAD, not by the SAD pipe; avg_us is one launch "
-                        "alone — in the pipelined device loop two launches (consecutive frame pairs) share the SMs, see config.flow_ms_per_pair_pipelined")}
+                        "alone — in the pipelined device loop three launches (consecutive frame pairs) share the SMs, see config.flow_ms_per_pair_pipelined and issue.pipelined_step")}
         if n.get("smsp__inst_executed.sum"):
             slots = pk.get("sm_max_mhz", 1965.0) * 1e6 * 4 * res["smCount"] * (kms["search"] * 1e-3)
             blk["issue"] = {"warp_instructions_per_launch": n["smsp__inst_executed.sum"], "issue_slots_in_launch": slots, "frac": n["smsp__inst_executed.sum"] / slots,
                             "instructions_per_evaluation": n["smsp__inst_executed.sum"] * 32 / evals,
                             "source": "smsp__inst_executed.sum of %s; 4 schedulers x SMs x max clock x measured launch time" % n.get("file")}
+            npk, nwp = env.ncu.get((tag, "pack"), {}), env.ncu.get((tag, "warp"), {})
+            if step_ms and res.get("pipelined") and npk.get("smsp__inst_executed.sum") and nwp.get("smsp__inst_executed.sum"):
+                # every kernel of a source frame: one search, one pack, the warps (the ncu summary holds a single-output launch)
+                wps = kcount["warp"] * opl / max(1, kcount["search"])
+                inst = n["smsp__inst_executed.sum"] + npk["smsp__inst_executed.sum"] + nwp["smsp__inst_executed.sum"] * wps
+                step_slots = pk.get("sm_max_mhz", 1965.0) * 1e6 * 4 * res["smCount"] * (step_ms * 1e-3)
+                blk["issue"]["pipelined_step"] = {"warp_instructions_per_source_frame": inst, "issue_slots_in_step": step_slots, "frac": inst / step_slots,
+                                                  "outputs_per_source_frame": wps,
+                                                  "note": "the searches of three consecutive pairs, the pack and the warps share the SMs in the device loop: instructions of all kernels of one source frame over the issue slots of the measured time per source frame"}
         roof["search"] = blk
     dom = max(per_step, key=per_step.get)
     return roof, dom
@@ -757,7 +767,7 @@ def run_ours(args):
             ke = 40 if "8k" in name else 100
             r = measure(env, name, ke, 5, radius, full=True)
             s = summarize(env, r, radius, ke, 5)
-            roof, dom = kernel_rooflines(env, r, radius)
+            roof, dom = kernel_rooflines(env, r, radius, s["ms_per_step"])
             ew, eh, epf, esf, edf, emode = WORKLOADS[name]
             blk = {"workload": name, "frame": "%dx%d" % (ew, eh), "mode": emode, "search_radius": radius, "steps": ke, "reps": s["reps"], "timed_region_s": s["timed_region_s"],
                    "value": s["value"], "unit": "frames/s", "ms_per_step": s["ms_per_step"],
@@ -790,7 +800,7 @@ def run_ours(args):
                            "kernels_rank0": {k: {"avg_us": v["avg_us"], "frac": v["frac"], "bound": v["bound"]} for k, v in broof.items()}}
 
     if rank == 0:
-        roof, dom = kernel_rooflines(env, res, radius)
+        roof, dom = kernel_rooflines(env, res, radius, summ["ms_per_step"])
         line = {
             "metric": "interpolated frames/s", "value": summ["value"], "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W_, "reps": summ["reps"], "timed_region_s": summ["timed_region_s"], "ms_per_step": summ["ms_per_step"],

@@ -156,6 +156,7 @@ struct HrContext {
 
     /* pageable host planes (hr_staging.h): a ring of pinned chunks and the threads that fill / drain it */
     HrCopyCrew *crew;
+    HrStagePlan *plan;
     int stageThreads;
     size_t stageChunk;
     uint8_t *stage;
@@ -474,7 +475,7 @@ static int create_impl(HrContext *ctx) {
     const char *stt = getenv("HR_STAGE_THREADS"), *stc = getenv("HR_STAGE_CHUNK_KB"); /* hr_staging.h */
     ctx->stageThreads = stt ? atoi(stt) : 4;
     if (ctx->stageThreads > 16) ctx->stageThreads = 16;
-    const int chunkKb = stc ? atoi(stc) : 512;
+    const int chunkKb = stc ? atoi(stc) : 1024;
     ctx->stageChunk = (size_t)(chunkKb < 64 ? 64 : chunkKb > 16384 ? 16384 : chunkKb) << 10;
     const char *ss = getenv("HR_SEARCH_STAGED"); /* developer knob: 0 = never the TMA-staged variant */
     ctx->stagedOn = !(ss && ss[0] == '0');
@@ -888,7 +889,7 @@ static int host_is_pageable(const void *p) {
 }
 /* 1: the ring is there (built on first use), 0: staging is switched off, -1: error */
 static int stage_ready(HrContext *ctx) {
-    if (ctx->stageThreads < 2) return 0;
+    if (ctx->stageThreads < 1) return 0;
     if (ctx->stage) return 1;
     if (cudaHostAlloc((void **)&ctx->stage, HR_STAGE_SLOTS * ctx->stageChunk, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
@@ -901,11 +902,14 @@ static int stage_ready(HrContext *ctx) {
         ctx->stageBusy[i] = 0;
     }
     ctx->crew = new HrCopyCrew(ctx->stageThreads);
+    ctx->plan = new HrStagePlan();
     return 1;
 }
 static void stage_release(HrContext *ctx) {
     delete ctx->crew;
     ctx->crew = NULL;
+    delete ctx->plan;
+    ctx->plan = NULL;
     for (int i = 0; i < HR_STAGE_SLOTS; ++i) {
         if (ctx->evStage[i]) cudaEventDestroy(ctx->evStage[i]);
         ctx->evStage[i] = NULL;
@@ -913,55 +917,91 @@ static void stage_release(HrContext *ctx) {
     if (ctx->stage) cudaFreeHost(ctx->stage);
     ctx->stage = NULL;
 }
-/* host -> device: the crew fills chunk c + 1 while the copy engine moves chunk c; everything is enqueued on return */
+/* every transfer of the crew ends in finish(), also one that a CUDA call cut short */
+struct StageTransfer {
+    HrCopyCrew *crew;
+    ~StageTransfer() { crew->finish(); }
+};
+/* host -> device: the crew fills the ring chunk by chunk, the copy engine follows it; everything is enqueued on return */
 static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t bytes) {
     const size_t ch = ctx->stageChunk;
-    for (size_t o = 0; o < bytes; o += ch) {
-        const size_t len = bytes - o < ch ? bytes - o : ch;
-        const int slot = ctx->stageNext++ % HR_STAGE_SLOTS;
+    ctx->plan->build(bytes, ch, true);
+    const size_t nch = ctx->plan->n;
+    const unsigned base = ctx->stageNext;
+    ctx->stageNext += (unsigned)nch;
+    size_t released = 0;
+    for (; released < nch && released < HR_STAGE_SLOTS; ++released) {
+        const int slot = (base + released) % HR_STAGE_SLOTS;
         if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
-        ctx->crew->copy(ctx->stage + slot * ch, hSrc + o, len);
+    }
+    ctx->crew->begin(true, (uint8_t *)hSrc, ctx->stage, ch, base, ctx->plan);
+    StageTransfer guard{ctx->crew};
+    ctx->crew->release(released);
+    for (size_t c = 0; c < nch; ++c) {
+        while (!ctx->crew->chunk_done(c)) {
+            /* a slot goes back to the crew as soon as the copy engine is through with the chunk that was in it */
+            if (released < nch && released < c + HR_STAGE_SLOTS && cudaEventQuery(ctx->evStage[(base + released) % HR_STAGE_SLOTS]) == cudaSuccess)
+                ctx->crew->release(++released);
+            else
+                HrCopyCrew::relax();
+        }
+        cudaGetLastError(); /* cudaErrorNotReady of the queries */
+        const int slot = (base + c) % HR_STAGE_SLOTS;
+        const size_t o = ctx->plan->off[c], len = ctx->plan->len[c];
         CU(cudaMemcpyAsync(dDst + o, ctx->stage + slot * ch, len, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
         ctx->stageBusy[slot] = 1;
+        if (released <= c + 1 && released < nch) { /* the crew is about to run out of slots: wait for the oldest chunk in flight */
+            CU(cudaEventSynchronize(ctx->evStage[(base + released) % HR_STAGE_SLOTS]));
+            ctx->crew->release(++released);
+        }
     }
     return 0;
 }
 /* device -> host in two halves, so that the caller can put work between them: the first chunks are handed to the copy
- * engine, ... */
-static int staged_d2h_begin(HrContext *ctx, const uint8_t *dSrc, size_t bytes, unsigned *base) {
+ * engine and the crew is told where they will land, ... */
+struct StageDown {
+    unsigned base;
+    size_t queued;
+};
+static int staged_d2h_enqueue(HrContext *ctx, const uint8_t *dSrc, const StageDown &d, size_t k) {
     const size_t ch = ctx->stageChunk;
-    const size_t nch = (bytes + ch - 1) / ch;
-    *base = ctx->stageNext;
-    for (size_t k = 0; k < nch && k < HR_STAGE_SLOTS; ++k) {
-        const int slot = (*base + k) % HR_STAGE_SLOTS;
-        if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
-        const size_t o = k * ch, len = bytes - o < ch ? bytes - o : ch;
-        CU(cudaMemcpyAsync(ctx->stage + slot * ch, dSrc + o, len, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
-        ctx->stageBusy[slot] = 1;
-    }
+    const int slot = (d.base + k) % HR_STAGE_SLOTS;
+    const size_t o = ctx->plan->off[k], len = ctx->plan->len[k];
+    CU(cudaMemcpyAsync(ctx->stage + slot * ch, dSrc + o, len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
+    ctx->stageBusy[slot] = 1;
+    return 0;
+}
+static int staged_d2h_begin(HrContext *ctx, uint8_t *hDst, const uint8_t *dSrc, size_t bytes, StageDown *d) {
+    const size_t ch = ctx->stageChunk;
+    ctx->plan->build(bytes, ch, false);
+    const size_t nch = ctx->plan->n;
+    d->base = ctx->stageNext;
     ctx->stageNext += (unsigned)nch;
+    for (d->queued = 0; d->queued < nch && d->queued < HR_STAGE_SLOTS; ++d->queued) {
+        const int slot = (d->base + d->queued) % HR_STAGE_SLOTS;
+        if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot])); /* an upload's chunk still in the slot */
+        if (staged_d2h_enqueue(ctx, dSrc, *d, d->queued)) return 1;
+    }
+    ctx->crew->begin(false, hDst, ctx->stage, ch, d->base, ctx->plan);
     return 0;
 }
 /* ... and drained in order by the crew, every emptied slot going back to the copy engine; complete on return */
-static int staged_d2h_end(HrContext *ctx, uint8_t *hDst, const uint8_t *dSrc, size_t bytes, unsigned base) {
-    const size_t ch = ctx->stageChunk;
-    const size_t nch = (bytes + ch - 1) / ch;
+static int staged_d2h_end(HrContext *ctx, const uint8_t *dSrc, StageDown *d) {
+    StageTransfer guard{ctx->crew};
+    const size_t nch = ctx->plan->n;
     for (size_t c = 0; c < nch; ++c) {
-        const int slot = (base + c) % HR_STAGE_SLOTS;
-        const size_t o = c * ch, len = bytes - o < ch ? bytes - o : ch;
-        CU(cudaEventSynchronize(ctx->evStage[slot]));
-        ctx->crew->copy(hDst + o, ctx->stage + slot * ch, len);
-        ctx->stageBusy[slot] = 0;
-        const size_t k = c + HR_STAGE_SLOTS;
-        if (k < nch) {
-            const size_t o2 = k * ch, len2 = bytes - o2 < ch ? bytes - o2 : ch;
-            CU(cudaMemcpyAsync(ctx->stage + slot * ch, dSrc + o2, len2, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
-            ctx->stageBusy[slot] = 1;
+        while (d->queued < nch && (d->queued <= c || ctx->crew->chunk_done(d->queued - HR_STAGE_SLOTS))) {
+            ctx->crew->wait_chunk(d->queued - HR_STAGE_SLOTS); /* waits only when chunk c itself has no slot yet */
+            if (staged_d2h_enqueue(ctx, dSrc, *d, d->queued)) return 1;
+            ++d->queued;
         }
+        CU(cudaEventSynchronize(ctx->evStage[(d->base + c) % HR_STAGE_SLOTS]));
+        ctx->crew->release(c + 1);
     }
+    ctx->crew->finish();
+    for (size_t c = nch > HR_STAGE_SLOTS ? nch - HR_STAGE_SLOTS : 0; c < nch; ++c) ctx->stageBusy[(d->base + c) % HR_STAGE_SLOTS] = 0;
     return 0;
 }
 
@@ -986,7 +1026,7 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     const int ahead = pipe_on(ctx) && ctx->aheadOn && ctx->lastFlow.valid && ctx->framesSeen >= 2 && !ctx->traceOn && !ctx->timelineOn;
     /* pageable planes (what mpv's pool and the decoder hand the filter) go through the pinned ring */
     int staged = 0;
-    if (ctx->stageThreads >= 2 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
+    if (ctx->stageThreads >= 1 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
         staged = stage_ready(ctx);
         if (staged < 0) return 1;
     }
@@ -1059,6 +1099,7 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
         }
     }
     CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
+    if (staged) memset(ctx->stageBusy, 0, sizeof(ctx->stageBusy)); /* the copy engine is through with every slot */
     return 0;
 }
 
@@ -1705,7 +1746,7 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
     if (bind_device(ctx)) return 1;
     const size_t ylen = (size_t)ctx->H * ctx->W * ctx->bps, uvlen = (size_t)(ctx->H / 2) * ctx->W * ctx->bps;
     int staged = 0;
-    if (ctx->stageThreads >= 2 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
+    if (ctx->stageThreads >= 1 && (host_is_pageable(yPlane) || host_is_pageable(uvPlane))) {
         staged = stage_ready(ctx);
         if (staged < 0) return 1;
     }
@@ -1713,13 +1754,15 @@ extern "C" int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *
         /* pageable planes: device -> pinned ring by the copy engine, ring -> the caller's planes by the crew; the
          * next frame is warped ahead while the crew copies */
         const int oneRun = (uint8_t *)uvPlane == (uint8_t *)yPlane + ylen && (uint8_t *)ctx->outUV == (uint8_t *)ctx->outY + ylen;
-        unsigned base = 0;
-        if (staged_d2h_begin(ctx, (const uint8_t *)ctx->outY, oneRun ? ylen + uvlen : ylen, &base)) return 1;
-        if (oneRun && ylen + uvlen <= HR_STAGE_SLOTS * ctx->stageChunk && warp_ahead(ctx)) return 1; /* the whole frame is with the copy engine already */
-        if (staged_d2h_end(ctx, (uint8_t *)yPlane, (const uint8_t *)ctx->outY, oneRun ? ylen + uvlen : ylen, base)) return 1;
+        StageDown d;
+        const size_t run = oneRun ? ylen + uvlen : ylen;
+        if (staged_d2h_begin(ctx, (uint8_t *)yPlane, (const uint8_t *)ctx->outY, run, &d)) return 1;
+        int failed = 0;
+        if (oneRun && ctx->plan->n <= HR_STAGE_SLOTS) failed = warp_ahead(ctx); /* the whole frame is with the copy engine already */
+        if (staged_d2h_end(ctx, (const uint8_t *)ctx->outY, &d) || failed) return 1;
         if (!oneRun) {
-            if (staged_d2h_begin(ctx, (const uint8_t *)ctx->outUV, uvlen, &base)) return 1;
-            if (staged_d2h_end(ctx, (uint8_t *)uvPlane, (const uint8_t *)ctx->outUV, uvlen, base)) return 1;
+            if (staged_d2h_begin(ctx, (uint8_t *)uvPlane, (const uint8_t *)ctx->outUV, uvlen, &d)) return 1;
+            if (staged_d2h_end(ctx, (const uint8_t *)ctx->outUV, &d)) return 1;
         }
         g_d2hBytes += ylen + uvlen;
         CU(cudaEventRecord(ctx->evDlEnd, ctx->stream));

@@ -10,10 +10,11 @@
  * engine moves the chunk before / after. Planes that are pinned already never come here (hr_cuda.cu asks
  * cudaPointerGetAttributes), and nothing about the results changes — the bytes only take another road.
  *
- * Knobs (environment, read at hr_create): HR_STAGE_THREADS (copying threads including the caller's, default 4;
- * 0 or 1: leave pageable planes to the driver as before), HR_STAGE_CHUNK_KB (chunk size, default 512).
+ * Knobs (environment, read at hr_create): HR_STAGE_THREADS (copying threads beside the caller's, default 4;
+ * 0: leave pageable planes to the driver as before), HR_STAGE_CHUNK_KB (chunk size, default 1024).
  */
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -21,15 +22,78 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__) && !defined(HR_STAGE_PLAIN_MEMCPY)
+#include <emmintrin.h>
+#define HR_STAGE_STREAMING 1
+#endif
 
 #define HR_STAGE_SLOTS 8
 
-/* memcpy of one range by nThreads participants (the caller is one of them). Workers spin for a short while after a job
- * — the next chunk follows within microseconds — and sleep on a condition variable when the stream pauses. */
+/* The chunks of one transfer: full-size ones, and short ones at the end that nothing overlaps — the first chunk of an
+ * upload (the copy engine has nothing to move until the crew has filled it) and the last chunk of a download (the crew
+ * has to drain it after the copy engine has gone quiet): chunk / 8, / 4, / 2 before (after) the full-size ones. */
+struct HrStagePlan {
+    std::vector<size_t> off, len;
+    size_t n = 0;
+    void build(size_t bytes, size_t chunk, bool shortFirst) {
+        len.clear();
+        size_t left = bytes, c = chunk / 8 < 65536 ? (chunk < 65536 ? chunk : 65536) : chunk / 8;
+        while (left) {
+            const size_t l = left < c ? left : c;
+            len.push_back(l);
+            left -= l;
+            if (c < chunk) c = c * 2 < chunk ? c * 2 : chunk;
+        }
+        if (!shortFirst) std::reverse(len.begin(), len.end());
+        n = len.size();
+        off.resize(n);
+        size_t o = 0;
+        for (size_t i = 0; i < n; ++i) {
+            off[i] = o;
+            o += len[i];
+        }
+    }
+};
+
+/* One participant's share of a copy. Neither side is read again by this core (the ring is read by the copy engine, the
+ * caller's plane by whoever comes next), so the stores go past the cache (MOVNTDQ: no read-for-ownership of the
+ * destination lines, a third less memory traffic than memcpy below glibc's own non-temporal threshold). */
+static inline void hr_stage_copy(uint8_t *dst, const uint8_t *src, size_t n) {
+#ifdef HR_STAGE_STREAMING
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (n < 256 + head) {
+        memcpy(dst, src, n);
+        return;
+    }
+    memcpy(dst, src, head);
+    dst += head, src += head, n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+        _mm_stream_si128((__m128i *)(dst + i), a);
+        _mm_stream_si128((__m128i *)(dst + i + 16), b);
+        _mm_stream_si128((__m128i *)(dst + i + 32), c);
+        _mm_stream_si128((__m128i *)(dst + i + 48), d);
+    }
+    _mm_sfence();
+    memcpy(dst + i, src + i, n - i);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
+/* The copying threads. A transfer is a run of chunks between one host range and the slots of the ring; chunk c may be
+ * copied once the coordinator (the calling thread, which also drives the copy engine) has released it — its slot is
+ * free (host -> device) or its bytes have arrived (device -> host). Every worker copies its share of every chunk, in
+ * order, and publishes how far it has come; nobody waits at a barrier between chunks, so the crew keeps copying while
+ * the coordinator is inside a CUDA call. Workers spin for a short while after a transfer — the next one follows within
+ * microseconds in a running stream — and sleep on a condition variable when the stream pauses. */
 class HrCopyCrew {
 public:
-    explicit HrCopyCrew(int nThreads) : n_(nThreads < 1 ? 1 : nThreads) {
-        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { run(i); });
+    explicit HrCopyCrew(int nThreads) : n_(nThreads < 1 ? 1 : nThreads > 16 ? 16 : nThreads) {
+        for (int i = 0; i < n_; ++i) progress_[i].v.store(0, std::memory_order_relaxed);
+        for (int i = 0; i < n_; ++i) workers_.emplace_back([this, i] { run(i); });
     }
     ~HrCopyCrew() {
         {
@@ -44,25 +108,38 @@ public:
     HrCopyCrew &operator=(const HrCopyCrew &) = delete;
     int threads() const { return n_; }
 
-    void copy(void *dst, const void *src, size_t bytes) {
-        if (n_ == 1 || bytes < (size_t)n_ * 16384) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        dst_ = (uint8_t *)dst;
-        src_ = (const uint8_t *)src;
-        bytes_ = bytes;
-        left_.store(n_ - 1, std::memory_order_relaxed);
+    /* toRing: chunk c of the plan, host + off[c] -> ring slot (firstSlot + c) % HR_STAGE_SLOTS; otherwise the other way
+     * round. The plan stays the caller's and must not change before finish(). */
+    void begin(bool toRing, uint8_t *host, uint8_t *ring, size_t chunk, unsigned firstSlot, const HrStagePlan *plan) {
+        toRing_ = toRing;
+        host_ = host;
+        ring_ = ring;
+        chunk_ = chunk;
+        firstSlot_ = firstSlot;
+        plan_ = plan;
+        nch_ = plan->n;
+        released_.store(0, std::memory_order_relaxed);
+        for (int i = 0; i < n_; ++i) progress_[i].v.store(0, std::memory_order_relaxed);
         gen_.fetch_add(1, std::memory_order_release);
         if (sleepers_.load(std::memory_order_acquire) > 0) {
             { std::lock_guard<std::mutex> lk(m_); }
             cv_.notify_all();
         }
-        slice(0);
-        while (left_.load(std::memory_order_acquire) > 0) relax();
     }
-
-private:
+    void release(size_t upTo) { released_.store(upTo, std::memory_order_release); }
+    bool chunk_done(size_t c) const {
+        for (int i = 0; i < n_; ++i)
+            if (progress_[i].v.load(std::memory_order_acquire) <= c) return false;
+        return true;
+    }
+    void wait_chunk(size_t c) const {
+        while (!chunk_done(c)) relax();
+    }
+    /* every transfer ends here, also a failed one: the workers must be through before the next begin */
+    void finish() {
+        release(nch_);
+        if (nch_) wait_chunk(nch_ - 1);
+    }
     static void relax() {
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
@@ -70,11 +147,8 @@ private:
         asm volatile("yield");
 #endif
     }
-    void slice(int id) {
-        const size_t per = (((bytes_ + n_ - 1) / n_) + 4095) & ~(size_t)4095;
-        const size_t o = (size_t)id * per;
-        if (o < bytes_) memcpy(dst_ + o, src_ + o, bytes_ - o < per ? bytes_ - o : per);
-    }
+
+private:
     void run(int id) {
         uint64_t seen = 0;
         for (;;) {
@@ -92,19 +166,37 @@ private:
             }
             seen = gen_.load(std::memory_order_acquire);
             if (quit_.load(std::memory_order_acquire)) return;
-            slice(id);
-            left_.fetch_sub(1, std::memory_order_release);
+            const size_t nch = nch_;
+            for (size_t c = 0; c < nch; ++c) {
+                while (released_.load(std::memory_order_acquire) <= c) relax();
+                const size_t o = plan_->off[c], len = plan_->len[c];
+                const size_t per = (((len + n_ - 1) / n_) + 4095) & ~(size_t)4095, so = (size_t)id * per;
+                if (so < len) {
+                    uint8_t *h = host_ + o + so, *r = ring_ + (size_t)((firstSlot_ + c) % HR_STAGE_SLOTS) * chunk_ + so;
+                    const size_t m = len - so < per ? len - so : per;
+                    if (toRing_) hr_stage_copy(r, h, m);
+                    else hr_stage_copy(h, r, m);
+                }
+                progress_[id].v.store(c + 1, std::memory_order_release);
+            }
         }
     }
 
+    struct alignas(64) Progress {
+        std::atomic<size_t> v;
+    };
     const int n_;
     std::vector<std::thread> workers_;
     std::atomic<uint64_t> gen_{0};
-    std::atomic<int> left_{0}, sleepers_{0};
+    std::atomic<size_t> released_{0};
+    std::atomic<int> sleepers_{0};
     std::atomic<bool> quit_{false};
     std::mutex m_;
     std::condition_variable cv_;
-    uint8_t *dst_ = nullptr;
-    const uint8_t *src_ = nullptr;
-    size_t bytes_ = 0;
+    Progress progress_[16];
+    bool toRing_ = true;
+    uint8_t *host_ = nullptr, *ring_ = nullptr;
+    size_t chunk_ = 0, nch_ = 0;
+    const HrStagePlan *plan_ = nullptr;
+    unsigned firstSlot_ = 0;
 };

@@ -250,7 +250,7 @@ def test_lattice_rows_first_upload(hr, synth, w, h, stride, pixfmt):
     plain.close()
 
 
-@pytest.mark.parametrize("w,h,pixfmt,chunk_kb,threads", [(1920, 1080, 0, 512, 4), (1920, 1080, 0, 64, 3), (3840, 2160, 1, 512, 4), (1280, 720, 1, 64, 2), (1920, 1080, 0, 512, 0)])
+@pytest.mark.parametrize("w,h,pixfmt,chunk_kb,threads", [(1920, 1080, 0, 512, 4), (1920, 1080, 0, 64, 3), (1920, 1080, 0, 128, 1), (3840, 2160, 1, 512, 4), (1280, 720, 1, 64, 2), (1920, 1080, 0, 512, 0)])
 def test_pageable_planes_through_the_staging_ring(hr, synth, monkeypatch, w, h, pixfmt, chunk_kb, threads):
     """Pageable planes go through the pinned ring of csrc/hr_staging.h (copying threads + copy engine, chunk by chunk;
     small chunks make a frame go round the eight slots several times), pinned planes straight to the copy engine, and

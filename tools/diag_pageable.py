@@ -57,6 +57,6 @@ def leg(pinned, threads, chunk):
 print("%dx%d pf=%d" % (w, h, pf))
 print("pinned planes:                 %8.0f frames/s  %5.1f GB/s over PCIe" % leg(True, 4, 512))
 print("pageable, driver's own path:   %8.0f frames/s  %5.1f GB/s" % leg(False, 0, 512))
-for threads in (2, 3, 4, 6, 8):
-    for chunk in (256, 512, 1024):
+for threads in (2, 3, 4, 6):
+    for chunk in (512, 1024, 2048):
         print("pageable, %d threads, %4d KB: %8.0f frames/s  %5.1f GB/s" % ((threads, chunk) + leg(False, threads, chunk)))
