@@ -115,6 +115,12 @@ struct HrContext {
     cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
     cudaEvent_t evWarp[HR_FLOW_BUFS][HR_MAX_WARP_EVENTS]; /* by flow buffer: the warps reading it              */
     int nWarpEv[HR_FLOW_BUFS], haveSearch[HR_FLOW_BUFS], havePack[HR_PACK_BUFS], packedId[2];
+    /* Every record of the events above takes a serial number. pipe_join orders the main stream after all of them; once
+     * the host has waited for the main stream behind such a join, everything up to the join's number is over, and the
+     * next join leaves those events out (a blocking update used to spend ~15 us of stream waits on work long finished
+     * before its upload could start). */
+    unsigned long long evSeq, joinedSeq, doneSeq;
+    unsigned long long packSeq[HR_PACK_BUFS], searchSeq[HR_FLOW_BUFS], warpSeq[HR_FLOW_BUFS][HR_MAX_WARP_EVENTS];
     int flowCur;                               /* flow buffer of the most recent search                        */
     int16_t *blurB[HR_FLOW_BUFS];
     uint32_t *blurXYB[HR_FLOW_BUFS];
@@ -754,6 +760,7 @@ static int launch_pack(HrContext *ctx) {
     }
     if (ctx->sPack) {
         CU(cudaEventRecord(ctx->evPack[id], st));
+        ctx->packSeq[id] = ++ctx->evSeq;
         ctx->havePack[id] = 1;
     }
     ctx->launches++;
@@ -790,17 +797,23 @@ static int wait_warps(HrContext *ctx, cudaStream_t st, int b) {
 /* order the main stream after everything in flight on the internal streams (no host wait) */
 static int pipe_join(HrContext *ctx) {
     if (!ctx->sPack) return 0;
+    const unsigned long long done = ctx->doneSeq;
     for (int b = 0; b < HR_PACK_BUFS; ++b)
-        if (ctx->havePack[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evPack[b], 0));
+        if (ctx->havePack[b] && ctx->packSeq[b] > done) CU(cudaStreamWaitEvent(ctx->stream, ctx->evPack[b], 0));
     for (int b = 0; b < HR_FLOW_BUFS; ++b) {
-        if (ctx->haveSearch[b]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evSearch[b], 0));
-        if (wait_warps(ctx, ctx->stream, b)) return 1;
+        if (ctx->haveSearch[b] && ctx->searchSeq[b] > done) CU(cudaStreamWaitEvent(ctx->stream, ctx->evSearch[b], 0));
+        for (int i = 0; i < ctx->nWarpEv[b]; ++i)
+            if (ctx->warpSeq[b][i] > done) CU(cudaStreamWaitEvent(ctx->stream, ctx->evWarp[b][i], 0));
     }
+    ctx->joinedSeq = ctx->evSeq;
     return 0;
 }
+/* the host has waited for the main stream: what the last join ordered in front of it is over */
+static void joined_work_is_done(HrContext *ctx) { ctx->doneSeq = ctx->joinedSeq; }
 static int sync_all(HrContext *ctx) {
     if (pipe_join(ctx)) return 1;
     CU(cudaStreamSynchronize(ctx->stream));
+    joined_work_is_done(ctx);
     return 0;
 }
 
@@ -1099,6 +1112,7 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
         }
     }
     CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
+    joined_work_is_done(ctx);                /* the join at the top of this call */
     if (staged) memset(ctx->stageBusy, 0, sizeof(ctx->stageBusy)); /* the copy engine is through with every slot */
     return 0;
 }
@@ -1331,6 +1345,7 @@ static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int ne
     }
     if (ctx->sPack) {
         CU(cudaEventRecord(ctx->evSearch[fb], st));
+        ctx->searchSeq[fb] = ++ctx->evSeq;
         ctx->haveSearch[fb] = 1;
         ctx->packRead[ctx->packedId[0]] = ctx->evSearch[fb];
     }
@@ -1601,6 +1616,7 @@ static int launch_warp(HrContext *ctx, int n, const float *ts, void *const *outY
             if (wait_warps(ctx, st, fb)) return 1;
             ctx->nWarpEv[fb] = 0;
         }
+        ctx->warpSeq[fb][ctx->nWarpEv[fb]] = ++ctx->evSeq;
         CU(cudaEventRecord(ctx->evWarp[fb][ctx->nWarpEv[fb]++], st));
     }
     return 0;
