@@ -28,7 +28,8 @@
 #define HR_WARP_STREAMS 3
 /* Three search lanes (measured against two, same box: 29.3 -> 25.7 us per source frame at 1080p R = 5, 48.7 -> 45.5 at
  * R = 16, 24.5 -> 18.5 at 720p; nothing at 4K / 8K where the warps are the step): three launches of the third search
- * generation share the SMs at three CTAs each (HR3_CTAS_PER_SM). The rings follow from the lanes: */
+ * generation share the SMs at three CTAs each (HR3_CTAS_PER_SM); four lanes at four CTAs (64 registers) measured the same
+ * at R = 5 and slower from R = 8 on. The rings follow from the lanes: */
 #ifndef HR_SEARCH_LANES
 #define HR_SEARCH_LANES 3
 #endif
