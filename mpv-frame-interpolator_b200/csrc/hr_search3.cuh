@@ -46,8 +46,13 @@ struct Search3Shared {
 /* Several CTAs per SM: in pipelined mode the searches of consecutive frame pairs (the search lanes of hr_cuda.cu)
  * then run side by side on the same SMs, each filling the issue slots the others leave
  * empty while they wait — which the first generation could not do (512 threads x 88 registers: one CTA per SM). */
+#ifdef HR3_MAXNREG
+#define HR3_BOUNDS __maxnreg__(HR3_MAXNREG)
+#else
+#define HR3_BOUNDS __launch_bounds__(HR3_THREADS, HR3_CTAS_PER_SM)
+#endif
 template <int RT, bool DBG = false>
-__global__ void __launch_bounds__(HR3_THREADS, HR3_CTAS_PER_SM) flow_search3_kernel(const __grid_constant__ FlowParams P) {
+__global__ void HR3_BOUNDS flow_search3_kernel(const __grid_constant__ FlowParams P) {
     static_assert(RT >= 2 && RT <= HR_RMAX, "search radius");
     constexpr int ZC = RT < HR_ZCHUNK ? RT : HR_ZCHUNK; /* layers in flight at once: 4 * ZC loads per thread */
     __shared__ Search3Shared sh;
