@@ -224,6 +224,11 @@ int hr_debug_rcp_table(float *out, int n);
  * evalsPerSecond = thread-level packed SADs per second over the whole GPU (CUDA events), warpInstrPerClkPerSm = the
  * same as warp instructions per SM clock. Either pointer may be NULL. Blocking. */
 int hr_debug_int_peak(int device, double *evalsPerSecond, double *warpInstrPerClkPerSm);
+/* Developer tap (host only, no context, no GPU): the predictor of the filter's next blending scalar
+ * (csrc/hr_pacing_predict.h; the pacing arithmetic of vf_HopperRender.c:371-374,481 seen through warpFrames' float
+ * argument) fed with n scalars in call order. predicted[i] / nextFrame[i] = its guess for scalars[i], made after
+ * scalars[0 .. i-1], and whether it expected a new source frame first; have[i] = 0: no guess. */
+int hr_debug_predict_pacing(const float *scalars, int n, float *predicted, int *nextFrame, int *have);
 
 /* Developer tap: SM-clock stamps taken by thread 0 of every search CTA at fixed points of the launch
  * (step start, layers reduced, window published / complete, level done, search done, blur done).

@@ -82,6 +82,7 @@ ABI = {
     "hr_get_step_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hr_debug_rcp_table": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_debug_int_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hr_debug_predict_pacing": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hr_debug_set_search_generation": (C.c_int, [C.c_void_p, C.c_int]),
     "hr_debug_last_search_generation": (C.c_int, [C.c_void_p]),
     "hr_debug_set_search_staged": (C.c_int, [C.c_void_p, C.c_int]),
@@ -163,6 +164,17 @@ def debug_int_peak(device=-1):
     if load_library().hr_debug_int_peak(int(device), C.byref(a), C.byref(b)):
         raise HrError(load_library().hr_last_error(None).decode())
     return a.value, b.value
+
+
+def debug_predict_pacing(scalars):
+    """The library's guess for every blending scalar of a call sequence, made from the scalars before it (developer tap,
+    host only): list of (predicted float32, expects_new_source_frame, has_guess)."""
+    n = len(scalars)
+    ts = (C.c_float * max(1, n))(*[float(t) for t in scalars])
+    pred, nf, have = (C.c_float * max(1, n))(), (C.c_int * max(1, n))(), (C.c_int * max(1, n))()
+    if load_library().hr_debug_predict_pacing(ts, n, pred, nf, have):
+        raise HrError("hr_debug_predict_pacing failed")
+    return [(np.float32(pred[i]), bool(nf[i]), bool(have[i])) for i in range(n)]
 
 
 class HrCuda:

@@ -14,6 +14,7 @@
 #include "hr_search2.cuh"
 #include "hr_search3.cuh"
 #include "hr_staging.h"
+#include "hr_pacing_predict.h"
 #include "hr_warp.cuh"
 #include "hr_warp_fast.cuh"
 
@@ -153,6 +154,11 @@ struct HrContext {
     unsigned long long flowSerial[HR_FLOW_BUFS], colourSerial[HR_FLOW_BUFS]; /* content stamps: flow buffer / its colour table */
     unsigned long long flowStamp;
     float lastT, lastDelta, lastBlack, lastWhite;
+    HrPacingPredictor *pace; /* the filter's pacing arithmetic followed from the blending scalars it asks for (hr_pacing_predict.h) */
+    struct FirstAhead {      /* hr_download's guess when the next output belongs to the next source frame: warped from hr_update_frame */
+        int valid, frames;
+        float t;
+    } firstAhead;
     int lastWarpFrames, lastMode, aheadOn;
     int lastSearchGen; /* generation the most recent search launch ran */
     int lastSearchStaged; /* ... and whether it was the TMA-staged variant */
@@ -211,6 +217,7 @@ static void pipeline_release(HrContext *ctx);
 static int pipe_join(HrContext *ctx);
 static int pipe_on(const HrContext *ctx);
 static void stage_release(HrContext *ctx);
+static int warp_ahead_first(HrContext *ctx);
 static int launch_flow(HrContext *ctx, int searchRadius, int deltaScalar, int neighborBiasScalar, cudaStream_t *stOut);
 
 extern "C" int hr_abi_version(void) { return HR_ABI_VERSION; }
@@ -293,6 +300,8 @@ extern "C" int hr_destroy(HrContext *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
     stage_release(ctx);
+    delete ctx->pace;
+    ctx->pace = NULL;
     /* ctx->blur / blurXY / off / T / partial alias entry [x] of their rings; entry [0] is freed below through them */
     pipeline_release(ctx);
     if (ctx->banded) { /* the flow arrays live in the arena while bands are configured: back to the context's own */
@@ -501,6 +510,10 @@ extern "C" int hr_create(HrContext **out, int frameHeight, int frameWidth, int a
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(NULL, "hr_create: cudaGetDevice failed");
     if (device >= ndev) return fail(NULL, "hr_create: device %d out of range (%d devices)", device, ndev);
     HrContext *ctx = (HrContext *)calloc(1, sizeof(HrContext));
+    if (ctx) {
+        ctx->pace = new HrPacingPredictor;
+        ctx->pace->reset();
+    }
     if (!ctx) return fail(NULL, "hr_create: out of host memory");
     ctx->H = frameHeight;
     ctx->W = frameWidth;
@@ -617,6 +630,21 @@ __global__ void __launch_bounds__(1024, 2) int_peak_kernel(uint32_t *out, int it
 /* Developer tap: packed-SAD issue rate of `device` (< 0: current). evalsPerSecond = thread-level VABSDIFF4.U8.ACC per
  * second over the whole GPU by CUDA events (= candidate evaluations per second if the search did nothing but its
  * SADs); warpInstrPerClkPerSm from the SM clock counter of the slowest CTA. Either pointer may be NULL. */
+extern "C" int hr_debug_predict_pacing(const float *scalars, int n, float *predicted, int *nextFrame, int *have) {
+    if (!scalars || !predicted || !nextFrame || !have || n < 0) return 1;
+    HrPacingPredictor p;
+    p.reset();
+    for (int i = 0; i < n; ++i) {
+        bool nf = false;
+        float t = 0.0f;
+        have[i] = p.predict(&t, &nf) ? 1 : 0;
+        predicted[i] = t;
+        nextFrame[i] = nf ? 1 : 0;
+        p.observe(scalars[i]);
+    }
+    return 0;
+}
+
 extern "C" int hr_debug_int_peak(int device, double *evalsPerSecond, double *warpInstrPerClkPerSm) {
     HrContext *ctx = NULL;
     if (device < 0) CU(cudaGetDevice(&device));
@@ -1112,6 +1140,7 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
             ctx->specFlow.frames = ctx->framesSeen;
         }
     }
+    if (warp_ahead_first(ctx)) return 1;
     CU(cudaStreamSynchronize(ctx->stream)); /* the reference's writes are blocking (CL_TRUE) */
     joined_work_is_done(ctx);                /* the join at the top of this call */
     if (staged) memset(ctx->stageBusy, 0, sizeof(ctx->stageBusy)); /* the copy engine is through with every slot */
@@ -1364,12 +1393,13 @@ extern "C" int hr_calc_flow(HrContext *ctx, int searchRadius, int deltaScalar, i
         return fail(ctx, "hr_calc_flow: search radius %d needs a larger halo than the bands were configured for (hr_band_set_max_radius: %d)", searchRadius, ctx->bandMaxRadius);
     if (bind_device(ctx)) return 1;
     const int pl = pipe_on(ctx);
-    ctx->specWarp.valid = 0; /* a new flow: whatever was warped ahead is void */
     if (ctx->specFlow.valid && ctx->specFlow.frames == ctx->framesSeen && ctx->specFlow.R == searchRadius && ctx->specFlow.dS == deltaScalar &&
         ctx->specFlow.nS == neighborBiasScalar) {
-        /* hr_update_frame launched exactly this search already (same frame pair, same knobs): nothing to enqueue */
+        /* hr_update_frame launched exactly this search already (same frame pair, same knobs): nothing to enqueue, and
+         * the pair's first output, if it was warped ahead behind that search, stands */
         ctx->specFlow.valid = 0;
     } else {
+        ctx->specWarp.valid = 0; /* a new flow: whatever was warped ahead is void */
         ctx->specFlow.valid = 0;
         cudaStream_t st;
         if (launch_flow(ctx, searchRadius, deltaScalar, neighborBiasScalar, &st)) return 1;
@@ -1649,6 +1679,7 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
         /* history for hr_download's guess of the next blending scalar (vf_HopperRender.c:371-374: t advances by a
          * constant ratio within a source frame) */
         if (ctx->lastWarpFrames == ctx->framesSeen && t > ctx->lastT) ctx->lastDelta = t - ctx->lastT;
+        if (!(ctx->lastWarpFrames == ctx->framesSeen && memcmp(&t, &ctx->lastT, sizeof(float)) == 0)) ctx->pace->observe(t); /* (the same frame warped again, another mode: not an output of the pacing) */
         ctx->lastT = t;
         ctx->lastWarpFrames = ctx->framesSeen;
         ctx->lastMode = mode;
@@ -1674,11 +1705,7 @@ extern "C" int hr_warp(HrContext *ctx, float t, int mode, float black, float whi
 }
 
 /* hr_download, after its copy has been enqueued: warp the frame the pacing will most likely ask for next */
-static int warp_ahead(HrContext *ctx) {
-    if (!pipe_on(ctx) || !ctx->aheadOn || ctx->outY != ctx->outBuf || !ctx->outBuf2 || ctx->specWarp.valid) return 0;
-    if (!(ctx->lastDelta > 0.0f) || ctx->lastWarpFrames != ctx->framesSeen) return 0;
-    const float tp = ctx->lastT + ctx->lastDelta;
-    if (!(tp < 1.0f)) return 0; /* the next source frame comes first */
+static int warp_ahead_launch(HrContext *ctx, float tp) {
     const int fb = ctx->flowCur;
     void *keepY = ctx->outY, *keepUV = ctx->outUV;
     ctx->outY = ctx->outBuf2;
@@ -1696,6 +1723,31 @@ static int warp_ahead(HrContext *ctx) {
     ctx->specWarp.epoch = ctx->epoch;
     ctx->specWarp.done = ctx->evWarp[fb][ctx->nWarpEv[fb] - 1];
     return 0;
+}
+static int warp_ahead(HrContext *ctx) {
+    if (!pipe_on(ctx) || !ctx->aheadOn || ctx->outY != ctx->outBuf || !ctx->outBuf2 || ctx->specWarp.valid) return 0;
+    if (ctx->lastWarpFrames != ctx->framesSeen) return 0;
+    float tp = 0.0f;
+    bool nextFrame = false;
+    ctx->firstAhead.valid = 0;
+    if (!ctx->pace->predict(&tp, &nextFrame)) return 0;
+    if (nextFrame) { /* the next source frame comes first: its update warps this one behind the search it starts */
+        ctx->firstAhead.valid = 1;
+        ctx->firstAhead.frames = ctx->framesSeen + 1;
+        ctx->firstAhead.t = tp;
+        return 0;
+    }
+    return warp_ahead_launch(ctx, tp);
+}
+/* hr_update_frame, after it has started the new pair's search and the pack: the pair's first output, as hr_download
+ * guessed it, behind the search and the last row of the upload */
+static int warp_ahead_first(HrContext *ctx) {
+    const int want = ctx->firstAhead.valid && ctx->firstAhead.frames == ctx->framesSeen;
+    ctx->firstAhead.valid = 0;
+    if (!want || !pipe_on(ctx) || !ctx->aheadOn || ctx->outY != ctx->outBuf || !ctx->outBuf2 || ctx->specWarp.valid) return 0;
+    if (!ctx->specFlow.valid || ctx->specFlow.frames != ctx->framesSeen) return 0; /* no search was started ahead */
+    CU(cudaStreamWaitEvent(ctx->sWarp[0], ctx->evIn, 0)); /* the search may have started behind the lattice rows alone */
+    return warp_ahead_launch(ctx, ctx->firstAhead.t);
 }
 
 /* One source frame of a device-resident stream in ONE call: update + flow + nWarps warps, each into its own
