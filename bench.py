@@ -10,7 +10,8 @@ One "step" = one source frame of a stream through the hot path:
                `reps` times inside ONE event pair so that the timed region lasts >= 0.5 s whatever K is.
   e2e          the same metric through the reference-facing C host layer with pinned HOST planes: updateFrame (H2D) /
                calculateOpticalFlow / warpFrames / downloadFrame (D2H) per output, every call blocking.
-  e2e_pageable the same with malloc'd planes (what mpv's image pool hands a filter); e2e_zero_copy: device planes in,
+  e2e_pageable the same with malloc'd planes (what mpv's image pool hands a filter); e2e_pinned_pool: pageable source
+  frames, the output image from allocHostPlanes (the filter's pool with patches/0004); e2e_zero_copy: device planes in,
                device planes out (the IMGFMT_CUDA hand-off) — no PCIe crossing at all.
   host_ceiling what the PCIe legs alone allow (one frame up, the step's frames down, no kernels), serial and duplex.
   roofline     dominant kernel of the step by device time. The search is integer-ALU work: candidate evaluations/s
@@ -531,8 +532,17 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
         else:
             lib = hr.load_ofc_library()
 
-            def replay_leg(pinned):
+            def replay_leg(pinned, pool_out=False):
                 hring, hout = host_ring(pinned)
+                pool = None
+                if pool_out:        # the output image as the filter's pool allocates it with patches/0004 (allocHostPlanes)
+                    nbytes = (hout[0].numel() + hout[1].numel()) * hout[0].element_size()
+                    pool = lib.allocHostPlanes(nbytes + 64)
+                    if not pool:
+                        raise SystemExit("allocHostPlanes failed")
+                    flat = np.ctypeslib.as_array(ctypes.cast(pool, ctypes.POINTER(ctypes.c_uint8)), (nbytes,)).view(base[0][0].dtype)
+                    ny = hout[0].numel()
+                    hout = (flat[:ny].reshape(tuple(hout[0].shape)), flat[ny:].reshape(tuple(hout[1].shape)))
                 cofc = hr.COpticalFlowCalc()
                 cofc.pixelFormat = pixfmt
                 cofc.cudaDevice = local + 1
@@ -549,12 +559,17 @@ def measure(env, workload, K, W, radius, with_e2e=True, serial_only=False, bande
                 eouts = hr.replay_stream_c(cofc, hring, 5, ets[5:5 + Ke], mode, hout)
                 edt = time.perf_counter() - t0
                 lib.freeOFC(ctypes.byref(cofc))
+                if pool:
+                    lib.freeHostPlanes(None, pool)
                 return {"outs": eouts, "secs": edt, "steps": Ke}
 
             res["e2e"] = dict(replay_leg(True), api=("libhopperrender_ofc.so: initOpticalFlowCalc, then hrReplayStream = updateFrame/calculateOpticalFlow/"
                                                      "warpFrames/downloadFrame in the filter's order, pinned host planes, every call blocking like the reference's"))
             if full:
                 res["e2e_pageable"] = dict(replay_leg(False), api="the same calls with malloc'd (pageable) planes, as mpv's image pool delivers them")
+                res["e2e_pinned_pool"] = dict(replay_leg(False, pool_out=True),
+                                              api=("the same calls, pageable source frames (a software decoder's) and the output image from allocHostPlanes: "
+                                                   "the filter's output pool with patches/0004"))
                 res["e2e_zero_copy"] = zero_copy_leg(env, g, ring, out_ring, ets, nring, radius, mode)
     if banded:
         lo, hi, _ = g.band_halo()
@@ -727,7 +742,7 @@ def summarize(env, res, radius, K, W):
         tot_outs //= world
     out = {"value": tot_outs / max_s, "ms_per_step": max_s * 1e3 / (K * res["reps"]), "reps": res["reps"], "timed_region_s": max_s,
            "gpu_launches": int(launches), "outs": tot_outs}
-    for key in ("e2e", "e2e_pageable", "e2e_zero_copy"):
+    for key in ("e2e", "e2e_pageable", "e2e_pinned_pool", "e2e_zero_copy"):
         if key in res:
             e_outs, e_dt = env.reduce(res[key]["outs"], res[key]["secs"])
             if banded:
@@ -773,7 +788,7 @@ def run_ours(args):
                    "value": s["value"], "unit": "frames/s", "ms_per_step": s["ms_per_step"],
                    "serial_frames_per_s": (1.0 / r["serial_s_per_output"]) if r["serial_s_per_output"] else None,
                    "interp_only_frames_per_s": s["value"] * r["interp_share"], "kernels": roof, "dominant_kernel": dom}
-            for key in ("e2e", "e2e_pageable", "e2e_zero_copy"):
+            for key in ("e2e", "e2e_pageable", "e2e_pinned_pool", "e2e_zero_copy"):
                 if key in s:
                     blk[key] = {"value": s[key]["value"], "unit": "frames/s", "steps": s[key]["steps"]}
             if "e2e" in s:
@@ -829,7 +844,7 @@ def run_ours(args):
             line["e2e"] = {"value": summ["e2e"]["value"], "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes * band_frac),
                            "d2h_bytes_per_step": int(frame_bytes * band_frac * dfps / sfps),
                            "steps": summ["e2e"]["steps"], "api": summ["e2e"]["api"], "host_cpus_near_gpu": env.numa_cpus}
-            for key in ("e2e_pageable", "e2e_zero_copy"):
+            for key in ("e2e_pageable", "e2e_pinned_pool", "e2e_zero_copy"):
                 if key in summ:
                     line[key] = {"value": summ[key]["value"], "unit": "frames/s", "steps": summ[key]["steps"], "api": summ[key]["api"]}
         if ceiling:

@@ -152,6 +152,18 @@ int hr_download(HrContext *ctx, void *yPlane, void *uvPlane, double *seconds);
 int hr_finish(HrContext *ctx, double *seconds);
 int hr_debug_host_transfer_bytes(unsigned long long *h2d, unsigned long long *d2h);
 
+/* Page-locked host memory for the frames a filter allocates itself (SURVEY.md §8f N1 "pinned staging"; no reference
+ * counterpart — the reference's output images come from mp_image_pool's default allocator, HR/vf_HopperRender.c:385,699,
+ * i.e. pageable memory the driver has to stage). A filter hands hr_host_alloc / hr_host_free to
+ * mp_image_pool_set_allocator (video/mp_image_pool.h:20-22, through mp_image_from_buffer, video/mp_image.h:139-142:
+ * patches/0004): hr_download then copies straight into the image, 2.5 of the 3.5 transfers per source frame at 24->60.
+ * No context is needed (the memory is portable across devices); hr_host_free may be called from any thread.
+ * hr_debug_host_pointer_kind: 0 = pageable host memory (goes through the pinned ring of hr_staging.h), 1 = page-locked
+ * host memory, 2 = device or managed memory. */
+int hr_host_alloc(void **out, size_t bytes);
+int hr_host_free(void *p);
+int hr_debug_host_pointer_kind(const void *p);
+
 /* Device-side view of the output frame (zero-copy hand-off to a CUDA VO; N2). Valid until the
  * next hr_warp on this context; ordered on the context's stream. */
 int hr_get_output_device(HrContext *ctx, void **dYPlane, void **dUvPlane);

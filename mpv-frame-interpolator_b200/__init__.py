@@ -63,6 +63,9 @@ ABI = {
     "hr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hr_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "hr_debug_host_transfer_bytes": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "hr_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "hr_host_free": (C.c_int, [C.c_void_p]),
+    "hr_debug_host_pointer_kind": (C.c_int, [C.c_void_p]),
     "hr_get_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "hr_set_output_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hr_band_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -618,6 +621,8 @@ def load_ofc_library():
         ("downloadFrame", C.c_bool, [P, PP]),
         ("calculateOpticalFlow", C.c_bool, [P]),
         ("warpFrames", C.c_bool, [P, C.c_float, C.c_int]),
+        ("allocHostPlanes", C.c_void_p, [C.c_size_t]),
+        ("freeHostPlanes", None, [C.c_void_p, C.c_void_p]),
         ("hrControlParse", C.c_int, [C.c_char_p]),
         ("hrControlApply", C.c_int, [P, C.POINTER(HrControlState), C.c_int]),
         ("hrControlPoll", C.c_int, [C.c_int, P, C.POINTER(HrControlState)]),

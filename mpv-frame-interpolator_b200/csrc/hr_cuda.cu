@@ -2256,6 +2256,34 @@ extern "C" int hr_debug_host_transfer_bytes(unsigned long long *h2d, unsigned lo
     return 0;
 }
 
+/* Page-locked host memory for frames the filter allocates itself (its output image pool, patches/0004) */
+extern "C" int hr_host_alloc(void **out, size_t bytes) {
+    if (!out || bytes == 0) return 1;
+    *out = NULL;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = NULL;
+        return 1;
+    }
+    return 0;
+}
+extern "C" int hr_host_free(void *p) {
+    if (!p) return 0;
+    if (cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
+}
+extern "C" int hr_debug_host_pointer_kind(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeUnregistered ? 0 : a.type == cudaMemoryTypeHost ? 1 : 2;
+}
+
 /* Everything enqueued so far is complete when this returns (outputs in caller-owned device planes included);
  * seconds: device time from the start of the most recent hr_warp to now (= warpCalcTime of a frame that is not
  * downloaded, opticalFlowCalc.c:117-122). */

@@ -74,6 +74,16 @@ bool finishFrames(struct OpticalFlowCalc *ofc) {
     return 0;
 }
 
+unsigned char *allocHostPlanes(size_t bytes) {
+    void *p = NULL;
+    return hr_host_alloc(&p, bytes) ? NULL : (unsigned char *)p;
+}
+
+void freeHostPlanes(void *opaque, unsigned char *data) {
+    (void)opaque;
+    hr_host_free(data);
+}
+
 /* reference :236-253 (the struct itself belongs to the filter) */
 void freeOFC(struct OpticalFlowCalc *ofc) {
     if (ofc->impl) hr_destroy((HrContext *)ofc->impl);

@@ -11,6 +11,7 @@
 #define OPTICALFLOWCALC_H
 
 #include <stdbool.h>
+#include <stddef.h>
 
 #include "config.h"
 
@@ -56,5 +57,13 @@ bool warpFrames(struct OpticalFlowCalc *ofc, const float blendingScalar, const i
 bool updateFrameDevice(struct OpticalFlowCalc *ofc, unsigned char **devicePlanes);
 bool warpFramesToDevice(struct OpticalFlowCalc *ofc, const float blendingScalar, const int frameOutputMode, unsigned char **devicePlanes);
 bool finishFrames(struct OpticalFlowCalc *ofc);
+
+/* Page-locked host memory for the images the filter allocates itself (its output pool, reference vf_HopperRender.c:385,
+ * :699): downloadFrame then copies straight into the image instead of through a staging buffer. Shaped for
+ * mp_image_from_buffer (video/mp_image.h:139-142): allocHostPlanes returns NULL when no page-locked memory is to be had
+ * (the caller falls back to mp_image_alloc), freeHostPlanes has the signature of its free callback and may run on any
+ * thread. */
+unsigned char *allocHostPlanes(size_t bytes);
+void freeHostPlanes(void *opaque, unsigned char *data);
 
 #endif /* OPTICALFLOWCALC_H */

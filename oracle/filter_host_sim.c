@@ -60,6 +60,7 @@ void mp_image_unrefp(struct mp_image **p) {
     if (!img) return;
     if (--*img->refcount == 0) {
         free(img->storage);
+        if (img->bufferFree) img->bufferFree(img->bufferOpaque, img->buffer);
         if (img->deviceStorage) cudaFree(img->deviceStorage);
         free(img->refcount);
     }
@@ -70,17 +71,75 @@ void mp_image_copy_attributes(struct mp_image *dst, struct mp_image *src) {
     dst->pts = src->pts;
     dst->nominal_fps = src->nominal_fps;
 }
+/* NV12 / P010 layout as mp_image_layout() computes it (video/mp_image.c:59-98): strides aligned to stride_align, the
+ * chroma plane behind the luma plane, plane offsets aligned likewise */
+static int plane_layout(int fmt, int w, int h, int align, int *stride, int *uvOffset) {
+    if (w < 1 || h < 1 || align < 1) return -1;
+    *stride = (w * fmt_bps(fmt) + align - 1) / align * align;
+    *uvOffset = (*stride * h + align - 1) / align * align;
+    return *uvOffset + (*stride * ((h + 1) / 2) + align - 1) / align * align;
+}
+int mp_image_get_alloc_size(int imgfmt, int w, int h, int stride_align) {
+    int stride, uvOffset;
+    return plane_layout(imgfmt, w, h, stride_align, &stride, &uvOffset);
+}
+struct mp_image *mp_image_from_buffer(int imgfmt, int w, int h, int stride_align, unsigned char *buffer, int buffer_size, void *free_opaque,
+                                      void (*free_fn)(void *opaque, unsigned char *data)) {
+    int stride, uvOffset;
+    const int size = plane_layout(imgfmt, w, h, stride_align, &stride, &uvOffset);
+    const int shift = (int)(((size_t)buffer + stride_align - 1) / stride_align * stride_align - (size_t)buffer);
+    if (size < 0 || size > buffer_size || buffer_size - size < shift) return NULL;
+    struct mp_image *img = calloc(1, sizeof(*img));
+    img->w = w;
+    img->h = h;
+    img->imgfmt = imgfmt;
+    img->planes[0] = buffer + shift;
+    img->planes[1] = buffer + shift + uvOffset;
+    img->stride[0] = img->stride[1] = stride;
+    img->buffer = buffer;
+    img->bufferOpaque = free_opaque;
+    img->bufferFree = free_fn;
+    img->refcount = malloc(sizeof(int));
+    *img->refcount = 1;
+    return img;
+}
+struct mp_image *mp_image_alloc(int fmt, int w, int h) { return image_alloc(w, h, fmt); }
+
+/* The pool keeps the images it has handed out and hands an image out again once every other reference to it is gone
+ * (video/mp_image_pool.c:117-170, 204-237); new ones come from the allocator callback if one is set (:247-252). */
+#define SIM_POOL_MAX 64
 struct mp_image_pool {
-    int unused;
+    struct mp_image *images[SIM_POOL_MAX];
+    int n, allocated;
+    mp_image_allocator allocator;
+    void *allocatorData;
 };
+static int g_poolImagesAllocated;
 struct mp_image_pool *mp_image_pool_new(void *tparent) {
     (void)tparent;
     return calloc(1, sizeof(struct mp_image_pool));
 }
-struct mp_image *mp_image_pool_get(struct mp_image_pool *pool, int fmt, int w, int h) {
-    (void)pool;
-    return image_alloc(w, h, fmt);
+void mp_image_pool_set_allocator(struct mp_image_pool *pool, mp_image_allocator cb, void *cb_data) {
+    pool->allocator = cb;
+    pool->allocatorData = cb_data;
 }
+struct mp_image *mp_image_pool_get(struct mp_image_pool *pool, int fmt, int w, int h) {
+    for (int i = 0; i < pool->n; ++i) {
+        struct mp_image *img = pool->images[i];
+        if (*img->refcount == 1 && img->imgfmt == fmt && img->w == w && img->h == h) return mp_image_new_ref(img);
+    }
+    if (pool->n == SIM_POOL_MAX) return NULL;
+    struct mp_image *img = pool->allocator ? pool->allocator(pool->allocatorData, fmt, w, h) : image_alloc(w, h, fmt);
+    if (!img) return NULL;
+    pool->images[pool->n++] = img;
+    ++g_poolImagesAllocated;
+    return mp_image_new_ref(img);
+}
+void mp_image_pool_clear(struct mp_image_pool *pool) {
+    for (int i = 0; i < pool->n; ++i) mp_image_unrefp(&pool->images[i]); /* images still referenced outside live on */
+    pool->n = 0;
+}
+int hr_sim_pool_images_allocated(void) { return g_poolImagesAllocated; }
 
 /* ---- the slice of libavutil / mpv hardware-frame plumbing the IMGFMT_CUDA patch uses --------------------------- */
 static struct AVBufferRef g_deviceRef;          /* "the CUDA device": one per process here                 */
@@ -155,7 +214,6 @@ struct mp_image *mp_image_from_av_frame(AVFrame *src) {
     return img;
 }
 int hr_sim_device_images_allocated(void) { return g_deviceImagesAllocated; }
-void mp_image_pool_clear(struct mp_image_pool *pool) { (void)pool; }
 
 bool mp_frame_is_signaling(struct mp_frame frame) { return frame.type == MP_FRAME_EOF; }
 

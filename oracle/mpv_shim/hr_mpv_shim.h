@@ -67,7 +67,15 @@ struct mp_image {
     int *refcount;          /* shared between references                      */
     unsigned char *storage; /* freed with the last reference (host images)    */
     void *deviceStorage;    /* cudaFree()d with the last reference            */
+    unsigned char *buffer;  /* mp_image_from_buffer: handed to bufferFree with the last reference */
+    void *bufferOpaque;
+    void (*bufferFree)(void *opaque, unsigned char *data);
 };
+#define MP_IMAGE_BYTE_ALIGN 64 /* video/mp_image.h:35 */
+int mp_image_get_alloc_size(int imgfmt, int w, int h, int stride_align); /* video/mp_image.h:138 */
+struct mp_image *mp_image_from_buffer(int imgfmt, int w, int h, int stride_align, unsigned char *buffer, int buffer_size, void *free_opaque,
+                                      void (*free)(void *opaque, unsigned char *data)); /* video/mp_image.h:139-142 */
+struct mp_image *mp_image_alloc(int fmt, int w, int h);                  /* video/mp_image.h:144 */
 AVFrame *av_frame_alloc(void);
 void av_frame_free(AVFrame **frame);
 int av_hwframe_get_buffer(struct AVBufferRef *hwframe_ctx, AVFrame *frame, int flags);
@@ -82,6 +90,8 @@ struct mp_image_pool;
 struct mp_image_pool *mp_image_pool_new(void *tparent);
 struct mp_image *mp_image_pool_get(struct mp_image_pool *pool, int fmt, int w, int h);
 void mp_image_pool_clear(struct mp_image_pool *pool);
+typedef struct mp_image *(*mp_image_allocator)(void *data, int fmt, int w, int h);                    /* video/mp_image_pool.h:20 */
+void mp_image_pool_set_allocator(struct mp_image_pool *pool, mp_image_allocator cb, void *cb_data); /* video/mp_image_pool.h:21-22 */
 
 /* ---- frames ------------------------------------------------------------------------------------ */
 enum mp_frame_type { MP_FRAME_NONE = 0, MP_FRAME_VIDEO, MP_FRAME_AUDIO, MP_FRAME_PACKET, MP_FRAME_EOF };

@@ -5,7 +5,8 @@ scratch copy) on top of the CUDA path — the three rows SURVEY.md §8f leaves t
   N4  the headless control channel (patches/0002): the applet's integer codes from a FIFO named by $HOPPERRENDER_CONTROL
       and from `vf-command ... hr <code>`, with the radius pinned,
   N2  IMGFMT_CUDA in and out (patches/0003): source frames stay where a CUDA decoder left them, outputs are warped into
-      device images of a hardware pool; not one byte crosses PCIe (hr_debug_host_transfer_bytes stands still).
+      device images of a hardware pool; not one byte crosses PCIe (hr_debug_host_transfer_bytes stands still),
+  N1  the output pool in page-locked memory (patches/0004): downloadFrame copies straight into the image that travels on.
 
 oracle/filter_host_sim.c stands in for mpv's filter runtime and for the slice of libavutil's hardware-frame API the patch
 uses. Every output is compared with direct C-ABI calls at the blend positions of the pacing replay: identical."""
@@ -185,4 +186,57 @@ def test_imgfmt_cuda_in_and_out_without_host_copies(hr, synth, sim, pixfmt):
             assert np.array_equal(oy, ey) and np.array_equal(ouv, euv), "source frame %d t=%r" % (k, t)
             j += 1
     assert j == len(got)
+    sim.hr_sim_destroy(s)
+
+
+@pytest.mark.parametrize("pixfmt,w,h", [(0, 1280, 720), (1, 960, 562)])
+def test_output_pool_is_page_locked(hr, synth, sim, pixfmt, w, h):
+    """patches/0004: the filter's output images (reference vf_HopperRender.c:385) come from hr_host_alloc through
+    mp_image_pool_set_allocator / mp_image_from_buffer, are recycled by the pool, and hold the frames the direct calls
+    give (960 x 562 P010: an odd number of chroma rows to lay out behind the luma plane)."""
+    from hopperrender_b200 import pacing
+    fps = 24.0
+    lib = hr.load_library()
+    sim.hr_sim_pool_images_allocated.restype = C.c_int
+    ndt = np.uint16 if pixfmt else np.uint8
+    bps = 2 if pixfmt else 1
+    clip = synth.MovingTextureClip(w, h, pixfmt=pixfmt)
+    s = sim.hr_sim_create(2, 60.0)
+    before = sim.hr_sim_pool_images_allocated()
+    stride = (w * bps + 63) // 64 * 64 // bps                                  # the pool's strides are 64-byte aligned (video/mp_image.h:35)
+    direct = hr.HrCuda(h, stride, w, pixfmt)
+    pacer = pacing.Pacer(fps, 60.0)
+    checked = 0
+    for k in range(6):
+        y, uv = clip.frame(k)
+        assert sim.hr_sim_push_fmt(s, C.c_void_p(y.ctypes.data), C.c_void_p(uv.ctypes.data), w, h, IMGFMT_P010 if pixfmt else IMGFMT_NV12, k / fps, fps) >= 0
+        ys, uvs = np.zeros((h, stride), ndt), np.zeros((h // 2, stride), ndt)
+        ys[:, :w], uvs[:, :w] = y, uv
+        direct.update_frame(ys, uvs)
+        ts = pacer.next_source_frame()
+        if k:
+            direct.calc_flow(5)
+        n = 0
+        while True:
+            fmt, sub, p0, p1, pitch, pts = C.c_int(), C.c_int(), C.c_void_p(), C.c_void_p(), C.c_int(), C.c_double()
+            if sim.hr_sim_pop_image(s, C.byref(fmt), C.byref(sub), C.byref(p0), C.byref(p1), C.byref(pitch), C.byref(pts)):
+                break
+            n += 1
+            if k == 0:
+                continue                                                        # the first source frame passes as it is
+            assert lib.hr_debug_host_pointer_kind(p0) == 1 and lib.hr_debug_host_pointer_kind(p1) == 1, "output image is not page-locked"
+            assert pitch.value == stride * bps and p0.value % 64 == 0 and p1.value % 64 == 0
+            oy = np.ctypeslib.as_array(C.cast(p0, C.POINTER(C.c_uint16 if pixfmt else C.c_uint8)), (h, stride))
+            ouv = np.ctypeslib.as_array(C.cast(p1, C.POINTER(C.c_uint16 if pixfmt else C.c_uint8)), (h // 2, stride))
+            direct.warp(ts[n - 1], 2)
+            ey, euv, _ = direct.download()
+            assert np.array_equal(oy[:, :w], ey[:, :w]) and np.array_equal(ouv[:, :w], euv[:, :w]), "source frame %d t=%r" % (k, ts[n - 1])
+            checked += 1
+        if k:
+            assert n == len(ts)
+    assert checked == 3 + 2 + 3 + 2 + 3
+    # thirteen outputs from at most four images: the three of one source frame wait in the harness's queue and one more is
+    # held by hr_sim_pop_image while the filter asks for the next
+    assert 1 <= sim.hr_sim_pool_images_allocated() - before <= 4
+    sim.hr_sim_pop_image(s, None, None, None, None, None, None)                # drop the image the harness still holds
     sim.hr_sim_destroy(s)
