@@ -47,11 +47,12 @@ WORKLOADS = {
     # name: (width, height, pixfmt, source fps, display fps, mode)
     "1080p-nv12-24to60": (1920, 1080, 0, 24.0, 60.0, 2),
     "4k-nv12-24to60": (3840, 2160, 0, 24.0, 60.0, 2),
+    "4k-p010-24to60": (3840, 2160, 1, 24.0, 60.0, 2),
     "4k-p010-24to144": (3840, 2160, 1, 24.0, 144.0, 2),
     "4k-p010-24to144-hsv": (3840, 2160, 1, 24.0, 144.0, 3),
     "8k-p010-24to60": (7680, 4320, 1, 24.0, 60.0, 2),
 }
-EXTRA_CONFIGS = ["4k-p010-24to144", "4k-p010-24to144-hsv", "8k-p010-24to60"]
+EXTRA_CONFIGS = ["4k-p010-24to60", "4k-p010-24to144", "4k-p010-24to144-hsv", "8k-p010-24to60"]
 L2_BYTES = 126 * 1024 * 1024
 MIN_REGION_S = 0.5
 KERNEL_OF = {"search": "flow_search", "warp": "warp_fast_kernel", "pack": "pack_frame16_kernel"}
