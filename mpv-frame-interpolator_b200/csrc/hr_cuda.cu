@@ -965,9 +965,13 @@ struct StageTransfer {
     ~StageTransfer() { crew->finish(); }
 };
 /* host -> device: the crew fills the ring chunk by chunk, the copy engine follows it; everything is enqueued on return */
-static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t bytes) {
+/* blockBytes != 0: a pitched picture on both sides — bytes / blockBytes blocks of blockBytes every `pitch` bytes, back
+ * to back in the ring, one pitched copy per chunk (blockBytes <= the chunk size) */
+static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t bytes, size_t blockBytes = 0, size_t pitch = 0) {
     const size_t ch = ctx->stageChunk;
-    ctx->plan->build(bytes, ch, true);
+    if (blockBytes == pitch) blockBytes = pitch = 0; /* blocks that touch are one range */
+    if (blockBytes) ctx->plan->build_blocks(bytes / blockBytes, blockBytes, ch, true);
+    else ctx->plan->build(bytes, ch, true);
     const size_t nch = ctx->plan->n;
     const unsigned base = ctx->stageNext;
     ctx->stageNext += (unsigned)nch;
@@ -976,7 +980,7 @@ static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t
         const int slot = (base + released) % HR_STAGE_SLOTS;
         if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
     }
-    ctx->crew->begin(true, (uint8_t *)hSrc, ctx->stage, ch, base, ctx->plan);
+    ctx->crew->begin(true, (uint8_t *)hSrc, ctx->stage, ch, base, ctx->plan, blockBytes, pitch);
     StageTransfer guard{ctx->crew};
     ctx->crew->release(released);
     for (size_t c = 0; c < nch; ++c) {
@@ -990,7 +994,8 @@ static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t
         cudaGetLastError(); /* cudaErrorNotReady of the queries */
         const int slot = (base + c) % HR_STAGE_SLOTS;
         const size_t o = ctx->plan->off[c], len = ctx->plan->len[c];
-        CU(cudaMemcpyAsync(dDst + o, ctx->stage + slot * ch, len, cudaMemcpyHostToDevice, ctx->stream));
+        if (!blockBytes) CU(cudaMemcpyAsync(dDst + o, ctx->stage + slot * ch, len, cudaMemcpyHostToDevice, ctx->stream));
+        else CU(cudaMemcpy2DAsync(dDst + (o / blockBytes) * pitch, pitch, ctx->stage + slot * ch, blockBytes, blockBytes, len / blockBytes, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
         ctx->stageBusy[slot] = 1;
         if (released <= c + 1 && released < nch) { /* the crew is about to run out of slots: wait for the oldest chunk in flight */
@@ -1072,7 +1077,38 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
         staged = stage_ready(ctx);
         if (staged < 0) return 1;
     }
-    if (staged) {
+    if (staged && ahead && ctx->splitUpload && ctx->s >= 1 && (size_t)((1 << ctx->s) - 1) * ctx->W * ctx->bps <= ctx->stageChunk) {
+        /* lattice rows first, as below for pinned planes: the crew gathers them into the ring, the copy engine scatters
+         * them with pitched copies, the search starts behind them and runs while the other rows follow */
+        const size_t rowBytes = (size_t)ctx->W * ctx->bps;
+        const uint8_t *src[2] = {(const uint8_t *)yPlane, (const uint8_t *)uvPlane};
+        uint8_t *dpl[2] = {dst, dst + ylen};
+        const int rows[2] = {ctx->H, ctx->H / 2}, stride[2] = {1 << ctx->s, (1 << ctx->s) / 2 > 1 ? (1 << ctx->s) / 2 : 1};
+        for (int pl = 0; pl < 2; ++pl) {
+            const int groups = (rows[pl] + stride[pl] - 1) / stride[pl];
+            if (staged_h2d(ctx, dpl[pl], src[pl], (size_t)groups * rowBytes, rowBytes, stride[pl] * rowBytes)) return 1;
+        }
+        CU(cudaEventRecord(ctx->evLattice, ctx->stream));
+        ctx->latticeFirst = 1;
+        cudaStream_t st;
+        if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
+        CU(cudaEventRecord(ctx->evFlowEnd, st));
+        ctx->specFlow = ctx->lastFlow;
+        ctx->specFlow.frames = ctx->framesSeen;
+        for (int pl = 0; pl < 2; ++pl) {
+            const int full = rows[pl] / stride[pl], tail = rows[pl] - full * stride[pl];
+            if (stride[pl] > 1 && full > 0 &&
+                staged_h2d(ctx, dpl[pl] + rowBytes, src[pl] + rowBytes, (size_t)full * (stride[pl] - 1) * rowBytes, (stride[pl] - 1) * rowBytes, stride[pl] * rowBytes))
+                return 1;
+            if (tail > 1) {
+                const size_t o = ((size_t)full * stride[pl] + 1) * rowBytes;
+                if (staged_h2d(ctx, dpl[pl] + o, src[pl] + o, (size_t)(tail - 1) * rowBytes)) return 1;
+            }
+        }
+        g_h2dBytes += ylen + uvlen;
+        if (launch_pack(ctx)) return 1;
+        ctx->latticeFirst = 0;
+    } else if (staged) {
         if ((const uint8_t *)uvPlane == (const uint8_t *)yPlane + ylen) {
             if (staged_h2d(ctx, dst, (const uint8_t *)yPlane, ylen + uvlen)) return 1;
         } else {

@@ -53,6 +53,28 @@ struct HrStagePlan {
             o += len[i];
         }
     }
+    /* The same for a transfer made of nBlocks blocks of blockBytes each (rows of a pitched picture, hr_cuda.cu: the
+     * lattice rows of a frame go first): every chunk is a whole number of blocks, so that the copy engine can move it
+     * with one pitched copy. blockBytes <= chunk. */
+    void build_blocks(size_t nBlocks, size_t blockBytes, size_t chunk, bool shortFirst) {
+        len.clear();
+        const size_t full = chunk / blockBytes;
+        size_t left = nBlocks, c = full / 8 ? full / 8 : 1;
+        while (left) {
+            const size_t l = left < c ? left : c;
+            len.push_back(l * blockBytes);
+            left -= l;
+            if (c < full) c = c * 2 < full ? c * 2 : full;
+        }
+        if (!shortFirst) std::reverse(len.begin(), len.end());
+        n = len.size();
+        off.resize(n);
+        size_t o = 0;
+        for (size_t i = 0; i < n; ++i) {
+            off[i] = o;
+            o += len[i];
+        }
+    }
 };
 
 /* One participant's share of a copy. Neither side is read again by this core (the ring is read by the copy engine, the
@@ -109,10 +131,14 @@ public:
     int threads() const { return n_; }
 
     /* toRing: chunk c of the plan, host + off[c] -> ring slot (firstSlot + c) % HR_STAGE_SLOTS; otherwise the other way
-     * round. The plan stays the caller's and must not change before finish(). */
-    void begin(bool toRing, uint8_t *host, uint8_t *ring, size_t chunk, unsigned firstSlot, const HrStagePlan *plan) {
+     * round. The plan stays the caller's and must not change before finish(). With blockBytes / hostPitch the host side is
+     * a pitched picture (blocks of blockBytes every hostPitch bytes) and the ring holds the blocks back to back. */
+    void begin(bool toRing, uint8_t *host, uint8_t *ring, size_t chunk, unsigned firstSlot, const HrStagePlan *plan, size_t blockBytes = 0,
+               size_t hostPitch = 0) {
         toRing_ = toRing;
         host_ = host;
+        blockBytes_ = blockBytes; /* 0: the host range is contiguous; otherwise byte x of the transfer lives at */
+        hostPitch_ = hostPitch;   /* host + (x / blockBytes) * hostPitch + x % blockBytes                        */
         ring_ = ring;
         chunk_ = chunk;
         firstSlot_ = firstSlot;
@@ -172,10 +198,21 @@ private:
                 const size_t o = plan_->off[c], len = plan_->len[c];
                 const size_t per = (((len + n_ - 1) / n_) + 4095) & ~(size_t)4095, so = (size_t)id * per;
                 if (so < len) {
-                    uint8_t *h = host_ + o + so, *r = ring_ + (size_t)((firstSlot_ + c) % HR_STAGE_SLOTS) * chunk_ + so;
-                    const size_t m = len - so < per ? len - so : per;
-                    if (toRing_) hr_stage_copy(r, h, m);
-                    else hr_stage_copy(h, r, m);
+                    uint8_t *r = ring_ + (size_t)((firstSlot_ + c) % HR_STAGE_SLOTS) * chunk_ + so;
+                    size_t m = len - so < per ? len - so : per;
+                    if (!blockBytes_) {
+                        uint8_t *h = host_ + o + so;
+                        if (toRing_) hr_stage_copy(r, h, m);
+                        else hr_stage_copy(h, r, m);
+                    } else {
+                        for (size_t x = o + so; m;) { /* block by block */
+                            const size_t w = x % blockBytes_, l = blockBytes_ - w < m ? blockBytes_ - w : m;
+                            uint8_t *h = host_ + (x / blockBytes_) * hostPitch_ + w;
+                            if (toRing_) hr_stage_copy(r, h, l);
+                            else hr_stage_copy(h, r, l);
+                            r += l, x += l, m -= l;
+                        }
+                    }
                 }
                 progress_[id].v.store(c + 1, std::memory_order_release);
             }
@@ -196,7 +233,7 @@ private:
     Progress progress_[16];
     bool toRing_ = true;
     uint8_t *host_ = nullptr, *ring_ = nullptr;
-    size_t chunk_ = 0, nch_ = 0;
+    size_t chunk_ = 0, nch_ = 0, blockBytes_ = 0, hostPitch_ = 0;
     const HrStagePlan *plan_ = nullptr;
     unsigned firstSlot_ = 0;
 };

@@ -219,19 +219,30 @@ def test_many_frames_per_call(hr, synth):
     b.close()
 
 
+@pytest.mark.parametrize("road", ["pinned", "pageable", "pageable-64k"])
 @pytest.mark.parametrize("w,h,stride,pixfmt", [(1000, 562, 1024, 0), (854, 480, 896, 0), (1918, 1080, 1920, 1), (3840, 2160, 3840, 0), (7680, 4320, 7680, 1)])
-def test_lattice_rows_first_upload(hr, synth, w, h, stride, pixfmt):
+def test_lattice_rows_first_upload(hr, synth, monkeypatch, w, h, stride, pixfmt, road):
     """updateFrame through the host layer uploads the rows the search reads first (pitched copies) and the rest behind
     them while the search runs: ragged heights (a partial last row group), resolution scalars 1 to 4, NV12 and P010, the
-    frame in device memory and everything computed from it equal to a plain context's."""
+    frame in device memory and everything computed from it equal to a plain context's. Pinned planes go row group by
+    row group straight to the copy engine; pageable ones are gathered into the pinned ring by the copying threads first
+    (csrc/hr_staging.h, with 64 KB chunks every part of a frame goes round the eight slots several times — or, where a row
+    group is larger than a chunk, the frame goes up in one piece)."""
+    import torch
+    if road == "pageable-64k":
+        monkeypatch.setenv("HR_STAGE_CHUNK_KB", "64")
     clip = synth.MovingTextureClip(w, h, stride=stride, pixfmt=pixfmt)
     dt = np.uint16 if pixfmt else np.uint8
     plain = hr.HrCuda(h, stride, w, pixfmt)
     ofc = hr.OpticalFlowCalc()
     assert not hr.initOpticalFlowCalc(ofc, h, stride, w, pixfmt)
+    lib = hr.load_library()
     for k in range(4):
         f = clip.frame(k)
         plain.update_frame(*f)
+        if road == "pinned":
+            f = tuple(torch.from_numpy(p.view(np.int16) if pixfmt else p).pin_memory() for p in f)
+        assert lib.hr_debug_host_pointer_kind(hr._ptr(f[0])) == (1 if road == "pinned" else 0)
         assert not hr.updateFrame(ofc, list(f))
         if k == 0:
             continue
