@@ -112,6 +112,7 @@ struct HrContext {
     cudaEvent_t evLattice;                     /* main stream: the rows of the newest frame the search reads (its lattice rows) are there */
     int latticeFirst;                          /* this frame was uploaded lattice rows first: the search waits for evLattice, not evIn */
     int splitUpload;                           /* developer knob HR_SPLIT_UPLOAD=0: one transfer per frame, always */
+    int stageSplit;                            /* developer knob HR_STAGE_SPLIT=1: pageable planes go up lattice rows first as well (measured: no gain) */
     cudaEvent_t evPack[HR_PACK_BUFS];                     /* by packed-buffer identity: its pack kernel is done           */
     cudaEvent_t packRead[HR_PACK_BUFS];                   /* by packed-buffer identity: the search that read it last (not owned) */
     cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
@@ -488,6 +489,8 @@ static int create_impl(HrContext *ctx) {
     ctx->searchGen = (sg && sg[0] >= '1' && sg[0] <= '3') ? sg[0] - '0' : 0;
     const char *su = getenv("HR_SPLIT_UPLOAD"); /* developer knob: 0 = never upload a frame lattice rows first */
     ctx->splitUpload = !(su && su[0] == '0');
+    const char *stsp = getenv("HR_STAGE_SPLIT");
+    ctx->stageSplit = stsp && stsp[0] == '1';
     const char *stt = getenv("HR_STAGE_THREADS"), *stc = getenv("HR_STAGE_CHUNK_KB"); /* hr_staging.h */
     ctx->stageThreads = stt ? atoi(stt) : 4;
     if (ctx->stageThreads > 16) ctx->stageThreads = 16;
@@ -1077,9 +1080,12 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
         staged = stage_ready(ctx);
         if (staged < 0) return 1;
     }
-    if (staged && ahead && ctx->splitUpload && ctx->s >= 1 && (size_t)((1 << ctx->s) - 1) * ctx->W * ctx->bps <= ctx->stageChunk) {
+    if (staged && ahead && ctx->splitUpload && ctx->stageSplit && ctx->s >= 1 && (size_t)((1 << ctx->s) - 1) * ctx->W * ctx->bps <= ctx->stageChunk) {
         /* lattice rows first, as below for pinned planes: the crew gathers them into the ring, the copy engine scatters
-         * them with pitched copies, the search starts behind them and runs while the other rows follow */
+         * them with pitched copies, the search starts behind them and runs while the other rows follow. Behind a knob:
+         * measured at 1080p / 4K / 8K it gives nothing (5.4 k against 5.1-5.4 k frames/s with pageable planes, 7.7 k
+         * against 7.7-7.8 k with the page-locked output pool) — what the search gains by starting early the four
+         * transfers lose where one ends and the next has to fill its first chunk before the copy engine can go on. */
         const size_t rowBytes = (size_t)ctx->W * ctx->bps;
         const uint8_t *src[2] = {(const uint8_t *)yPlane, (const uint8_t *)uvPlane};
         uint8_t *dpl[2] = {dst, dst + ylen};
