@@ -112,7 +112,7 @@ struct HrContext {
     cudaEvent_t evLattice;                     /* main stream: the rows of the newest frame the search reads (its lattice rows) are there */
     int latticeFirst;                          /* this frame was uploaded lattice rows first: the search waits for evLattice, not evIn */
     int splitUpload;                           /* developer knob HR_SPLIT_UPLOAD=0: one transfer per frame, always */
-    int stageSplit;                            /* developer knob HR_STAGE_SPLIT=1: pageable planes go up lattice rows first as well (measured: no gain) */
+    int stageSplit;                            /* developer knob HR_STAGE_SPLIT=0: pageable planes go up in one piece instead of lattice rows first */
     cudaEvent_t evPack[HR_PACK_BUFS];                     /* by packed-buffer identity: its pack kernel is done           */
     cudaEvent_t packRead[HR_PACK_BUFS];                   /* by packed-buffer identity: the search that read it last (not owned) */
     cudaEvent_t evSearch[HR_FLOW_BUFS];        /* by flow buffer: the search that filled it is done            */
@@ -490,7 +490,7 @@ static int create_impl(HrContext *ctx) {
     const char *su = getenv("HR_SPLIT_UPLOAD"); /* developer knob: 0 = never upload a frame lattice rows first */
     ctx->splitUpload = !(su && su[0] == '0');
     const char *stsp = getenv("HR_STAGE_SPLIT");
-    ctx->stageSplit = stsp && stsp[0] == '1';
+    ctx->stageSplit = !(stsp && stsp[0] == '0');
     const char *stt = getenv("HR_STAGE_THREADS"), *stc = getenv("HR_STAGE_CHUNK_KB"); /* hr_staging.h */
     ctx->stageThreads = stt ? atoi(stt) : 4;
     if (ctx->stageThreads > 16) ctx->stageThreads = 16;
@@ -1008,6 +1008,48 @@ static int staged_h2d(HrContext *ctx, uint8_t *dDst, const uint8_t *hSrc, size_t
     }
     return 0;
 }
+/* The same for an upload of several segments in ONE run of the ring (no seam between them: the crew goes on filling slots
+ * while the copy engine works off the previous segment). When the last chunk of segment hookAfter has been handed to the
+ * copy engine, hook(ctx) runs on this thread — the crew keeps copying into the slots already released. */
+static int staged_h2d_segments(HrContext *ctx, const HrStageSeg *segs, int nSegs, int hookAfter, int (*hook)(HrContext *)) {
+    const size_t ch = ctx->stageChunk;
+    ctx->plan->build_segments(segs, nSegs, ch);
+    const size_t nch = ctx->plan->n;
+    const unsigned base = ctx->stageNext;
+    ctx->stageNext += (unsigned)nch;
+    size_t released = 0;
+    for (; released < nch && released < HR_STAGE_SLOTS; ++released) {
+        const int slot = (base + released) % HR_STAGE_SLOTS;
+        if (ctx->stageBusy[slot]) CU(cudaEventSynchronize(ctx->evStage[slot]));
+    }
+    ctx->crew->begin(true, NULL, ctx->stage, ch, base, ctx->plan);
+    StageTransfer guard{ctx->crew};
+    ctx->crew->release(released);
+    for (size_t c = 0; c < nch; ++c) {
+        while (!ctx->crew->chunk_done(c)) {
+            if (released < nch && released < c + HR_STAGE_SLOTS && cudaEventQuery(ctx->evStage[(base + released) % HR_STAGE_SLOTS]) == cudaSuccess)
+                ctx->crew->release(++released);
+            else
+                HrCopyCrew::relax();
+        }
+        cudaGetLastError(); /* cudaErrorNotReady of the queries */
+        const int slot = (base + c) % HR_STAGE_SLOTS;
+        const HrStageSeg &sg = segs[ctx->plan->seg[c]];
+        const size_t so = ctx->plan->segOff[c], len = ctx->plan->len[c];
+        if (!sg.blockBytes) CU(cudaMemcpyAsync(sg.dev + so, ctx->stage + slot * ch, len, cudaMemcpyHostToDevice, ctx->stream));
+        else CU(cudaMemcpy2DAsync(sg.dev + (so / sg.blockBytes) * sg.pitch, sg.pitch, ctx->stage + slot * ch, sg.blockBytes, sg.blockBytes, len / sg.blockBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(ctx->evStage[slot], ctx->stream));
+        ctx->stageBusy[slot] = 1;
+        if (hook && ctx->plan->seg[c] == hookAfter && (c + 1 == nch || ctx->plan->seg[c + 1] != hookAfter)) {
+            if (hook(ctx)) return 1;
+        }
+        if (released <= c + 1 && released < nch) { /* the crew is about to run out of slots: wait for the oldest chunk in flight */
+            CU(cudaEventSynchronize(ctx->evStage[(base + released) % HR_STAGE_SLOTS]));
+            ctx->crew->release(++released);
+        }
+    }
+    return 0;
+}
 /* device -> host in two halves, so that the caller can put work between them: the first chunks are handed to the copy
  * engine and the crew is told where they will land, ... */
 struct StageDown {
@@ -1082,35 +1124,41 @@ extern "C" int hr_update_frame(HrContext *ctx, const void *yPlane, const void *u
     }
     if (staged && ahead && ctx->splitUpload && ctx->stageSplit && ctx->s >= 1 && (size_t)((1 << ctx->s) - 1) * ctx->W * ctx->bps <= ctx->stageChunk) {
         /* lattice rows first, as below for pinned planes: the crew gathers them into the ring, the copy engine scatters
-         * them with pitched copies, the search starts behind them and runs while the other rows follow. Behind a knob:
-         * measured at 1080p / 4K / 8K it gives nothing (5.4 k against 5.1-5.4 k frames/s with pageable planes, 7.7 k
-         * against 7.7-7.8 k with the page-locked output pool) — what the search gains by starting early the four
-         * transfers lose where one ends and the next has to fill its first chunk before the copy engine can go on. */
+         * them with pitched copies, the search starts behind them and runs while the other rows follow — all of it one
+         * run of the ring (staged_h2d_segments; HR_STAGE_SPLIT=0 restores one piece per frame). */
         const size_t rowBytes = (size_t)ctx->W * ctx->bps;
-        const uint8_t *src[2] = {(const uint8_t *)yPlane, (const uint8_t *)uvPlane};
+        uint8_t *src[2] = {(uint8_t *)yPlane, (uint8_t *)uvPlane};
         uint8_t *dpl[2] = {dst, dst + ylen};
         const int rows[2] = {ctx->H, ctx->H / 2}, stride[2] = {1 << ctx->s, (1 << ctx->s) / 2 > 1 ? (1 << ctx->s) / 2 : 1};
-        for (int pl = 0; pl < 2; ++pl) {
-            const int groups = (rows[pl] + stride[pl] - 1) / stride[pl];
-            if (staged_h2d(ctx, dpl[pl], src[pl], (size_t)groups * rowBytes, rowBytes, stride[pl] * rowBytes)) return 1;
+        HrStageSeg segs[6];
+        int n = 0;
+        for (int pl = 0; pl < 2; ++pl) { /* first row of every group of `stride` rows */
+            const size_t groups = (size_t)(rows[pl] + stride[pl] - 1) / stride[pl];
+            if (stride[pl] > 1) segs[n++] = HrStageSeg{src[pl], dpl[pl], groups * rowBytes, rowBytes, stride[pl] * rowBytes};
+            else segs[n++] = HrStageSeg{src[pl], dpl[pl], groups * rowBytes, 0, 0};
         }
-        CU(cudaEventRecord(ctx->evLattice, ctx->stream));
-        ctx->latticeFirst = 1;
-        cudaStream_t st;
-        if (launch_flow(ctx, ctx->lastFlow.R, ctx->lastFlow.dS, ctx->lastFlow.nS, &st)) return 1;
-        CU(cudaEventRecord(ctx->evFlowEnd, st));
-        ctx->specFlow = ctx->lastFlow;
-        ctx->specFlow.frames = ctx->framesSeen;
-        for (int pl = 0; pl < 2; ++pl) {
-            const int full = rows[pl] / stride[pl], tail = rows[pl] - full * stride[pl];
-            if (stride[pl] > 1 && full > 0 &&
-                staged_h2d(ctx, dpl[pl] + rowBytes, src[pl] + rowBytes, (size_t)full * (stride[pl] - 1) * rowBytes, (stride[pl] - 1) * rowBytes, stride[pl] * rowBytes))
-                return 1;
+        const int latticeSegs = n;
+        for (int pl = 0; pl < 2; ++pl) { /* the other rows of every full group, then what is left of a partial last group */
+            const size_t full = (size_t)rows[pl] / stride[pl], tail = rows[pl] - full * stride[pl];
+            if (stride[pl] > 1 && full > 0)
+                segs[n++] = HrStageSeg{src[pl] + rowBytes, dpl[pl] + rowBytes, full * (stride[pl] - 1) * rowBytes, stride[pl] > 2 ? (stride[pl] - 1) * rowBytes : rowBytes,
+                                       stride[pl] * rowBytes};
             if (tail > 1) {
-                const size_t o = ((size_t)full * stride[pl] + 1) * rowBytes;
-                if (staged_h2d(ctx, dpl[pl] + o, src[pl] + o, (size_t)(tail - 1) * rowBytes)) return 1;
+                const size_t o = (full * stride[pl] + 1) * rowBytes;
+                segs[n++] = HrStageSeg{src[pl] + o, dpl[pl] + o, (tail - 1) * rowBytes, 0, 0};
             }
         }
+        auto latticeArrived = [](HrContext *c) -> int {
+            if (cudaEventRecord(c->evLattice, c->stream) != cudaSuccess) return fail(c, "hr_update_frame: %s", cudaGetErrorString(cudaGetLastError()));
+            c->latticeFirst = 1;
+            cudaStream_t st;
+            if (launch_flow(c, c->lastFlow.R, c->lastFlow.dS, c->lastFlow.nS, &st)) return 1;
+            if (cudaEventRecord(c->evFlowEnd, st) != cudaSuccess) return fail(c, "hr_update_frame: %s", cudaGetErrorString(cudaGetLastError()));
+            c->specFlow = c->lastFlow;
+            c->specFlow.frames = c->framesSeen;
+            return 0;
+        };
+        if (staged_h2d_segments(ctx, segs, n, latticeSegs - 1, latticeArrived)) return 1;
         g_h2dBytes += ylen + uvlen;
         if (launch_pack(ctx)) return 1;
         ctx->latticeFirst = 0;

@@ -32,10 +32,22 @@
 /* The chunks of one transfer: full-size ones, and short ones at the end that nothing overlaps — the first chunk of an
  * upload (the copy engine has nothing to move until the crew has filled it) and the last chunk of a download (the crew
  * has to drain it after the copy engine has gone quiet): chunk / 8, / 4, / 2 before (after) the full-size ones. */
+/* One piece of a transfer made of several: `bytes` bytes between host and dev, contiguous (blockBytes == 0) or blocks of
+ * blockBytes every `pitch` bytes on both sides. */
+struct HrStageSeg {
+    uint8_t *host, *dev;
+    size_t bytes, blockBytes, pitch;
+};
+
 struct HrStagePlan {
     std::vector<size_t> off, len;
     size_t n = 0;
+    /* transfers of several segments only (build_segments): the segment of every chunk and where in it the chunk starts */
+    std::vector<HrStageSeg> segs;
+    std::vector<int> seg;
+    std::vector<size_t> segOff;
     void build(size_t bytes, size_t chunk, bool shortFirst) {
+        segs.clear();
         len.clear();
         size_t left = bytes, c = chunk / 8 < 65536 ? (chunk < 65536 ? chunk : 65536) : chunk / 8;
         while (left) {
@@ -57,6 +69,7 @@ struct HrStagePlan {
      * lattice rows of a frame go first): every chunk is a whole number of blocks, so that the copy engine can move it
      * with one pitched copy. blockBytes <= chunk. */
     void build_blocks(size_t nBlocks, size_t blockBytes, size_t chunk, bool shortFirst) {
+        segs.clear();
         len.clear();
         const size_t full = chunk / blockBytes;
         size_t left = nBlocks, c = full / 8 ? full / 8 : 1;
@@ -67,6 +80,36 @@ struct HrStagePlan {
             if (c < full) c = c * 2 < full ? c * 2 : full;
         }
         if (!shortFirst) std::reverse(len.begin(), len.end());
+        n = len.size();
+        off.resize(n);
+        size_t o = 0;
+        for (size_t i = 0; i < n; ++i) {
+            off[i] = o;
+            o += len[i];
+        }
+    }
+    /* An upload of several segments in one go (the lattice rows of a frame, then the rows between them): the ring keeps
+     * flowing across the seams, only the very first chunks are short. A chunk never spans two segments; in a segment of
+     * blocks it is a whole number of them (blockBytes <= chunk). */
+    void build_segments(const HrStageSeg *s, int nSegs, size_t chunk) {
+        segs.assign(s, s + nSegs);
+        len.clear();
+        seg.clear();
+        segOff.clear();
+        size_t ramp = chunk / 8 < 65536 ? (chunk < 65536 ? chunk : 65536) : chunk / 8; /* bytes, as in build() */
+        for (int i = 0; i < nSegs; ++i) {
+            const size_t bb = s[i].blockBytes;
+            for (size_t done = 0; done < s[i].bytes;) {
+                size_t l = ramp;
+                if (bb) l = l / bb ? l / bb * bb : bb;
+                if (l > s[i].bytes - done) l = s[i].bytes - done;
+                len.push_back(l);
+                seg.push_back(i);
+                segOff.push_back(done);
+                done += l;
+                if (ramp < chunk) ramp = ramp * 2 < chunk ? ramp * 2 : chunk;
+            }
+        }
         n = len.size();
         off.resize(n);
         size_t o = 0;
@@ -200,14 +243,22 @@ private:
                 if (so < len) {
                     uint8_t *r = ring_ + (size_t)((firstSlot_ + c) % HR_STAGE_SLOTS) * chunk_ + so;
                     size_t m = len - so < per ? len - so : per;
-                    if (!blockBytes_) {
-                        uint8_t *h = host_ + o + so;
+                    /* where the chunk's bytes live on the host: one range / one pitched picture for the whole transfer,
+                     * or the chunk's segment */
+                    uint8_t *hb = host_;
+                    size_t x = o + so, bb = blockBytes_, pt = hostPitch_;
+                    if (!plan_->segs.empty()) {
+                        const HrStageSeg &sg = plan_->segs[plan_->seg[c]];
+                        hb = sg.host, x = plan_->segOff[c] + so, bb = sg.blockBytes, pt = sg.pitch;
+                    }
+                    if (!bb) {
+                        uint8_t *h = hb + x;
                         if (toRing_) hr_stage_copy(r, h, m);
                         else hr_stage_copy(h, r, m);
                     } else {
-                        for (size_t x = o + so; m;) { /* block by block */
-                            const size_t w = x % blockBytes_, l = blockBytes_ - w < m ? blockBytes_ - w : m;
-                            uint8_t *h = host_ + (x / blockBytes_) * hostPitch_ + w;
+                        while (m) { /* block by block */
+                            const size_t w = x % bb, l = bb - w < m ? bb - w : m;
+                            uint8_t *h = hb + (x / bb) * pt + w;
                             if (toRing_) hr_stage_copy(r, h, l);
                             else hr_stage_copy(h, r, l);
                             r += l, x += l, m -= l;

@@ -225,14 +225,12 @@ def test_lattice_rows_first_upload(hr, synth, monkeypatch, w, h, stride, pixfmt,
     """updateFrame through the host layer uploads the rows the search reads first (pitched copies) and the rest behind
     them while the search runs: ragged heights (a partial last row group), resolution scalars 1 to 4, NV12 and P010, the
     frame in device memory and everything computed from it equal to a plain context's. Pinned planes go row group by
-    row group straight to the copy engine; pageable ones (with HR_STAGE_SPLIT=1) are gathered into the pinned ring by the copying threads first
+    row group straight to the copy engine; pageable ones are gathered into the pinned ring by the copying threads first
     (csrc/hr_staging.h, with 64 KB chunks every part of a frame goes round the eight slots several times — or, where a row
     group is larger than a chunk, the frame goes up in one piece)."""
     import torch
     if road == "pageable-64k":
         monkeypatch.setenv("HR_STAGE_CHUNK_KB", "64")
-    if road != "pinned":
-        monkeypatch.setenv("HR_STAGE_SPLIT", "1")       # off by default (no gain measured), kept correct
     clip = synth.MovingTextureClip(w, h, stride=stride, pixfmt=pixfmt)
     dt = np.uint16 if pixfmt else np.uint8
     plain = hr.HrCuda(h, stride, w, pixfmt)
